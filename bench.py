@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""
+bench.py -- GraphEm layout-iteration benchmark (BASELINE.json metric:
+"layout iters/sec & edge-updates/s, 1M-vertex BA graph, 1/2/4/8 B200 vs host CPU").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c3]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one update_positions (spring + midpoint KNN + intersection + update) on the
+synthetic workload.  `value` = edge-updates/s = E * iterations / second over ALL ranks (the same
+graph is edge-sharded across the ranks, so scaling is "strong").  Rank 0 prints ONE JSON line.
+
+Timing: W >= 3 warm-up steps; every timed step is bracketed by its own pair of CUDA events on
+the launching stream and preceded by an (untimed) L2 flush (a 512 MiB buffer write); the K step
+durations are summed, max over ranks.  `e2e` times the public API with host buffers: pinned
+host->device upload of the positions, update_positions(), device->host read of the result.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "layout iters/sec & edge-updates/s, 1M-vertex BA graph, 1/2/4/8 B200 vs host CPU"
+
+WORKLOADS = {
+    # BASELINE.json configs[2] -- the headline
+    "c3": dict(desc="barabasi_albert n=1000000 m=4 d=3 k=10 S=256", kind="ba", n=1_000_000, m=4, d=3, k=10, S=256),
+    # configs[1]
+    "c2": dict(desc="random_regular n=100000 deg=8 d=2 k=10 S=256", kind="rr", n=100_000, deg=8, d=2, k=10, S=256),
+    # configs[3]
+    "c4": dict(desc="sbm n=2000000 16 blocks d=3 k=32 S=256", kind="sbm", n=2_000_000, blocks=16, d=3, k=32, S=256),
+    # configs[4]
+    "c5": dict(desc="erdos_renyi n=10000000 avg_deg=10 d=3 k=10 S=256", kind="er", n=10_000_000, d=3, k=10, S=256),
+    # configs[0] (README quick start; CPU-runnable)
+    "c1": dict(desc="erdos_renyi n=1000 p=0.01 d=3 k=10 S=256", kind="er_small", n=1000, d=3, k=10, S=256),
+    "tiny": dict(desc="barabasi_albert n=20000 m=4 d=3 k=10 S=256", kind="ba", n=20_000, m=4, d=3, k=10, S=256),
+}
+
+
+def make_graph(w):
+    import graphem_rapids_b200.generators as gen
+    if w["kind"] == "ba":
+        return gen.generate_ba(w["n"], w["m"], seed=0)
+    if w["kind"] == "rr":
+        return gen.generate_random_regular(w["n"], w["deg"], seed=0)
+    if w["kind"] == "sbm":
+        npb = w["n"] // w["blocks"]
+        return gen.generate_sbm(npb, w["blocks"], 6.4e-5, 1.07e-6, seed=0)
+    if w["kind"] == "er":
+        return gen.erdos_renyi_graph(w["n"], 10.0 / w["n"], seed=0)
+    if w["kind"] == "er_small":
+        return gen.erdos_renyi_graph(w["n"], 0.01, seed=0)
+    raise ValueError(w["kind"])
+
+
+def initial_positions(n, d):
+    """randn*0.1 from default_rng(0): the reference's own fallback distribution
+    (embedder_pytorch.py:369); the Laplacian init is outside the timed path."""
+    return (np.random.default_rng(0).standard_normal((n, d)) * 0.1).astype(np.float32)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(smax)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port (torch CPU restatement of the reference) timed on
+# the host cores.  The ONLY place besides tests/ and smoke() that executes oracle/.
+# ----------------------------------------------------------------------------------------------
+def cpu_reference_timing(adj, w, steps, warmup, chunk=32):
+    from oracle import oracle
+    torch.set_num_threads(os.cpu_count() or 1)
+    edges = torch.from_numpy(oracle.extract_edges(adj).astype(np.int64))
+    E = edges.shape[0]
+    pos = torch.from_numpy(initial_positions(adj.shape[0], w["d"]))
+    gen = torch.Generator().manual_seed(0)
+    times = []
+    for it in range(warmup + steps):
+        samp = oracle.draw_sample(E, w["S"], gen)
+        t0 = time.perf_counter()
+        pos = oracle.layout_step(pos, edges, samp, n_neighbors=w["k"], strict=False, chunk_size=chunk)["new_pos"]
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    sec = float(np.mean(times))
+    return dict(E=int(E), sec_per_step=sec, cores=torch.get_num_threads(),
+                sample=f"{steps} full iterations of the workload (E={E}) after {warmup} warm-up, literal cdist+topk "
+                       f"restatement (oracle/oracle.py, strict=False), query chunk {chunk}, gc.collect/MemoryManager "
+                       f"of the reference omitted")
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    adj = make_graph(w)
+    steps = max(1, min(args.steps, 3))
+    warm = 1
+    r = cpu_reference_timing(adj, w, steps, warm)
+    val = r["E"] / r["sec_per_step"]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "edge-updates/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": r["sec_per_step"] * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "iters_per_s": 1.0 / r["sec_per_step"],
+        "config": {"workload": w["desc"], "E": r["E"], "note": "reference algorithm on host CPU cores (oracle port)"},
+        "cpu_baseline": {"value": val, "unit": "edge-updates/s", "cores": r["cores"], "kind": "port",
+                         "sample": r["sample"]},
+        "e2e": {"value": val, "unit": "edge-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------------
+def run_b200(args, w):
+    import torch.distributed as dist
+    import graphem_rapids_b200 as gr
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    adj = make_graph(w)
+    n, d = adj.shape[0], w["d"]
+    pos0 = initial_positions(n, d)
+    if world > 1:
+        from graphem_rapids_b200.sharded import ShardedGraphEmbedder
+        emb = ShardedGraphEmbedder(adj, n_components=d, device=dev, n_neighbors=w["k"], sample_size=w["S"],
+                                   verbose=False, seed=0, initial_positions=pos0)
+    else:
+        emb = gr.GraphEmbedderPyTorch(adj, n_components=d, device=dev, n_neighbors=w["k"], sample_size=w["S"],
+                                      verbose=False, seed=0, initial_positions=pos0)
+    E = emb.n_edges
+
+    flush_buf = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    K, W = args.steps, max(args.warmup, 3)
+    for _ in range(W):
+        emb.update_positions()
+    barrier()
+
+    # ---- device-resident timing: per-step events, L2 flushed (untimed) before every step
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(K):
+        flush_buf.fill_(i & 0xFF)
+        starts[i].record()
+        emb.update_positions()
+        ends[i].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    total_ms = float(np.sum(step_ms))
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---- back-to-back (warm L2, no flush; CUDA-graph replay when single GPU) for context
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    if world == 1:
+        emb.run_layout_device(K) if hasattr(emb, "run_layout_device") else [emb.update_positions() for _ in range(K)]
+    else:
+        for _ in range(K):
+            emb.update_positions()
+    b.record()
+    barrier()
+    b2b_ms = a.elapsed_time(b) / K
+
+    # ---- end to end through the public API with HOST buffers
+    host_in = torch.from_numpy(emb.positions).pin_memory()
+    host_out = torch.empty_like(host_in).pin_memory()
+    nbytes = host_in.numel() * 4
+    Ke = max(3, min(K, 10))
+    barrier()
+    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ea.record()
+    for _ in range(Ke):
+        emb.load_positions(host_in)            # H2D from pinned memory (positions setter semantics)
+        emb.update_positions()
+        emb.read_positions(host_out)           # D2H of the step's result + stream sync
+        host_in, host_out = host_out, host_in
+    eb.record()
+    barrier()
+    e2e_ms = ea.elapsed_time(eb) / Ke
+
+    # max over ranks
+    if world > 1:
+        t = torch.tensor([total_ms, b2b_ms, e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, b2b_ms, e2e_ms = [float(x) for x in t.tolist()]
+
+    # ---- per-kernel roofline (rank 0, single-GPU plan), measured live with CUDA events
+    stage = None
+    roof = None
+    extra_roof = {}
+    peaks, peak_src = measured_peaks()
+    if rank == 0 and world == 1:
+        runs = []
+        for i in range(5):
+            flush_buf.fill_(i)
+            runs.append(emb.profile_step())
+        stage = {k: float(np.median([r[k] for r in runs])) for k in runs[0]}
+        fp32_peak = emb.fp32_peak_flops()
+        S = min(w["S"], E)
+        N = n
+        flops = 2.0 * (d + 2) * S * E                        # 2(d+2) flop per query-candidate pair
+        scan_s = stage["knn_scan"] * 1e-3
+        roof = {"kernel": "knn_scan_kernel", "bound": "fp32", "achieved": flops / scan_s / 1e12,
+                "peak": fp32_peak / 1e12, "unit": "TFLOP/s", "frac": flops / scan_s / fp32_peak, "traffic": None,
+                "peak_source": "gem_fp32_peak_probe measured in this run (MEASURED_PEAKS.json has no FP32 figure)",
+                "algorithmic_flops_per_launch": flops, "ms": stage["knn_scan"],
+                "note": "2(d+2)*S*E flop per launch; the kernel executes d FFMA + 1 FSETP per pair (conservative "
+                        "filter) and re-checks the rare passes in the exact 5-op cdist chain"}
+        hbm = peaks["hbm_gbs"]
+        ka_bytes = 8.0 * E + 4.0 * d * N + 4.0 * d * N + 4.0 * d * E
+        kd_bytes = 20.0 * d * N
+        extra_roof = {
+            "spring_mid_kernel": {"bound": "hbm", "achieved": ka_bytes / (stage["spring_mid"] * 1e-3) / 1e9,
+                                  "peak": hbm, "unit": "GB/s",
+                                  "frac": ka_bytes / (stage["spring_mid"] * 1e-3) / 1e9 / hbm,
+                                  "algorithmic_bytes": ka_bytes, "ms": stage["spring_mid"]},
+            "update_pass1+2": {"bound": "hbm", "achieved": kd_bytes / (stage["update"] * 1e-3) / 1e9, "peak": hbm,
+                               "unit": "GB/s", "frac": kd_bytes / (stage["update"] * 1e-3) / 1e9 / hbm,
+                               "algorithmic_bytes": kd_bytes, "ms": stage["update"]},
+            "peak_source": peak_src,
+        }
+        # whole-iteration roofline: T_roof = B_iter/BW + F_iter/P
+        b_iter = 8.0 * E + 8.0 * d * E + 28.0 * d * N
+        t_roof = b_iter / (hbm * 1e9) + flops / fp32_peak
+        extra_roof["iteration"] = {"t_roof_ms": t_roof * 1e3, "achieved_ms": total_ms / K,
+                                   "frac": t_roof * 1e3 / (total_ms / K)}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline on this box's host cores (bounded sample)
+    cpu = None
+    if not args.no_cpu_baseline:
+        cb_steps = 2 if E > 1_000_000 else 3
+        r = cpu_reference_timing(adj, w, cb_steps, 1)
+        cpu = {"value": r["E"] / r["sec_per_step"], "unit": "edge-updates/s", "cores": r["cores"], "kind": "port",
+               "sample": r["sample"], "iters_per_s": 1.0 / r["sec_per_step"]}
+
+    ms_per_step = total_ms / K
+    value = E / (ms_per_step * 1e-3)
+    launches_per_step = 11 if world == 1 else 13
+    line = {
+        "metric": METRIC, "value": value, "unit": "edge-updates/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "iters_per_s": 1e3 / ms_per_step,
+        "config": {"workload": w["desc"], "N": n, "E": E, "sample_size": min(w["S"], E), "n_neighbors": w["k"],
+                   "parallelism": "single GPU" if world == 1 else f"edge-sharded x{world} (NCCL)",
+                   "l2": "flushed before every timed step (512 MiB write, untimed)",
+                   "sampler": "device (gem_sample_edges)", "init": "randn*0.1 default_rng(0)"},
+        "ms_per_step_back_to_back": b2b_ms,
+        "wall_s_timed_region": t_wall,
+        "e2e": {"value": E / (e2e_ms * 1e-3), "unit": "edge-updates/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+                "api": "load_positions(pinned) -> update_positions() -> read_positions(pinned)"},
+        "gpu_launches": launches_per_step * K,
+        "clocks": clk,
+        "roofline": roof,
+        "roofline_other": extra_roof,
+        "stage_ms": stage,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w)
+    else:
+        run_b200(args, w)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,574 @@
+"""
+GraphEmbedderPyTorch -- drop-in host class for the reference's
+graphem_rapids/backends/embedder_pytorch.py::GraphEmbedderPyTorch, with the layout iteration
+(`update_positions`, :776-806) executed by hand-written sm_100a kernels through the C ABI of
+include/graphem_b200.h.  Same constructor signature, attributes, methods and exceptions.
+
+Deliberate differences (DESIGN.md "Boundary"):
+  * CUDA fp32 only.  device='cpu', a non-fp32 dtype or a missing extension raise -- there is no
+    CPU / torch-op fallback on this path (the reference's backend dispatch, PyKeOps branch and
+    MemoryManager are removed).
+  * the S query edges are drawn on the device by a keyed bijection (gem_sample_edges) instead of
+    torch.randperm(E)[:S]; `sampler='torch'` restores the reference's call and RNG stream.
+  * extra keyword-only arguments: initial_positions, sampler, use_cuda_graph.
+"""
+from __future__ import annotations
+
+import ctypes
+import logging
+import os
+from typing import Optional
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+from . import _cabi
+
+logger = logging.getLogger(__name__)
+
+_SUPPORTED_BACKENDS = (None, "auto", "pytorch", "cuda", "cuvs", "b200")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+class GraphEmbedderPyTorch:
+    """Force-directed graph embedder; API of embedder_pytorch.py:27-180 (see module docstring)."""
+
+    def __init__(self, adjacency, n_components=2, device=None, dtype=torch.float32, L_min=1.0,
+                 k_attr=0.2, k_inter=0.5, n_neighbors=10, sample_size=256, batch_size=None,
+                 memory_efficient=True, verbose=True, logger_instance=None, seed=None, *,
+                 initial_positions=None, sampler="device", use_cuda_graph=True):
+        # seeding contract (embedder_pytorch.py:106-111)
+        if seed is not None:
+            np.random.seed(seed)
+            torch.manual_seed(seed)
+            if torch.cuda.is_available():
+                torch.cuda.manual_seed(seed)
+                torch.cuda.manual_seed_all(seed)
+
+        # device (:114-117).  torch.device('invalid_device') raises RuntimeError like the reference.
+        if device is None:
+            if not torch.cuda.is_available():
+                raise RuntimeError("graphem_rapids_b200 needs a CUDA device (sm_100a); no CPU fallback exists")
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        else:
+            self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError(f"graphem_rapids_b200 runs on CUDA only (got device={self.device}); "
+                               "the reference's CPU backend is not part of this path")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        if dtype != torch.float32:
+            raise NotImplementedError(f"graphem_rapids_b200 computes in float32 only (got {dtype})")
+
+        if logger_instance is not None:
+            self.logger = logger_instance
+        else:
+            self.logger = logger
+            if verbose:
+                logging.basicConfig(level=logging.INFO)
+
+        adjacency = self._validate_adjacency(adjacency)
+        self.adjacency = adjacency
+        self.n = adjacency.shape[0]
+        self.n_components = n_components
+        self.dtype = dtype
+        self.L_min = L_min
+        self.k_attr = k_attr
+        self.k_inter = k_inter
+        self.n_neighbors = n_neighbors
+        self.memory_efficient = memory_efficient
+        self.batch_size = batch_size
+        if n_components <= 0:                                   # :143-146
+            raise ValueError(f"Number of components must be positive, got {n_components}")
+        if k_attr < 0:
+            raise ValueError(f"Attractive force constant k_attr must be non-negative, got {k_attr}")
+        self.verbose = verbose
+        if sampler not in ("device", "torch"):
+            raise ValueError("sampler must be 'device' or 'torch'")
+        self.sampler = sampler
+        self.use_cuda_graph = bool(use_cuda_graph)
+
+        _cabi.load()
+        _cabi.init_device(self.device.index)
+        self._lib = _cabi.load()
+        self._ld = self._lib.gem_row_pitch(int(n_components))
+        self._mld = self._lib.gem_mid_pitch(int(n_components))
+
+        edges = self._extract_edges_from_adjacency(adjacency)
+        self.n_edges = len(edges)
+        self.sample_size = min(sample_size, self.n_edges)       # :156
+        if self.n >= 2 ** 31:
+            raise ValueError("graphem_rapids_b200 stores edge endpoints as int32: n must be < 2^31")
+        self.edges = torch.tensor(edges, device=self.device, dtype=torch.long).reshape(-1, 2)   # :159
+        self._edges32 = self.edges.to(torch.int32).contiguous()
+
+        self._has_pykeops = False                               # the PyKeOps branch (:247-258) is removed
+        if self.batch_size is None:
+            self.batch_size = max(1, min(self.n, 1024))         # kept for API compatibility; unused
+        self._sampler_seed = int(seed) if seed is not None else int(torch.randint(0, 2 ** 62, (1,)).item())
+        self._bufs = {}
+        self._graph = None
+        self._graph_key = None
+        self.last_sampled_indices = None
+        self.last_knn_indices = None
+
+        if self.verbose:
+            self.logger.info("Initialized GraphEmbedderPyTorch (B200 kernels) on %s", self.device)
+            self.logger.info("Graph: %d vertices, %d edges, %dD", self.n, self.n_edges, self.n_components)
+
+        self._pos = torch.zeros((self.n, self._ld), device=self.device, dtype=torch.float32)
+        if initial_positions is not None:
+            self.positions = initial_positions
+        else:
+            self._positions = self._compute_laplacian_embedding()
+
+    # ------------------------------------------------------------------ input handling
+    def _validate_adjacency(self, adjacency):
+        """embedder_pytorch.py:182-218: any array-like -> CSR, square, non-empty."""
+        if sp.issparse(adjacency):
+            adjacency = adjacency.tocsr()
+        elif not isinstance(adjacency, np.ndarray):
+            adjacency = np.asarray(adjacency)
+        if adjacency.shape[0] != adjacency.shape[1]:
+            raise ValueError(f"Adjacency matrix must be square, got shape {adjacency.shape}")
+        if adjacency.shape[0] == 0:
+            raise ValueError("Adjacency matrix cannot be empty")
+        if not sp.issparse(adjacency):
+            adjacency = sp.csr_matrix(adjacency)
+        return adjacency
+
+    def _extract_edges_from_adjacency(self, adjacency):
+        """embedder_pytorch.py:220-245: nonzero() order, upper triangle i<j."""
+        rows, cols = adjacency.nonzero()
+        keep = rows < cols
+        edges = np.column_stack([rows[keep], cols[keep]])
+        if self.verbose and len(edges) == 0:
+            self.logger.warning("No edges found in adjacency matrix")
+        return edges
+
+    def _check_pykeops_availability(self):
+        return False
+
+    def _get_adaptive_chunk_size(self, n_query, n_ref, backend):
+        """API compatibility (:260-322): the fused KNN never materialises a distance matrix, so
+        there is nothing to chunk; returns a positive size bounded by n_query."""
+        return max(1, min(int(self.batch_size), int(n_query)))
+
+    # ------------------------------------------------------------------ state
+    @property
+    def _positions(self):
+        """(n, d) view of the padded device buffer (reference attribute `_positions`)."""
+        return self._pos[:, : self.n_components]
+
+    @_positions.setter
+    def _positions(self, value):
+        value = torch.as_tensor(value).to(device=self.device, dtype=torch.float32)
+        if value.shape != (self.n, self.n_components):
+            raise ValueError(f"positions must have shape {(self.n, self.n_components)}, got {tuple(value.shape)}")
+        buf = torch.zeros((self.n, self._ld), device=self.device, dtype=torch.float32)
+        buf[:, : self.n_components] = value
+        self._pos = buf
+        self._graph = None
+
+    @property
+    def positions(self):
+        """numpy copy (:324-327)."""
+        return self._positions.detach().cpu().numpy()
+
+    @positions.setter
+    def positions(self, value):
+        """ndarray or tensor -> device (:329-335)."""
+        if isinstance(value, np.ndarray):
+            value = torch.tensor(value, dtype=torch.float32)
+        self._positions = value
+
+    def _compute_laplacian_embedding(self):
+        """Initial embedding (embedder_pytorch.py:337-379): eigenvectors 2..d+1 of the normalised
+        Laplacian via ARPACK on the host; random*0.1 if that fails.  One-off, outside the timed
+        path (SURVEY.md section 8(f) lists a device eigensolver as the next step)."""
+        import scipy.sparse.linalg as spla
+        from scipy.sparse.csgraph import laplacian
+        self.logger.info("Computing Laplacian embedding")
+        sym = sp.csr_matrix(self.adjacency + self.adjacency.transpose())
+        sym.data = np.ones_like(sym.data)
+        lap = laplacian(sym, normed=True)
+        k = self.n_components + 1
+        try:
+            _, vecs = spla.eigsh(lap, k, which="SM")
+            emb = vecs[:, 1:k]
+        except Exception as exc:  # pylint: disable=broad-exception-caught
+            self.logger.warning("Eigendecomposition failed: %s", exc)
+            emb = np.random.randn(self.n, self.n_components) * 0.1
+        return torch.tensor(emb, device=self.device, dtype=torch.float32)
+
+    # ------------------------------------------------------------------ buffers / plan
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _buffers(self):
+        """Scratch owned by the object, (re)allocated when S, k or E change."""
+        S = min(int(self.sample_size), self.n_edges)
+        kp1 = int(self.n_neighbors) + 1
+        key = (S, kp1, self.n_edges)
+        if self._bufs.get("key") == key:
+            return self._bufs
+        dev, f32 = self.device, torch.float32
+        E = max(self.n_edges, 1)
+        ws_bytes = ctypes.c_size_t(0)
+        _cabi.check(self._lib.gem_knn_workspace_bytes(E, int(self.n_components), max(S, 1), kp1,
+                                                      ctypes.byref(ws_bytes)), "gem_knn_workspace_bytes")
+        st_bytes = ctypes.c_size_t(0)
+        _cabi.check(self._lib.gem_update_workspace_bytes(self.n, int(self.n_components), ctypes.byref(st_bytes)),
+                    "gem_update_workspace_bytes")
+        self._bufs = dict(
+            key=key, S=S, kp1=kp1,
+            force=torch.zeros((self.n, self._ld), device=dev, dtype=f32),
+            mid=torch.zeros((E + 1, self._mld), device=dev, dtype=f32),
+            qmid=torch.zeros((max(S, 1), self._mld), device=dev, dtype=f32),
+            samp=torch.zeros((max(S, 1),), device=dev, dtype=torch.long),
+            knn_idx=torch.zeros((max(S, 1), kp1), device=dev, dtype=torch.long),
+            knn_dist=torch.zeros((max(S, 1), kp1), device=dev, dtype=f32),
+            iter=self._bufs.get("iter", torch.zeros((1,), device=dev, dtype=torch.long)),
+            knn_ws=torch.zeros((ws_bytes.value + 256,), device=dev, dtype=torch.uint8),
+            stats_ws=torch.zeros((st_bytes.value + 256,), device=dev, dtype=torch.uint8),
+            knn_ws_bytes=ws_bytes.value,
+        )
+        self._graph = None
+        return self._bufs
+
+    def _plan(self, external_sample: bool) -> _cabi.GemPlan:
+        b = self._buffers()
+        p = _cabi.GemPlan()
+        p.n, p.e, p.s = self.n, self.n_edges, b["S"]
+        p.d, p.kp1 = int(self.n_components), b["kp1"]
+        p.k_attr, p.l_min, p.k_inter = float(self.k_attr), float(self.L_min), float(self.k_inter)
+        p.seed = self._sampler_seed & (2 ** 64 - 1)
+        p.pos = self._pos.data_ptr()
+        p.edges = self._edges32.data_ptr()
+        p.force = b["force"].data_ptr()
+        p.mid = b["mid"].data_ptr()
+        p.qmid = b["qmid"].data_ptr()
+        p.samp = b["samp"].data_ptr()
+        p.knn_idx = b["knn_idx"].data_ptr()
+        p.knn_dist = b["knn_dist"].data_ptr()
+        p.iter_counter = b["iter"].data_ptr()
+        p.knn_ws = b["knn_ws"].data_ptr()
+        p.knn_ws_bytes = b["knn_ws_bytes"]
+        p.stats_ws = b["stats_ws"].data_ptr()
+        p.external_sample = 1 if external_sample else 0
+        p.mm_mode = -1
+        return p
+
+    # ------------------------------------------------------------------ the hot path
+    def update_positions(self, sampled_indices=None):
+        """One layout iteration (embedder_pytorch.py:776-806) = one gem_layout_step call.
+
+        `sampled_indices` (optional, extension) injects the S query edge ids -- this is how the
+        parity tests drive this class and the oracle from the same sample."""
+        if self.n_edges == 0:
+            # the reference reaches torch.topk with k+1 > 0 candidates and raises (:583)
+            raise RuntimeError("selected index k out of range")
+        b = self._buffers()
+        external = sampled_indices is not None or self.sampler == "torch"
+        if sampled_indices is not None:
+            s = torch.as_tensor(sampled_indices).to(device=self.device, dtype=torch.long).reshape(-1)
+            if s.numel() != b["S"]:
+                raise ValueError(f"sampled_indices must have {b['S']} entries, got {s.numel()}")
+            b["samp"].copy_(s)
+        elif self.sampler == "torch":
+            E, S = self.n_edges, b["S"]
+            b["samp"].copy_(torch.randperm(E, device=self.device)[:S] if S < E
+                            else torch.arange(E, device=self.device))       # :408-413
+        plan = self._plan(external)
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.gem_layout_step(ctypes.byref(plan), self._stream()), "gem_layout_step")
+        self.last_sampled_indices = b["samp"]
+        self.last_knn_indices = b["knn_idx"][:, 1:]
+
+    def profile_step(self):
+        """One iteration with a CUDA event after every stage (gem_profile_step; synchronises).
+        Returns {stage name: milliseconds}.  Used by bench.py for the per-kernel roofline."""
+        plan = self._plan(False)
+        ms = (ctypes.c_float * len(_cabi.STAGE_NAMES))()
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.gem_profile_step(ctypes.byref(plan), self._stream(), ms), "gem_profile_step")
+        return dict(zip(_cabi.STAGE_NAMES, [float(x) for x in ms]))
+
+    def fp32_peak_flops(self) -> float:
+        """Measured FP32 FMA throughput of this device in flop/s (gem_fp32_peak_probe)."""
+        out = ctypes.c_double(0.0)
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.gem_fp32_peak_probe(ctypes.byref(out), self._stream()), "gem_fp32_peak_probe")
+        return float(out.value)
+
+    def _run_graph(self, num_iterations: int) -> bool:
+        """Replay one captured iteration `num_iterations` times (device sampler only)."""
+        b = self._buffers()
+        key = (self._pos.data_ptr(), b["key"], float(self.k_attr), float(self.L_min), float(self.k_inter))
+        if self._graph is None or self._graph_key != key:
+            plan = self._plan(False)
+            graph = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize(self.device)
+            it0 = b["iter"].clone()
+            pos0 = self._pos.clone()
+            with torch.cuda.graph(graph):
+                rc = self._lib.gem_layout_step(ctypes.byref(plan), self._stream())
+            _cabi.check(rc, "gem_layout_step (capture)")
+            # capture does not execute, but keep state exactly as it was in any case
+            b["iter"].copy_(it0)
+            self._pos.copy_(pos0)
+            self._graph, self._graph_key = graph, key
+        for _ in range(num_iterations):
+            self._graph.replay()
+        self.last_sampled_indices = b["samp"]
+        self.last_knn_indices = b["knn_idx"][:, 1:]
+        return True
+
+    def run_layout(self, num_iterations=100):
+        """embedder_pytorch.py:808-833; returns the positions as ndarray."""
+        if self.verbose:
+            self.logger.info("Running layout for %d iterations", num_iterations)
+        if self.n_edges == 0 and num_iterations > 0:
+            raise RuntimeError("selected index k out of range")
+        with torch.cuda.device(self.device):
+            if self.use_cuda_graph and self.sampler == "device" and num_iterations > 1:
+                if self.n_neighbors + 1 > self.n_edges:
+                    raise RuntimeError("selected index k out of range")
+                self._run_graph(int(num_iterations))
+            else:
+                for _ in range(int(num_iterations)):
+                    self.update_positions()
+        if self.verbose:
+            self.logger.info("Layout computation completed")
+        return self.positions
+
+    def get_positions(self):
+        """embedder_pytorch.py:835-844."""
+        return self.positions
+
+    # host-buffer fast paths of the positions setter / getter (extensions; bench.py e2e)
+    def load_positions(self, host_positions: torch.Tensor):
+        """Asynchronous H2D of an (n, d) fp32 host tensor (pinned for full speed) into the device state."""
+        d = self.n_components
+        if tuple(host_positions.shape) != (self.n, d) or host_positions.dtype != torch.float32:
+            raise ValueError(f"expected an fp32 tensor of shape {(self.n, d)}")
+        if self._ld == d:
+            self._pos.copy_(host_positions, non_blocking=True)
+        else:
+            stage = self._bufs.get("h2d_stage")
+            if stage is None or stage.shape != host_positions.shape:
+                stage = torch.empty((self.n, d), device=self.device, dtype=torch.float32)
+                self._bufs["h2d_stage"] = stage
+            stage.copy_(host_positions, non_blocking=True)
+            self._pos[:, :d].copy_(stage)
+
+    def read_positions(self, out: torch.Tensor):
+        """D2H of the current positions into an (n, d) fp32 host tensor, then stream sync."""
+        d = self.n_components
+        if self._ld == d:
+            out.copy_(self._pos, non_blocking=True)
+        else:
+            stage = self._bufs.get("d2h_stage")
+            if stage is None or stage.shape != out.shape:
+                stage = torch.empty((self.n, d), device=self.device, dtype=torch.float32)
+                self._bufs["d2h_stage"] = stage
+            stage.copy_(self._pos[:, :d])
+            out.copy_(stage, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return out
+
+    def run_layout_device(self, num_iterations=100):
+        """run_layout without the final device->host copy (positions stay in HBM)."""
+        with torch.cuda.device(self.device):
+            if self.use_cuda_graph and self.sampler == "device" and num_iterations > 1:
+                self._run_graph(int(num_iterations))
+            else:
+                for _ in range(int(num_iterations)):
+                    self.update_positions()
+
+    # ------------------------------------------------------------------ stage-level (private, unit-tested) API
+    def _pad_rows(self, x: torch.Tensor) -> torch.Tensor:
+        x = x.to(device=self.device, dtype=torch.float32)
+        d = self.n_components
+        if self._ld == d and x.is_contiguous():
+            return x
+        buf = torch.zeros((x.shape[0], self._ld), device=self.device, dtype=torch.float32)
+        buf[:, :d] = x
+        return buf
+
+    def _edges_as_int32(self, edges: torch.Tensor) -> torch.Tensor:
+        if edges is self.edges:
+            return self._edges32
+        return edges.to(device=self.device, dtype=torch.int32).contiguous()
+
+    def _compute_spring_forces(self, positions, edges):
+        """embedder_pytorch.py:595-636 -> (n, d) tensor."""
+        pos = self._pad_rows(positions)
+        e32 = self._edges_as_int32(edges)
+        force = torch.empty_like(pos)
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.gem_spring_midpoints(_ptr(pos), _ptr(e32), pos.shape[0], e32.shape[0],
+                                                       int(self.n_components), float(self.k_attr), float(self.L_min),
+                                                       _ptr(force), None, self._stream()), "gem_spring_midpoints")
+        return force[:, : self.n_components]
+
+    def _compute_midpoints(self, positions, edges):
+        """The expression at embedder_pytorch.py:785 -> (e, d) tensor (extension, used by tests)."""
+        pos = self._pad_rows(positions)
+        e32 = self._edges_as_int32(edges)
+        force = torch.empty_like(pos)
+        mid = torch.zeros((e32.shape[0] + 1, self._mld), device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.gem_spring_midpoints(_ptr(pos), _ptr(e32), pos.shape[0], e32.shape[0],
+                                                       int(self.n_components), float(self.k_attr), float(self.L_min),
+                                                       _ptr(force), _ptr(mid), self._stream()), "gem_spring_midpoints")
+        return mid[:-1, : self.n_components]
+
+    def _knn_points(self, query, reference, k, exact=False, return_distances=False):
+        query = query.to(device=self.device, dtype=torch.float32).contiguous()
+        reference = reference.to(device=self.device, dtype=torch.float32).contiguous()
+        nq, d = query.shape
+        nr = reference.shape[0]
+        if k > nr:
+            raise RuntimeError("selected index k out of range")          # torch.topk (:583)
+        mld = self._lib.gem_mid_pitch(int(d))
+        rm = torch.zeros((nr + 1, mld), device=self.device, dtype=torch.float32)
+        qm = torch.zeros((nq, mld), device=self.device, dtype=torch.float32)
+        idx = torch.empty((nq, k), device=self.device, dtype=torch.long)
+        dist = torch.empty((nq, k), device=self.device, dtype=torch.float32)
+        st = self._stream()
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.gem_pack_points(_ptr(reference), nr, int(d), _ptr(rm), st), "gem_pack_points")
+            _cabi.check(self._lib.gem_pack_points(_ptr(query), nq, int(d), _ptr(qm), st), "gem_pack_points")
+            if exact:
+                _cabi.check(self._lib.gem_knn_midpoints_exact(_ptr(rm), nr, 0, int(d), _ptr(qm), nq, int(k), -1,
+                                                              _ptr(idx), _ptr(dist), st), "gem_knn_midpoints_exact")
+            else:
+                nbytes = ctypes.c_size_t(0)
+                _cabi.check(self._lib.gem_knn_workspace_bytes(nr, int(d), nq, int(k), ctypes.byref(nbytes)))
+                ws = torch.zeros((nbytes.value + 256,), device=self.device, dtype=torch.uint8)
+                _cabi.check(self._lib.gem_knn_midpoints(_ptr(rm), nr, 0, int(d), _ptr(qm), nq, int(k), -1, _ptr(idx),
+                                                        _ptr(dist), _ptr(ws), nbytes.value, st), "gem_knn_midpoints")
+        return (idx, dist) if return_distances else idx
+
+    def _compute_knn_chunked(self, query_points, reference_points, k):
+        """embedder_pytorch.py:426-483 -> (n_query, k) int64, rows ascending by (distance, index)."""
+        return self._knn_points(query_points, reference_points, k)
+
+    def _compute_knn_torch(self, query_points, reference_points, k, chunk_size):
+        """embedder_pytorch.py:543-593 (cdist + topk); chunk_size is irrelevant here."""
+        return self._knn_points(query_points, reference_points, k)
+
+    def _compute_knn_pykeops(self, query_points, reference_points, k, chunk_size):
+        raise ImportError("PyKeOps not available")                       # :511-514
+
+    def _locate_knn_midpoints(self, midpoints, k, sampled_indices=None):
+        """embedder_pytorch.py:381-424 -> (knn (S,k) with column 0 dropped, sampled ids (S,))."""
+        E = midpoints.shape[0]
+        S = min(int(self.sample_size), E)
+        if sampled_indices is not None:
+            samp = torch.as_tensor(sampled_indices).to(device=self.device, dtype=torch.long)
+        elif S < E:
+            if self.sampler == "torch":
+                samp = torch.randperm(E, device=self.device)[:S]
+            else:
+                b = self._buffers()
+                samp = torch.empty((S,), device=self.device, dtype=torch.long)
+                with torch.cuda.device(self.device):
+                    _cabi.check(self._lib.gem_sample_edges(self._sampler_seed & (2 ** 64 - 1), _ptr(b["iter"]), 1, E, S,
+                                                           _ptr(samp), self._stream()), "gem_sample_edges")
+        else:
+            samp = torch.arange(E, device=self.device)
+        midpoints = midpoints.to(device=self.device, dtype=torch.float32)
+        knn = self._knn_points(midpoints[samp], midpoints, k + 1)
+        return knn[:, 1:], samp
+
+    def _compute_intersection_forces(self, positions, edges, knn_indices, sampled_indices):
+        """embedder_pytorch.py:638-736 -> (n, d) tensor."""
+        if self.n_components < 2:
+            raise IndexError("index 1 is out of bounds for dimension 1 with size 1")   # :762
+        pos = self._pad_rows(positions)
+        e32 = self._edges_as_int32(edges)
+        knn = knn_indices.to(device=self.device, dtype=torch.long)
+        samp = sampled_indices.to(device=self.device, dtype=torch.long).contiguous()
+        S, k = knn.shape
+        full = torch.zeros((S, k + 1), device=self.device, dtype=torch.long)
+        full[:, 1:] = knn
+        force = torch.zeros_like(pos)
+        if S * k > 0:
+            with torch.cuda.device(self.device):
+                _cabi.check(self._lib.gem_intersection_forces(_ptr(pos), _ptr(e32), pos.shape[0], int(self.n_components),
+                                                              _ptr(samp), _ptr(full), S, k + 1, float(self.k_inter),
+                                                              _ptr(force), self._stream()), "gem_intersection_forces")
+        return force[:, : self.n_components]
+
+    def _check_line_intersections(self, p1, p2, q1, q2):
+        """embedder_pytorch.py:738-774 -> bool (P,)."""
+        ts = [t.to(device=self.device, dtype=torch.float32).contiguous() for t in (p1, p2, q1, q2)]
+        P, d = ts[0].shape
+        out = torch.zeros((P,), device=self.device, dtype=torch.uint8)
+        if P > 0:
+            with torch.cuda.device(self.device):
+                _cabi.check(self._lib.gem_check_line_intersections(_ptr(ts[0]), _ptr(ts[1]), _ptr(ts[2]), _ptr(ts[3]),
+                                                                   P, int(d), _ptr(out), self._stream()),
+                            "gem_check_line_intersections")
+        return out.bool()
+
+    def _apply_update(self, positions, spring_forces, inter_forces):
+        """Tail of update_positions (embedder_pytorch.py:796-804) -> (n, d) tensor (extension)."""
+        pos = self._pad_rows(positions).clone()
+        fs = self._pad_rows(spring_forces)
+        fi = self._pad_rows(inter_forces) if inter_forces is not None else None
+        nbytes = ctypes.c_size_t(0)
+        _cabi.check(self._lib.gem_update_workspace_bytes(pos.shape[0], int(self.n_components), ctypes.byref(nbytes)))
+        ws = torch.zeros((nbytes.value + 256,), device=self.device, dtype=torch.uint8)
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.gem_update_positions(_ptr(pos), _ptr(fs), _ptr(fi), pos.shape[0], pos.shape[0],
+                                                       int(self.n_components), _ptr(ws), 0, self._stream()),
+                        "gem_update_positions")
+        return pos[:, : self.n_components]
+
+    # ------------------------------------------------------------------ misc
+    def display_layout(self, edge_width=1, node_size=3, node_colors=None):
+        """embedder_pytorch.py:846-969: plotly scatter of the layout (needs plotly)."""
+        if self.n_components not in (2, 3):
+            raise ValueError("Can only display 2D or 3D layouts")
+        import plotly.graph_objects as go  # pylint: disable=import-outside-toplevel
+        pos = self.get_positions()
+        ed = self.edges.cpu().numpy()
+        seg = np.full((len(ed), 3, self.n_components), np.nan)
+        seg[:, 0] = pos[ed[:, 0]]
+        seg[:, 1] = pos[ed[:, 1]]
+        seg = seg.reshape(-1, self.n_components)
+        marker = {"color": node_colors if node_colors is not None else "red", "colorscale": "Bluered",
+                  "size": node_size, "showscale": node_colors is not None}
+        if self.n_components == 2:
+            traces = [go.Scatter(x=seg[:, 0], y=seg[:, 1], mode="lines", line={"color": "gray", "width": edge_width},
+                                 hoverinfo="none"),
+                      go.Scatter(x=pos[:, 0], y=pos[:, 1], mode="markers", marker=marker, hoverinfo="none")]
+        else:
+            traces = [go.Scatter3d(x=seg[:, 0], y=seg[:, 1], z=seg[:, 2], mode="lines",
+                                   line={"color": "gray", "width": edge_width}, hoverinfo="none"),
+                      go.Scatter3d(x=pos[:, 0], y=pos[:, 1], z=pos[:, 2], mode="markers", marker=marker,
+                                   hoverinfo="none")]
+        fig = go.Figure(data=traces)
+        fig.update_layout(title=f"{self.n_components}D Graph Embedding (B200)", showlegend=False, width=800, height=800)
+        fig.show()
+
+    def __repr__(self):
+        return (f"GraphEmbedderPyTorch(n_vertices={self.n}, n_components={self.n_components}, "
+                f"device={self.device}, memory_efficient={self.memory_efficient})")
+
+
+def create_graphem(adjacency, n_components=2, backend=None, **kwargs):
+    """graphem_rapids/__init__.py:78-136.  Every GPU backend name routes to the B200 class; the
+    reference's backend selection (utils/backend_selection.py) is not part of this path."""
+    if backend == "cpu":
+        raise RuntimeError("graphem_rapids_b200 has no CPU backend (backend='cpu' requested)")
+    if backend not in _SUPPORTED_BACKENDS:
+        raise ValueError(f"Unknown backend {backend!r}")
+    return GraphEmbedderPyTorch(adjacency, n_components, **kwargs)

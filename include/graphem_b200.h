@@ -1,0 +1,168 @@
+/*
+ * graphem_b200 -- C ABI of the B200 (sm_100a) implementation of GraphEm's force-directed
+ * layout iteration.
+ *
+ * The reference (sashakolpakov/graphem-rapids v0.2.0) is pure Python and has no FFI: the
+ * boundary a caller sees is the class GraphEmbedderPyTorch
+ * (graphem_rapids/backends/embedder_pytorch.py).  Each entry point below replaces the
+ * torch-op body of one of its methods; the Python host graphem_rapids_b200.embedder binds
+ * them with ctypes (see INTEGRATION.md for the stub a maintainer of the reference would add).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host; the library never
+ *     allocates, frees or synchronises: scratch comes from the caller-provided workspace,
+ *     every launch goes to `stream` (a cudaStream_t passed as void*), so every call is
+ *     CUDA-graph capturable;
+ *   - return value: 0 on success, otherwise a negative GEM_E_* code or the positive
+ *     cudaError_t of the failed launch; gem_error_string() describes both;
+ *   - vertex positions / forces are row-major (n, ld) fp32 with ld = gem_row_pitch(d):
+ *     2 for d=2, 4 for d=3 (lane 3 is zero padding so one 128-bit access moves a row),
+ *     d otherwise;
+ *   - midpoints are row-major (e, gem_mid_pitch(d)) fp32: d=2 -> (x, y);
+ *     d=3 -> (x, y, z, |m|^2); other d -> d coordinates followed by |m|^2;
+ *   - edge ids are int32 pairs (i<j, sorted by (i,j)) -- n < 2^31 at every target size; the
+ *     public `edges` attribute of the Python class stays int64;
+ *   - neighbour lists are int64 (global edge ids), ascending by (distance, index).
+ */
+#ifndef GRAPHEM_B200_H
+#define GRAPHEM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GEM_ABI_VERSION 1
+
+#define GEM_OK 0
+#define GEM_E_BADARG (-1)      /* null pointer, negative size, unsupported d */
+#define GEM_E_WORKSPACE (-2)   /* workspace too small / misaligned */
+#define GEM_E_KRANGE (-3)      /* k+1 > number of candidates (the reference's topk RuntimeError) */
+#define GEM_E_NODEVICE (-4)    /* no sm_100 device / kernel image not loadable */
+
+int gem_abi_version(void);
+/* Once per process and device, before the first launch (sets kernel attributes; not capturable). */
+int gem_init(void);
+const char *gem_error_string(int code);
+/* row pitch (floats) of positions/forces and of midpoints for n_components = d */
+int gem_row_pitch(int d);
+int gem_mid_pitch(int d);
+
+/* (a) spring forces + midpoints.  Replaces _compute_spring_forces (embedder_pytorch.py:595-636)
+ * and the midpoint expression of update_positions (:785).
+ * force (n, ld) is zeroed inside, then F[i] += f, F[j] -= f per edge.  mid may be NULL.
+ * `edges` points at the first edge of the (shard of the) list, `e` edges long. */
+int gem_spring_midpoints(const float *pos, const int32_t *edges, int64_t n, int64_t e, int d,
+                         float k_attr, float l_min, float *force, float *mid, void *stream);
+
+/* Sampling of the query edges.  Replaces `torch.randperm(E, device)[:S]` / `arange(E)`
+ * (_locate_knn_midpoints, :404-413) by a keyed bijection of [0,e) evaluated at 0..s-1
+ * (Feistel network with cycle walking, key = (seed, *iter_counter)); s distinct ids, no host
+ * sync, replayable from a CUDA graph.  When s >= e the result is arange(e).
+ * If bump_counter != 0 the kernel increments *iter_counter afterwards. */
+int gem_sample_edges(uint64_t seed, int64_t *iter_counter, int bump_counter, int64_t e, int64_t s,
+                     int64_t *samp, void *stream);
+
+/* Midpoints of the s sampled edges, computed from positions (identical bits to what
+ * gem_spring_midpoints writes): replaces `midpoints[sampled_indices]` (:410). */
+int gem_query_midpoints(const float *pos, const int32_t *edges, const int64_t *samp, int64_t s, int d,
+                        float *qmid, void *stream);
+
+/* (b) brute-force KNN over midpoints.  Replaces _compute_knn_chunked / _compute_knn_torch
+ * (:426-483, :543-593: torch.cdist + torch.topk(k+1, largest=False)).
+ * Distances reproduce torch.cdist bit for bit: matmul-mode FMA chain when s>25 or e_total>25,
+ * direct mode otherwise (mm_mode: 1 / 0; pass -1 to choose like torch does from s and e).
+ * out_idx (s, kp1) int64 = idx_offset + local candidate id, out_dist (s, kp1) fp32, each row
+ * ascending by (distance, index).  Column 0 is NOT dropped here (:421 is applied by the consumer).
+ * gem_knn_workspace_bytes sizes `ws` (256-byte aligned). */
+int gem_knn_workspace_bytes(int64_t e, int d, int64_t s, int kp1, size_t *bytes);
+int gem_knn_midpoints(const float *mid, int64_t e, int64_t idx_offset, int d, const float *qmid,
+                      int64_t s, int kp1, int mm_mode, int64_t *out_idx, float *out_dist, void *ws,
+                      size_t ws_bytes, void *stream);
+/* Same contract, single exact streaming kernel (one CTA per query); the slow, simple
+ * implementation used as in-library cross-check and as overflow fallback. */
+int gem_knn_midpoints_exact(const float *mid, int64_t e, int64_t idx_offset, int d, const float *qmid,
+                            int64_t s, int kp1, int mm_mode, int64_t *out_idx, float *out_dist,
+                            void *stream);
+/* Merge `parts` partial lists (parts, s, kp1) into (s, kp1) by (distance, index): the
+ * exchange step of the edge-sharded multi-GPU KNN (after an all-gather of the partial lists). */
+int gem_topk_merge(const float *dists, const int64_t *idxs, int parts, int64_t s, int kp1,
+                   int64_t *out_idx, float *out_dist, void *stream);
+
+/* (c) intersection repulsion.  Replaces _compute_intersection_forces (:638-736) and
+ * _check_line_intersections (:738-774).  knn_full is the (s, kp1) list INCLUDING column 0,
+ * which the kernel skips (:421).  Accumulates into `force` (n, ld) (not zeroed). */
+int gem_intersection_forces(const float *pos, const int32_t *edges, int64_t n, int d,
+                            const int64_t *samp, const int64_t *knn_full, int64_t s, int kp1,
+                            float k_inter, float *force, void *stream);
+
+/* (d) position update.  Replaces the tail of update_positions (:796-804):
+ * new = pos + (f_spring + f_inter); new -= mean; new /= (unbiased std + 1e-6).
+ * f_inter may be NULL.  stats_ws: 256-byte aligned scratch of gem_update_workspace_bytes(n,d),
+ * zero-initialised once by the caller.
+ * phase 0 = both passes; phase 1 = pass 1 only (writes unnormalised positions and the
+ * column sums {sum, sum of squares} as 2*ld doubles at the start of stats_ws, for a
+ * cross-rank all-reduce); phase 2 = pass 2 only (reads the reduced sums; n_total = global n). */
+int gem_update_workspace_bytes(int64_t n, int d, size_t *bytes);
+int gem_update_positions(float *pos, const float *f_spring, const float *f_inter, int64_t n,
+                         int64_t n_total, int d, void *stats_ws, int phase, void *stream);
+
+/* One whole iteration (update_positions, :776-806) on one GPU, launched back to back on
+ * `stream`: sample -> spring+midpoints -> query midpoints -> KNN -> intersection -> update. */
+typedef struct gem_plan {
+    int64_t n, e, s;          /* vertices, edges, sample size (already min(sample_size, e)) */
+    int32_t d, kp1;           /* n_components, n_neighbors + 1 */
+    float k_attr, l_min, k_inter;
+    uint64_t seed;
+    float *pos;               /* (n, ld)   in/out */
+    const int32_t *edges;     /* (e, 2) */
+    float *force;             /* (n, ld)   scratch */
+    float *mid;               /* (e, mld)  scratch */
+    float *qmid;              /* (s, mld)  scratch */
+    int64_t *samp;            /* (s)       out: the sample used (or in, when external_sample) */
+    int64_t *knn_idx;         /* (s, kp1)  out */
+    float *knn_dist;          /* (s, kp1)  out */
+    int64_t *iter_counter;    /* (1)       device iteration counter */
+    void *knn_ws; size_t knn_ws_bytes;
+    void *stats_ws;
+    int32_t external_sample;  /* 1: samp was filled by the caller (torch.randperm parity mode) */
+    int32_t mm_mode;          /* -1 auto */
+} gem_plan;
+
+int gem_layout_step(const gem_plan *plan_host, void *stream);
+
+/* Profiling variant (bench.py roofline): the same launches with a CUDA event after every stage;
+ * SYNCHRONISES the stream and writes the GEM_NUM_STAGES stage durations (ms) to ms_host.
+ * Only valid when the KNN needs a single query batch (s <= 2048). */
+#define GEM_STAGE_SAMPLE 0
+#define GEM_STAGE_SPRING 1         /* memset + spring/midpoint kernel */
+#define GEM_STAGE_QUERY_MID 2
+#define GEM_STAGE_KNN_BOUND 3      /* 2 memsets + bound kernel */
+#define GEM_STAGE_KNN_THRESHOLD 4
+#define GEM_STAGE_KNN_SCAN 5       /* the dominant kernel */
+#define GEM_STAGE_KNN_SELECT 6
+#define GEM_STAGE_KNN_FALLBACK 7   /* exact kernel: overflow fallback (or the whole KNN for tiny / generic-d inputs) */
+#define GEM_STAGE_INTERSECT 8
+#define GEM_STAGE_UPDATE 9         /* both passes */
+#define GEM_NUM_STAGES 10
+int gem_profile_step(const gem_plan *plan_host, void *stream, float *ms_host);
+
+/* Helpers behind the reference's private, unit-tested methods:
+ * gem_pack_points: arbitrary (n,d) row-major points -> midpoint layout, for
+ *   _compute_knn_chunked(query, reference, k) / _compute_knn_torch (:426-483, :543-593);
+ * gem_check_line_intersections: _check_line_intersections(p1,p2,q1,q2) (:738-774) on (p,d)
+ *   row-major inputs, out[i] in {0,1}. */
+int gem_pack_points(const float *pts, int64_t n, int d, float *out, void *stream);
+int gem_check_line_intersections(const float *p1, const float *p2, const float *q1, const float *q2, int64_t p, int d,
+                                 uint8_t *out, void *stream);
+
+/* Measured FP32 FMA throughput of the device (dependent-chain-free FFMA loop), for the
+ * roofline denominator of the KNN kernel: writes flop/s to *flops_host.  Synchronises. */
+int gem_fp32_peak_probe(double *flops_host, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRAPHEM_B200_H */
