@@ -25,8 +25,9 @@ class GemPlan(Structure):
         ("d", c_int32), ("kp1", c_int32),
         ("k_attr", c_float), ("l_min", c_float), ("k_inter", c_float),
         ("seed", c_uint64),
-        ("pos", c_void_p), ("edges", c_void_p), ("force", c_void_p), ("mid", c_void_p),
-        ("qmid", c_void_p), ("samp", c_void_p), ("knn_idx", c_void_p), ("knn_dist", c_void_p),
+        ("pos", c_void_p), ("edges", c_void_p), ("row_ptr", c_void_p), ("col", c_void_p),
+        ("force", c_void_p), ("mid", c_void_p),
+        ("qmid", c_void_p), ("tau_hint", c_void_p), ("samp", c_void_p), ("knn_idx", c_void_p), ("knn_dist", c_void_p),
         ("iter_counter", c_void_p),
         ("knn_ws", c_void_p), ("knn_ws_bytes", c_size_t),
         ("stats_ws", c_void_p),
@@ -46,10 +47,14 @@ SIGNATURES = {
     "gem_sample_edges": (c_int, [c_uint64, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p]),
     "gem_query_midpoints": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "gem_knn_workspace_bytes": (c_int, [c_int64, c_int, c_int64, c_int, POINTER(c_size_t)]),
-    "gem_knn_midpoints": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_int, c_int,
+    "gem_knn_midpoints": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_int, c_int, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "gem_knn_linegraph_hint": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int,
+                                       c_void_p, c_void_p]),
     "gem_knn_midpoints_exact": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_int, c_int,
                                         c_void_p, c_void_p, c_void_p]),
+    "gem_knn_debug_stats": (c_int, [c_int, c_int64, c_int, c_int64, c_int, POINTER(c_size_t), POINTER(c_size_t),
+                                    POINTER(c_size_t), POINTER(c_int), POINTER(c_int)]),
     "gem_topk_merge": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "gem_intersection_forces": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64,
                                         c_int, c_float, c_void_p, c_void_p]),

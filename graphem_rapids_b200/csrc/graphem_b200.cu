@@ -52,6 +52,7 @@ struct StageTimer {
     void mark() { if (n <= GEM_NUM_STAGES) cudaEventRecord(ev[n++], st); }
 };
 thread_local StageTimer *g_timer = nullptr;
+bool g_knn_stats = false;       // gem_knn_debug_stats(): count filter passes / inserts of the scan
 inline void stage_mark() { if (g_timer) g_timer->mark(); }
 
 // ------------------------------------------------------------------------------------------
@@ -350,37 +351,50 @@ __global__ void __launch_bounds__(kThreads) knn_exact_kernel(const float *__rest
 }
 
 // ---- fast path ------------------------------------------------------------------------------
-// phase 1  knn_bound_kernel   : per (CTA chunk, query) minimum exact d2 over a sample of the CTA's range
-// phase 1b knn_threshold_kernel: tau_q = (k+1)-th smallest chunk minimum  -> valid upper bound of the
-//                               (k+1)-th neighbour distance; theta_q = conservative filter threshold
-// phase 2  knn_scan_kernel    : all pairs, 3 FFMA + 1 FSETP each; rare exact re-check + append
-// phase 3  knn_select_kernel  : exact top-(k+1) by (distance, index) among the appended candidates
+// phase 1  knn_bound_kernel    : per (CTA, query) minimum exact d2 over the CTA's first tiles
+// phase 1b knn_threshold_kernel: tau_q = (k+1)-th smallest CTA minimum -> a valid upper bound of the
+//                                (k+1)-th neighbour distance; theta_q = conservative filter threshold
+// phase 2  knn_scan_kernel     : all pairs, d FFMA + 1 FSETP each; the rare passes are re-checked in
+//                                the exact cdist chain and inserted into a per-CTA top-(k+1) list in
+//                                shared memory whose worst key tightens the filter (bounded work even
+//                                when the bound is poor or thousands of distances tie at zero)
+// phase 3  knn_select_kernel   : exact top-(k+1) by (distance, index) among <= G*(k+1) survivors
 constexpr int kQ = 8;                       // queries per lane -> 256 queries per warp pass
 constexpr int kQB = 32 * kQ;                // query block
-constexpr int kTile = 2048;                 // candidates per smem stage
-constexpr int kStages = 3;
+constexpr int kTile = 512;                  // candidates per smem stage
+constexpr int kStages = 4;
 constexpr float kSlack = 3.814697265625e-06f;   // 2^-18, see DESIGN.md (filter error budget)
 constexpr int kSurvMax = 1024;
+constexpr int kMaxFastKp1 = 64;
 
 __device__ __forceinline__ void cand_xyzn(const float4 &c, float &x, float &y, float &z, float &n) { x = c.x; y = c.y; z = c.z; n = c.w; }
 __device__ __forceinline__ void cand_xyzn(const float2 &c, float &x, float &y, float &z, float &n) { x = c.x; y = c.y; z = 0.f; n = c.x * c.x + c.y * c.y; }
 
-// candidate range of scan CTA b out of g over e candidates (even boundaries for 8-byte rows)
-template <int D> __device__ __forceinline__ void cta_range(int64_t e, int b, int g, int64_t &lo, int64_t &hi) {
-    lo = (e * b) / g; hi = (e * (b + 1)) / g;
-    if (D == 2) { lo &= ~(int64_t)1; if (b + 1 < g) hi &= ~(int64_t)1; }
+// conservative filter threshold for "distance <= ta": with U = largest fp32 whose sqrt_rn is <= ta,
+//   fma(a0,y0,fma(a1,y1,fma(a2,y2,yn*(1-c)))) <= U - qn + c*qn      (right side rounded up)
+// holds for every candidate whose exact chain distance is <= ta (error budget: DESIGN.md).
+__device__ __forceinline__ float filter_threshold(float ta, float qn) {
+    if (!(ta < kInf)) return kInf;
+    float u = __fmul_rn(ta, ta);
+    for (int it = 0; it < 8 && __fsqrt_rn(u) > ta; ++it) u = __uint_as_float(__float_as_uint(u) - 1);
+    for (int it = 0; it < 8; ++it) {
+        const float un = __uint_as_float(__float_as_uint(u) + 1);
+        if (__fsqrt_rn(un) <= ta) u = un; else break;
+    }
+    float th = __fadd_ru(__fsub_ru(u, qn), __fmul_ru(kSlack, qn));
+    return __fadd_ru(th, 1e-37f);
 }
 
 template <int D>
 __global__ void __launch_bounds__(kThreads) knn_bound_kernel(const typename MidT<D>::T *__restrict__ mid, int64_t e,
                                                              const float *__restrict__ qmid, int s,
-                                                             int64_t sample_per_cta, float *__restrict__ chunkmin) {
+                                                             int tiles_per_cta, float *__restrict__ chunkmin) {
+    using CandT = typename MidT<D>::T;
     __shared__ float red[kWarps][kQB];
+    __shared__ __align__(16) CandT tile[kTile];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = gridDim.x;
-    int64_t lo, hi;
-    cta_range<D>(e, blockIdx.x, g, lo, hi);
-    const int64_t m = min(hi - lo, sample_per_cta);
+    const int64_t ntiles = (e + kTile - 1) / kTile;
     for (int qb = 0; qb * kQB < s; ++qb) {
         QueryPar qp[kQ];
         float best[kQ];
@@ -390,11 +404,23 @@ __global__ void __launch_bounds__(kThreads) knn_bound_kernel(const typename MidT
             qp[i] = load_query<D>(qmid, q < s ? q : 0);
             best[i] = kInf;
         }
-        for (int64_t c = lo + warp; c < lo + m; c += kWarps) {
-            float x, y, z, n;
-            cand_xyzn(__ldg(mid + c), x, y, z, n);
+        for (int j = 0; j < tiles_per_cta; ++j) {
+            // stratified sample: CTA b looks at tiles_per_cta consecutive tiles starting at b/g of the
+            // index range (NOT the scan's interleaving: its first g tiles are the lowest-index edges,
+            // i.e. the hub edges of a preferential-attachment graph -- a hopelessly biased sample)
+            const int64_t t = ((int64_t)blockIdx.x * ntiles) / g + j;
+            if (t >= ntiles || (blockIdx.x + 1 < g && t >= ((int64_t)(blockIdx.x + 1) * ntiles) / g)) break;
+            const int64_t base = t * kTile;
+            const int cnt = (int)min((int64_t)kTile, e - base);
+            __syncthreads();
+            for (int c = threadIdx.x; c < cnt; c += kThreads) tile[c] = __ldg(mid + base + c);
+            __syncthreads();
+            for (int c = warp; c < cnt; c += kWarps) {
+                float x, y, z, n;
+                cand_xyzn(tile[c], x, y, z, n);
 #pragma unroll
-            for (int i = 0; i < kQ; ++i) best[i] = fminf(best[i], chain_mm(qp[i], x, y, z, n, D));
+                for (int i = 0; i < kQ; ++i) best[i] = fminf(best[i], chain_mm(qp[i], x, y, z, n, D));
+            }
         }
 #pragma unroll
         for (int i = 0; i < kQ; ++i) red[warp][i * 32 + lane] = best[i];
@@ -410,42 +436,115 @@ __global__ void __launch_bounds__(kThreads) knn_bound_kernel(const typename MidT
     }
 }
 
-// one CTA per query; g <= 1024 chunk minima
+// Line-graph bound: the edges incident to the endpoints (u,v) of a query edge are distinct
+// candidates whose midpoints tend to be its nearest neighbours in a force-directed layout (and they
+// are clustered in index space, which the strided chunk sample cannot see).  hint_q = the (k+1)-th
+// smallest exact cdist-chain distance among up to 2*kLgMax of them: at least k+1 candidates lie
+// within hint_q, so it is a valid upper bound of the (k+1)-th neighbour distance.  One warp per query.
+constexpr int kLgPerLane = 8;
+constexpr int kLgMax = 16 * kLgPerLane;              // neighbours examined per endpoint
 template <int D>
-__global__ void __launch_bounds__(1024) knn_threshold_kernel(const float *__restrict__ chunkmin, int g, int kp1,
-                                                             const float *__restrict__ qmid,
-                                                             float *__restrict__ theta, float *__restrict__ tau) {
-    __shared__ float vals[1024];
-    __shared__ float s_kth;
-    const int q = blockIdx.x, t = threadIdx.x;
-    if (t < g) vals[t] = chunkmin[(int64_t)q * g + t];
-    if (t == 0) s_kth = kInf;
-    __syncthreads();
-    if (t < g && kp1 <= g) {
-        const float v = vals[t];
-        int r = 0;
-        for (int u = 0; u < g; ++u) { const float w = vals[u]; r += (w < v) || (w == v && u < t); }
-        if (r == kp1 - 1) s_kth = v;
-    }
-    __syncthreads();
-    if (t == 0) {
-        const float kth = s_kth;                          // exact chain value (not clamped)
-        float th = kInf, ta = kInf;
-        if (kth < kInf) {                                 // (NaN also fails -> inf thresholds -> exact fallback)
-            ta = __fsqrt_rn(fmaxf(kth, 0.f)) + 0.f;
-            // U = largest fp32 x with sqrt_rn(x) <= ta
-            float u = __fmul_rn(ta, ta);
-            for (int it = 0; it < 8 && __fsqrt_rn(u) > ta; ++it) u = __uint_as_float(__float_as_uint(u) - 1);
-            for (int it = 0; it < 8; ++it) {
-                const float un = __uint_as_float(__float_as_uint(u) + 1);
-                if (__fsqrt_rn(un) <= ta) u = un; else break;
+__global__ void __launch_bounds__(kThreads) knn_linegraph_hint_kernel(const float *__restrict__ pos,
+                                                                      const int64_t *__restrict__ row_ptr,
+                                                                      const int32_t *__restrict__ col,
+                                                                      const int2 *__restrict__ edges,
+                                                                      const int64_t *__restrict__ samp, int s, int kp1,
+                                                                      float *__restrict__ hint) {
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    if (q >= s) return;
+    const int2 ed = edges[samp[q]];
+    const Vec<D> mq = (Vec<D>::load(pos, ed.x) + Vec<D>::load(pos, ed.y)) / 2.0f;
+    QueryPar qp;
+    qp.a0 = -2.f * mq.x; qp.a1 = -2.f * mq.y;
+    if (D == 3) { const Vec<3> &m3 = reinterpret_cast<const Vec<3> &>(mq); qp.a2 = -2.f * m3.z; } else qp.a2 = 0.f;
+    qp.qn = (D == 3) ? sqsum(reinterpret_cast<const Vec<3> &>(mq)) : sqsum(reinterpret_cast<const Vec<2> &>(mq));
+    float v[kLgPerLane];
+#pragma unroll
+    for (int j = 0; j < kLgPerLane; ++j) v[j] = kInf;
+    // lanes 0-15 walk u's row, lanes 16-31 walk v's row; the edge (u,v) itself is counted once (from u)
+    const int side = lane >> 4, sl = lane & 15;
+    const int a = side ? ed.y : ed.x, other = side ? ed.x : ed.y;
+    const int64_t r0 = row_ptr[a];
+    const int deg = (int)min(row_ptr[a + 1] - r0, (int64_t)kLgMax);
+#pragma unroll
+    for (int j = 0; j < kLgPerLane; ++j) {
+        const int t = j * 16 + sl;
+        if (t < deg) {
+            const int w = col[r0 + t];
+            if (!(side == 1 && w == other)) {
+                const Vec<D> m = (Vec<D>::load(pos, min(a, w)) + Vec<D>::load(pos, max(a, w))) / 2.0f;
+                float x, y, z, n;
+                cand_xyzn(make_mid(m), x, y, z, n);
+                const float d2 = chain_mm(qp, x, y, z, n, D);
+                v[j] = (d2 == d2) ? d2 : kInf;
             }
-            const QueryPar qp = load_query<D>(qmid, q);
-            // filter: fma(a0,y0,fma(a1,y1,fma(a2,y2,yn*(1-c)))) <= U - qn + c*qn   (rounded up)
-            th = __fadd_ru(__fsub_ru(u, qp.qn), __fmul_ru(kSlack, qp.qn));
-            th = __fadd_ru(th, 1e-37f);
         }
-        theta[q] = th;
+    }
+    float kth = kInf;
+    for (int r = 0; r < kp1; ++r) {
+        float m = v[0];
+#pragma unroll
+        for (int j = 1; j < kLgPerLane; ++j) m = fminf(m, v[j]);
+        float wm = m;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) wm = fminf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+        kth = wm;
+        if (!(wm < kInf)) break;
+        const unsigned holders = __ballot_sync(0xffffffffu, m == wm);
+        if (lane == __ffs(holders) - 1) {
+            bool done = false;
+#pragma unroll
+            for (int j = 0; j < kLgPerLane; ++j)
+                if (!done && v[j] == wm) { v[j] = kInf; done = true; }
+        }
+    }
+    if (lane == 0) hint[q] = (kth < kInf) ? __fsqrt_rn(fmaxf(kth, 0.f)) + 0.f : kInf;
+}
+
+// one warp per query: (k+1)-th smallest of g <= 1024 chunk minima by repeated min extraction
+template <int D>
+__global__ void __launch_bounds__(kThreads) knn_threshold_kernel(const float *__restrict__ chunkmin, int g, int kp1,
+                                                                 const float *__restrict__ qmid, int s,
+                                                                 const float *__restrict__ hint,
+                                                                 float *__restrict__ theta, float *__restrict__ tau) {
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    if (q >= s) return;
+    float v[32];                                   // g <= 1024
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const int u = j * 32 + lane;
+        const float x = (u < g) ? chunkmin[(int64_t)q * g + u] : kInf;
+        v[j] = (x == x) ? x : kInf;                // NaN -> +inf
+    }
+    float kth = kInf;
+    if (kp1 <= g) {
+        for (int r = 0; r < kp1; ++r) {
+            float m = v[0];
+#pragma unroll
+            for (int j = 1; j < 32; ++j) m = fminf(m, v[j]);
+            float wm = m;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) wm = fminf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+            kth = wm;
+            // the first lane holding wm removes one copy of it
+            const unsigned holders = __ballot_sync(0xffffffffu, m == wm);
+            if (holders == 0) break;               // only +inf left
+            if (lane == __ffs(holders) - 1) {
+                bool done = false;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (!done && v[j] == wm) { v[j] = kInf; done = true; }
+            }
+        }
+    }
+    if (lane == 0) {
+        float ta = kInf;
+        if (kth < kInf) ta = __fsqrt_rn(fmaxf(kth, 0.f)) + 0.f;
+        if (hint != nullptr) ta = fminf(ta, hint[q]);     // caller-provided bound (line-graph neighbours)
+        const QueryPar qp = load_query<D>(qmid, q);
+        theta[q] = filter_threshold(ta, qp.qn);
         tau[q] = ta;
     }
 }
@@ -474,25 +573,54 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// dynamic shared memory of the scan: [tiles kStages*kTile CandT][lists kQB*kp1 u64][bound kQB u64]
+//                                    [ltheta kQB f32][lqn kQB f32][lcount kQB i32][lock kQB i32][wslot kQB i32]
+__host__ __device__ inline size_t scan_smem_bytes(int cand_bytes, int kp1) {
+    return (size_t)kStages * kTile * cand_bytes + (size_t)kQB * kp1 * 8 + (size_t)kQB * 8 + (size_t)kQB * 4 * 5;
+}
+
 template <int D>
 __global__ void __launch_bounds__(kThreads, 2) knn_scan_kernel(const typename MidT<D>::T *__restrict__ mid, int64_t e,
-                                                               const float *__restrict__ qmid, int s,
+                                                               const float *__restrict__ qmid, int s, int kp1,
                                                                const float *__restrict__ theta,
                                                                const float *__restrict__ tau,
                                                                uint32_t *__restrict__ counts,
-                                                               uint64_t *__restrict__ keys, int cap) {
+                                                               uint64_t *__restrict__ keys, int cap,
+                                                               unsigned long long *__restrict__ stats) {
     using CandT = typename MidT<D>::T;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     CandT *tiles = reinterpret_cast<CandT *>(smem_raw);
+    uint64_t *lists = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kStages * kTile * sizeof(CandT));
+    volatile uint64_t *bound = lists + (size_t)kQB * kp1;        // accept iff key < bound[q]
+    volatile float *ltheta = reinterpret_cast<volatile float *>(const_cast<uint64_t *>(bound) + kQB);
+    float *lqn = const_cast<float *>(ltheta) + kQB;
+    int *lcount = reinterpret_cast<int *>(lqn + kQB);
+    int *lock = lcount + kQB;
+    int *wslot = lock + kQB;
     __shared__ __align__(8) uint64_t full_bar[kStages];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int qb = blockIdx.y;
-    int64_t lo, hi;
-    cta_range<D>(e, blockIdx.x, gridDim.x, lo, hi);
-    const int ntiles = (int)((hi - lo + kTile - 1) / kTile);
+    const int g = gridDim.x;
+    const int64_t ntiles_all = (e + kTile - 1) / kTile;
+    // interleaved tiles: CTA b owns tiles b, b+g, b+2g, ...
+    const int ntiles = (int)((ntiles_all > blockIdx.x) ? (ntiles_all - blockIdx.x + g - 1) / g : 0);
 
-    // per-lane query block: a = -2q and the filter threshold
+    // per-query state of this CTA
+    {
+        const int q = qb * kQB + threadIdx.x;
+        float ta = -1.f, th = -kInf, qn = 0.f;
+        if (q < s) { ta = tau[q]; th = theta[q]; qn = load_query<D>(qmid, q).qn; }
+        // initial bound: every key whose distance is <= tau  (key < (tau_bits+1) << 32)
+        const uint64_t b0 = (q < s) ? (((uint64_t)__float_as_uint(ta) + 1ull) << 32) : 0ull;
+        bound[threadIdx.x] = b0;
+        ltheta[threadIdx.x] = th;
+        lqn[threadIdx.x] = qn;
+        lcount[threadIdx.x] = 0;
+        lock[threadIdx.x] = 0;
+        wslot[threadIdx.x] = 0;
+    }
+
     float a0[kQ], a1[kQ], a2[kQ], th[kQ];
 #pragma unroll
     for (int i = 0; i < kQ; ++i) {
@@ -505,8 +633,8 @@ __global__ void __launch_bounds__(kThreads, 2) knn_scan_kernel(const typename Mi
 
     auto issue = [&](int t) {                               // thread 0 only
         if (t >= ntiles) return;
-        const int64_t base = lo + (int64_t)t * kTile;
-        const int cnt = (int)min((int64_t)kTile, hi - base);
+        const int64_t base = ((int64_t)blockIdx.x + (int64_t)t * g) * kTile;
+        const int cnt = (int)min((int64_t)kTile, e - base);
         CandT *dst = tiles + (t % kStages) * kTile;
         int cnt_tma = cnt;
         if (sizeof(CandT) == 8 && (cnt & 1)) {              // keep the bulk size a multiple of 16 B
@@ -530,9 +658,12 @@ __global__ void __launch_bounds__(kThreads, 2) knn_scan_kernel(const typename Mi
 
     for (int it = 0; it < ntiles; ++it) {
         if (threadIdx.x == 0) issue(it + kStages - 1);      // stage freed by the barrier closing it-1
+        // pick up thresholds tightened by other warps
+#pragma unroll
+        for (int i = 0; i < kQ; ++i) th[i] = fminf(th[i], ltheta[i * 32 + lane]);
         mbar_wait(&full_bar[it % kStages], (uint32_t)((it / kStages) & 1));
-        const int64_t base = lo + (int64_t)it * kTile;
-        const int cnt = (int)min((int64_t)kTile, hi - base);
+        const int64_t base = ((int64_t)blockIdx.x + (int64_t)it * g) * kTile;
+        const int cnt = (int)min((int64_t)kTile, e - base);
         const CandT *tile = tiles + (it % kStages) * kTile;
 #pragma unroll 2
         for (int c = warp; c < cnt; c += kWarps) {
@@ -548,78 +679,116 @@ __global__ void __launch_bounds__(kThreads, 2) knn_scan_kernel(const typename Mi
                 any |= (f[i] <= th[i]);
             }
             if (any) {                                      // rare: exact re-check in cdist arithmetic
+                if (stats && lane == 0) atomicAdd(stats + 3, 1ull);
 #pragma unroll
                 for (int i = 0; i < kQ; ++i) {
                     if (f[i] <= th[i]) {
-                        const int q = qb * kQB + i * 32 + lane;
-                        const QueryPar p = load_query<D>(qmid, q);
+                        const int ql = i * 32 + lane;       // query slot in this CTA (a lane owns its slots)
+                        QueryPar p;
+                        p.a0 = a0[i]; p.a1 = a1[i]; p.a2 = a2[i]; p.qn = lqn[ql];
                         const uint64_t key = make_key(chain_mm(p, x, y, z, n, D), (uint32_t)(base + c));
-                        if (key_dist(key) <= tau[q]) {
-                            const uint32_t slot = atomicAdd(counts + q, 1u);
-                            if (slot < (uint32_t)cap) keys[(int64_t)q * cap + slot] = key;
+                        bool pending = key < bound[ql];
+                        if (stats) atomicAdd(stats + (pending ? 1 : 0), 1ull);
+                        while (pending) {                   // canonical SIMT-safe lock: work inside the loop
+                            if (atomicCAS(&lock[ql], 0, 1) == 0) {
+                                __threadfence_block();
+                                if (key < bound[ql]) {
+                                    uint64_t *lst = lists + (size_t)ql * kp1;
+                                    const int nl = lcount[ql];
+                                    if (nl < kp1) {
+                                        lst[nl] = key;
+                                        lcount[ql] = nl + 1;
+                                    } else {
+                                        lst[wslot[ql]] = key;   // replace the current worst
+                                    }
+                                    if (nl + 1 >= kp1) {        // list full: its worst key becomes the bound
+                                        uint64_t worst = lst[0];
+                                        int ws = 0;
+                                        for (int u = 1; u < kp1; ++u) {
+                                            const uint64_t ku = lst[u];
+                                            if (ku > worst) { worst = ku; ws = u; }
+                                        }
+                                        wslot[ql] = ws;
+                                        bound[ql] = worst;
+                                        ltheta[ql] = fminf(ltheta[ql], filter_threshold(key_dist(worst), p.qn));
+                                    }
+                                    if (stats) atomicAdd(stats + 2, 1ull);
+                                }
+                                __threadfence_block();
+                                atomicExch(&lock[ql], 0);
+                                pending = false;
+                            }
                         }
+                        th[i] = fminf(th[i], ltheta[ql]);
                     }
                 }
             }
         }
         __syncthreads();
     }
+    // publish this CTA's survivors: at most kp1 per query, so counts[q] <= gridDim.x * kp1 <= cap
+    {
+        const int q = qb * kQB + threadIdx.x;
+        const int nl = lcount[threadIdx.x];
+        if (q < s && nl > 0) {
+            const uint32_t slot = atomicAdd(counts + q, (uint32_t)nl);
+            const uint64_t *lst = lists + (size_t)threadIdx.x * kp1;
+            for (int u = 0; u < nl; ++u)
+                if (slot + u < (uint32_t)cap) keys[(int64_t)q * cap + slot + u] = lst[u];
+        }
+    }
 }
 
-// per query: exact top-kp1 among n = counts[q] appended keys (unique); n > cap or too many
-// survivors -> flags[q] = 1 (exact fallback kernel recomputes that query)
+// per query: exact top-kp1 among n = counts[q] <= cap published keys (unique)
 __global__ void __launch_bounds__(kThreads) knn_select_kernel(const uint32_t *__restrict__ counts,
                                                               const uint64_t *__restrict__ keys, int cap, int kp1,
-                                                              int64_t idx_offset, uint32_t *__restrict__ flags,
-                                                              int64_t *__restrict__ out_idx, float *__restrict__ out_dist) {
+                                                              int64_t idx_offset, int64_t *__restrict__ out_idx,
+                                                              float *__restrict__ out_dist) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *all = reinterpret_cast<uint64_t *>(smem_raw);        // cap
     __shared__ uint64_t sub[kThreads];
-    __shared__ uint64_t surv[kSurvMax];
     __shared__ uint64_t s_thr;
     __shared__ int s_nsurv;
     const int q = blockIdx.x, t = threadIdx.x;
-    const uint32_t nraw = counts[q];
-    if (nraw > (uint32_t)cap || nraw < (uint32_t)kp1) {             // overflow (or inconsistent): exact fallback
-        if (t == 0) flags[q] = 1;
-        return;
-    }
-    const int n = (int)nraw;
+    int n = (int)min(counts[q], (uint32_t)cap);
     for (int i = t; i < n; i += kThreads) all[i] = keys[(int64_t)q * cap + i];
-    if (t == 0) { s_thr = ~0ull; s_nsurv = 0; }
+    // a hinted (shard-local) search may find fewer than kp1 candidates: pad with (+inf, -1)
+    for (int r = n + t; r < kp1; r += kThreads) { out_idx[(int64_t)q * kp1 + r] = -1; out_dist[(int64_t)q * kp1 + r] = kInf; }
     __syncthreads();
-    // level 1: threshold from a strided subsample of m <= 256 keys
-    const int stride = (n + kThreads - 1) / kThreads;
-    const int m = (n + stride - 1) / stride;
-    if (stride > 1 && m >= kp1) {
+    // shrink by strided-subsample thresholds until direct rank counting is cheap
+    while (n > kSurvMax || (n > 2 * kThreads && n > 8 * kp1)) {
+        const int stride = (n + kThreads - 1) / kThreads;
+        const int m = (n + stride - 1) / stride;
+        if (m < kp1) break;
+        if (t == 0) { s_thr = ~0ull; s_nsurv = 0; }
         if (t < m) sub[t] = all[t * stride];
         __syncthreads();
         if (t < m) {
             const uint64_t k = sub[t];
             int r = 0;
             for (int u = 0; u < m; ++u) r += sub[u] < k;
-            if (r == kp1 - 1) s_thr = k;
+            if (r == kp1 - 1) s_thr = k;                 // kp1 sampled keys are <= k: a valid bound
         }
         __syncthreads();
+        const uint64_t thr = s_thr;
+        // in-place stable compaction, chunk by chunk (reads of a chunk complete before its writes)
+        for (int b0 = 0; b0 < n; b0 += kThreads) {
+            const int i = b0 + t;
+            const uint64_t k = (i < n) ? all[i] : ~0ull;
+            const bool keep = (i < n) && (k <= thr);
+            __syncthreads();
+            if (keep) all[atomicAdd(&s_nsurv, 1)] = k;   // s_nsurv <= b0 at this point: never overtakes unread data
+            __syncthreads();
+        }
+        const int ns = s_nsurv;
+        __syncthreads();
+        if (ns >= n) break;                              // no progress (cannot happen with unique keys)
+        n = ns;
     }
-    const uint64_t thr = s_thr;
     for (int i = t; i < n; i += kThreads) {
         const uint64_t k = all[i];
-        if (k <= thr) {
-            const int slot = atomicAdd(&s_nsurv, 1);
-            if (slot < kSurvMax) surv[slot] = k;
-        }
-    }
-    __syncthreads();
-    const int ns = s_nsurv;
-    if (ns > kSurvMax) {
-        if (t == 0) flags[q] = 1;
-        return;
-    }
-    for (int i = t; i < ns; i += kThreads) {
-        const uint64_t k = surv[i];
         int r = 0;
-        for (int u = 0; u < ns; ++u) r += surv[u] < k;
+        for (int u = 0; u < n; ++u) r += all[u] < k;
         if (r < kp1) {
             out_idx[(int64_t)q * kp1 + r] = idx_offset + (int64_t)(uint32_t)k;
             out_dist[(int64_t)q * kp1 + r] = key_dist(k);
@@ -954,10 +1123,10 @@ inline int grid_for(int64_t work, int per_sm) {
 // ---- KNN fast path plumbing -------------------------------------------------------------------
 struct KnnLayout {
     int g;                  // scan CTAs over the candidate axis (= chunks of the bound pass)
-    int cap;                // appended candidates kept per query
-    int64_t sample_per_cta; // bound-pass sample per CTA
+    int cap;                // published candidates kept per query  (>= g * kp1: cannot overflow)
+    int tiles_per_cta;      // bound-pass tiles per CTA
     int64_t sb;             // queries per batch
-    size_t off_chunkmin, off_theta, off_tau, off_counts, off_flags, off_keys, total;
+    size_t off_chunkmin, off_theta, off_tau, off_counts, off_stats, off_keys, total;
 };
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -965,23 +1134,23 @@ KnnLayout knn_layout(int64_t e, int64_t s, int kp1) {
     KnnLayout L;
     L.g = 2 * num_sms();
     if (L.g > 1024) L.g = 1024;
-    int64_t m = e / 32;
-    if (m < 8192) m = 8192;
-    if (m > 262144) m = 262144;
-    if (m > e) m = e;
-    L.sample_per_cta = (m + L.g - 1) / L.g;
-    const double expect = (double)kp1 * (double)e / (double)(L.sample_per_cta * L.g) * 1.25 + kp1;
-    int cap = 2048;
-    while (cap < 6.0 * expect && cap < 8192) cap *= 2;
+    const int64_t ntiles = (e + kTile - 1) / kTile;
+    // sample ~1/32 of the candidates (at least one tile per CTA, at most 16)
+    int64_t tps = ntiles / ((int64_t)32 * L.g);
+    if (tps < 1) tps = 1;
+    if (tps > 16) tps = 16;
+    L.tiles_per_cta = (int)tps;
+    int cap = (L.g * kp1 + 255) / 256 * 256;          // every CTA publishes at most kp1 keys per query
+    if (cap < 1024) cap = 1024;
     L.cap = cap;
-    L.sb = s < 2048 ? s : 2048;
+    L.sb = s < 1024 ? s : 1024;
     if (L.sb < 1) L.sb = 1;
     size_t o = 0;
     L.off_chunkmin = o; o = align_up(o + (size_t)L.sb * L.g * sizeof(float), 256);
     L.off_theta = o;    o = align_up(o + (size_t)L.sb * sizeof(float), 256);
     L.off_tau = o;      o = align_up(o + (size_t)L.sb * sizeof(float), 256);
     L.off_counts = o;   o = align_up(o + (size_t)L.sb * sizeof(uint32_t), 256);
-    L.off_flags = o;    o = align_up(o + (size_t)L.sb * sizeof(uint32_t), 256);
+    L.off_stats = o;    o = align_up(o + 8 * sizeof(unsigned long long), 256);
     L.off_keys = o;     o = align_up(o + (size_t)L.sb * L.cap * sizeof(uint64_t), 256);
     L.total = o;
     return L;
@@ -989,7 +1158,7 @@ KnnLayout knn_layout(int64_t e, int64_t s, int kp1) {
 
 template <int D>
 int knn_fast(const float *mid, int64_t e, int64_t idx_offset, const float *qmid, int64_t s, int kp1,
-             int64_t *out_idx, float *out_dist, void *ws, size_t ws_bytes, cudaStream_t st) {
+             const float *tau_hint, int64_t *out_idx, float *out_dist, void *ws, size_t ws_bytes, cudaStream_t st) {
     using CandT = typename MidT<D>::T;
     const KnnLayout L = knn_layout(e, s, kp1);
     if (ws == nullptr || ws_bytes < L.total || ((uintptr_t)ws & 255)) return GEM_E_WORKSPACE;
@@ -999,39 +1168,33 @@ int knn_fast(const float *mid, int64_t e, int64_t idx_offset, const float *qmid,
     float *theta = reinterpret_cast<float *>(w + L.off_theta);
     float *tau = reinterpret_cast<float *>(w + L.off_tau);
     uint32_t *counts = reinterpret_cast<uint32_t *>(w + L.off_counts);
-    uint32_t *flags = reinterpret_cast<uint32_t *>(w + L.off_flags);
     uint64_t *keys = reinterpret_cast<uint64_t *>(w + L.off_keys);
-    const size_t scan_smem = (size_t)kStages * kTile * sizeof(CandT);
+    const size_t scan_smem = scan_smem_bytes((int)sizeof(CandT), kp1);
     const size_t sel_smem = (size_t)L.cap * sizeof(uint64_t);
     const int mld = mid_pitch(D);
-    const size_t exact_smem = ((size_t)kp1 + kThreads) * sizeof(uint64_t) + (size_t)mld * sizeof(float);
-    int threshold_threads = 32;
-    while (threshold_threads < L.g) threshold_threads *= 2;
     for (int64_t q0 = 0; q0 < s; q0 += L.sb) {
         const int sb = (int)((s - q0) < L.sb ? (s - q0) : L.sb);
         const float *qm = qmid + q0 * mld;
         GEM_CUDA(cudaMemsetAsync(counts, 0, (size_t)sb * sizeof(uint32_t), st));
-        GEM_CUDA(cudaMemsetAsync(flags, 0, (size_t)sb * sizeof(uint32_t), st));
         knn_bound_kernel<D><<<L.g, kThreads, 0, st>>>(reinterpret_cast<const CandT *>(mid), e, qm, sb,
-                                                      L.sample_per_cta, chunkmin);
+                                                      L.tiles_per_cta, chunkmin);
         GEM_CHECK_LAUNCH();
         stage_mark();                                                   // GEM_STAGE_KNN_BOUND
-        knn_threshold_kernel<D><<<sb, threshold_threads, 0, st>>>(chunkmin, L.g, kp1, qm, theta, tau);
+        knn_threshold_kernel<D><<<(sb + kWarps - 1) / kWarps, kThreads, 0, st>>>(
+            chunkmin, L.g, kp1, qm, sb, tau_hint ? tau_hint + q0 : nullptr, theta, tau);
         GEM_CHECK_LAUNCH();
         stage_mark();                                                   // GEM_STAGE_KNN_THRESHOLD
         dim3 grid(L.g, (sb + kQB - 1) / kQB);
-        knn_scan_kernel<D><<<grid, kThreads, scan_smem, st>>>(reinterpret_cast<const CandT *>(mid), e, qm, sb, theta,
-                                                              tau, counts, keys, L.cap);
+        knn_scan_kernel<D><<<grid, kThreads, scan_smem, st>>>(reinterpret_cast<const CandT *>(mid), e, qm, sb, kp1,
+                                                              theta, tau, counts, keys, L.cap,
+                                                              g_knn_stats ? reinterpret_cast<unsigned long long *>(w + L.off_stats) : nullptr);
         GEM_CHECK_LAUNCH();
         stage_mark();                                                   // GEM_STAGE_KNN_SCAN
-        knn_select_kernel<<<sb, kThreads, sel_smem, st>>>(counts, keys, L.cap, kp1, idx_offset, flags,
+        knn_select_kernel<<<sb, kThreads, sel_smem, st>>>(counts, keys, L.cap, kp1, idx_offset,
                                                           out_idx + q0 * kp1, out_dist + q0 * kp1);
         GEM_CHECK_LAUNCH();
         stage_mark();                                                   // GEM_STAGE_KNN_SELECT
-        knn_exact_kernel<<<sb, kThreads, exact_smem, st>>>(mid, e, idx_offset, D, qm, kp1, 1, flags,
-                                                           out_idx + q0 * kp1, out_dist + q0 * kp1);
-        GEM_CHECK_LAUNCH();
-        stage_mark();                                                   // GEM_STAGE_KNN_FALLBACK
+        stage_mark();                                                   // GEM_STAGE_KNN_FALLBACK (none needed)
     }
     return GEM_OK;
 }
@@ -1058,10 +1221,10 @@ int gem_init(void) {
     g_num_sms = 0;
     (void)num_sms();
     GEM_CUDA(cudaFuncSetAttribute(knn_scan_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(kStages * kTile * sizeof(float2))));
+                                  (int)scan_smem_bytes(8, kMaxFastKp1)));
     GEM_CUDA(cudaFuncSetAttribute(knn_scan_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(kStages * kTile * sizeof(float4))));
-    GEM_CUDA(cudaFuncSetAttribute(knn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
+                                  (int)scan_smem_bytes(16, kMaxFastKp1)));
+    GEM_CUDA(cudaFuncSetAttribute(knn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     return GEM_OK;
 }
 
@@ -1121,6 +1284,21 @@ int gem_knn_workspace_bytes(int64_t e, int d, int64_t s, int kp1, size_t *bytes)
     return GEM_OK;
 }
 
+int gem_knn_debug_stats(int enable, int64_t e, int d, int64_t s, int kp1, size_t *stats_offset, size_t *counts_offset,
+                        size_t *tau_offset, int *cap, int *g) {
+    g_knn_stats = enable != 0;
+    if (e > 0 && s > 0 && kp1 > 0) {
+        const KnnLayout L = knn_layout(e, s, kp1);
+        if (stats_offset) *stats_offset = L.off_stats;
+        if (counts_offset) *counts_offset = L.off_counts;
+        if (tau_offset) *tau_offset = L.off_tau;
+        if (cap) *cap = L.cap;
+        if (g) *g = L.g;
+    }
+    (void)d;
+    return GEM_OK;
+}
+
 int gem_knn_midpoints_exact(const float *mid, int64_t e, int64_t idx_offset, int d, const float *qmid, int64_t s,
                             int kp1, int mm_mode, int64_t *out_idx, float *out_dist, void *stream) {
     if (!mid || !qmid || !out_idx || !out_dist || e <= 0 || s <= 0 || d <= 0 || kp1 <= 0) return GEM_E_BADARG;
@@ -1134,13 +1312,27 @@ int gem_knn_midpoints_exact(const float *mid, int64_t e, int64_t idx_offset, int
     return GEM_OK;
 }
 
+int gem_knn_linegraph_hint(const float *pos, const int64_t *row_ptr, const int32_t *col, const int32_t *edges,
+                           const int64_t *samp, int64_t s, int d, int kp1, float *tau_hint, void *stream) {
+    if (!pos || !row_ptr || !col || !edges || !samp || !tau_hint || s <= 0 || kp1 <= 0) return GEM_E_BADARG;
+    if (d != 2 && d != 3) return GEM_E_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int2 *ed = reinterpret_cast<const int2 *>(edges);
+    const int grid = (int)((s + kWarps - 1) / kWarps);
+    if (d == 2) knn_linegraph_hint_kernel<2><<<grid, kThreads, 0, st>>>(pos, row_ptr, col, ed, samp, (int)s, kp1, tau_hint);
+    else knn_linegraph_hint_kernel<3><<<grid, kThreads, 0, st>>>(pos, row_ptr, col, ed, samp, (int)s, kp1, tau_hint);
+    GEM_CHECK_LAUNCH();
+    return GEM_OK;
+}
+
 int gem_knn_midpoints(const float *mid, int64_t e, int64_t idx_offset, int d, const float *qmid, int64_t s, int kp1,
-                      int mm_mode, int64_t *out_idx, float *out_dist, void *ws, size_t ws_bytes, void *stream) {
+                      int mm_mode, const float *tau_hint, int64_t *out_idx, float *out_dist, void *ws, size_t ws_bytes,
+                      void *stream) {
     if (!mid || !qmid || !out_idx || !out_dist || e <= 0 || s <= 0 || d <= 0 || kp1 <= 0) return GEM_E_BADARG;
     if (kp1 > e) return GEM_E_KRANGE;
     const int mm = resolve_mm_mode(mm_mode, s, e);
     // tiny problems, generic d, direct-mode arithmetic and huge k go to the exact streaming kernel
-    if (!mm || (d != 2 && d != 3) || e < 2048 || kp1 > 512) {
+    if (!mm || (d != 2 && d != 3) || e < 2048 || kp1 > kMaxFastKp1) {
         for (int i = 0; i < 4; ++i) stage_mark();       // bound/threshold/scan/select are not run
         const int rc = gem_knn_midpoints_exact(mid, e, idx_offset, d, qmid, s, kp1, mm, out_idx, out_dist, stream);
         stage_mark();                                   // all of the KNN time lands in GEM_STAGE_KNN_FALLBACK
@@ -1148,8 +1340,8 @@ int gem_knn_midpoints(const float *mid, int64_t e, int64_t idx_offset, int d, co
     }
     if (e >= ((int64_t)1 << 32)) return GEM_E_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
-    return d == 2 ? knn_fast<2>(mid, e, idx_offset, qmid, s, kp1, out_idx, out_dist, ws, ws_bytes, st)
-                  : knn_fast<3>(mid, e, idx_offset, qmid, s, kp1, out_idx, out_dist, ws, ws_bytes, st);
+    return d == 2 ? knn_fast<2>(mid, e, idx_offset, qmid, s, kp1, tau_hint, out_idx, out_dist, ws, ws_bytes, st)
+                  : knn_fast<3>(mid, e, idx_offset, qmid, s, kp1, tau_hint, out_idx, out_dist, ws, ws_bytes, st);
 }
 
 int gem_topk_merge(const float *dists, const int64_t *idxs, int parts, int64_t s, int kp1, int64_t *out_idx,
@@ -1238,7 +1430,13 @@ int gem_layout_step(const gem_plan *p, void *stream) {
     rc = gem_query_midpoints(p->pos, p->edges, p->samp, p->s, p->d, p->qmid, stream);
     if (rc) return rc;
     stage_mark();                                                       // GEM_STAGE_QUERY_MID
-    rc = gem_knn_midpoints(p->mid, p->e, 0, p->d, p->qmid, p->s, p->kp1, p->mm_mode, p->knn_idx, p->knn_dist,
+    const float *hint = nullptr;
+    if (p->row_ptr && p->col && p->tau_hint && (p->d == 2 || p->d == 3)) {
+        rc = gem_knn_linegraph_hint(p->pos, p->row_ptr, p->col, p->edges, p->samp, p->s, p->d, p->kp1, p->tau_hint, stream);
+        if (rc) return rc;
+        hint = p->tau_hint;
+    }
+    rc = gem_knn_midpoints(p->mid, p->e, 0, p->d, p->qmid, p->s, p->kp1, p->mm_mode, hint, p->knn_idx, p->knn_dist,
                            p->knn_ws, p->knn_ws_bytes, stream);
     if (rc) return rc;
     if (p->kp1 > 1) {

@@ -105,6 +105,17 @@ class GraphEmbedderPyTorch:
             raise ValueError("graphem_rapids_b200 stores edge endpoints as int32: n must be < 2^31")
         self.edges = torch.tensor(edges, device=self.device, dtype=torch.long).reshape(-1, 2)   # :159
         self._edges32 = self.edges.to(torch.int32).contiguous()
+        # symmetric CSR of the graph (for the line-graph bound of the KNN)
+        if self.n_edges > 0:
+            e_np = np.asarray(edges, dtype=np.int64)
+            sym = sp.csr_matrix((np.ones(2 * len(e_np), dtype=np.int8),
+                                 (np.concatenate([e_np[:, 0], e_np[:, 1]]), np.concatenate([e_np[:, 1], e_np[:, 0]]))),
+                                shape=(self.n, self.n))
+            sym.sort_indices()
+            self._row_ptr = torch.from_numpy(sym.indptr.astype(np.int64)).to(self.device)
+            self._col = torch.from_numpy(sym.indices.astype(np.int32)).to(self.device)
+        else:
+            self._row_ptr = self._col = None
 
         self._has_pykeops = False                               # the PyKeOps branch (:247-258) is removed
         if self.batch_size is None:
@@ -229,6 +240,7 @@ class GraphEmbedderPyTorch:
             force=torch.zeros((self.n, self._ld), device=dev, dtype=f32),
             mid=torch.zeros((E + 1, self._mld), device=dev, dtype=f32),
             qmid=torch.zeros((max(S, 1), self._mld), device=dev, dtype=f32),
+            tau_hint=torch.zeros((max(S, 1),), device=dev, dtype=f32),
             samp=torch.zeros((max(S, 1),), device=dev, dtype=torch.long),
             knn_idx=torch.zeros((max(S, 1), kp1), device=dev, dtype=torch.long),
             knn_dist=torch.zeros((max(S, 1), kp1), device=dev, dtype=f32),
@@ -249,6 +261,9 @@ class GraphEmbedderPyTorch:
         p.seed = self._sampler_seed & (2 ** 64 - 1)
         p.pos = self._pos.data_ptr()
         p.edges = self._edges32.data_ptr()
+        p.row_ptr = self._row_ptr.data_ptr() if self._row_ptr is not None else None
+        p.col = self._col.data_ptr() if self._col is not None else None
+        p.tau_hint = b["tau_hint"].data_ptr()
         p.force = b["force"].data_ptr()
         p.mid = b["mid"].data_ptr()
         p.qmid = b["qmid"].data_ptr()
@@ -451,7 +466,7 @@ class GraphEmbedderPyTorch:
                 nbytes = ctypes.c_size_t(0)
                 _cabi.check(self._lib.gem_knn_workspace_bytes(nr, int(d), nq, int(k), ctypes.byref(nbytes)))
                 ws = torch.zeros((nbytes.value + 256,), device=self.device, dtype=torch.uint8)
-                _cabi.check(self._lib.gem_knn_midpoints(_ptr(rm), nr, 0, int(d), _ptr(qm), nq, int(k), -1, _ptr(idx),
+                _cabi.check(self._lib.gem_knn_midpoints(_ptr(rm), nr, 0, int(d), _ptr(qm), nq, int(k), -1, None, _ptr(idx),
                                                         _ptr(dist), _ptr(ws), nbytes.value, st), "gem_knn_midpoints")
         return (idx, dist) if return_distances else idx
 

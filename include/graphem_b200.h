@@ -79,13 +79,29 @@ int gem_query_midpoints(const float *pos, const int32_t *edges, const int64_t *s
  * gem_knn_workspace_bytes sizes `ws` (256-byte aligned). */
 int gem_knn_workspace_bytes(int64_t e, int d, int64_t s, int kp1, size_t *bytes);
 int gem_knn_midpoints(const float *mid, int64_t e, int64_t idx_offset, int d, const float *qmid,
-                      int64_t s, int kp1, int mm_mode, int64_t *out_idx, float *out_dist, void *ws,
-                      size_t ws_bytes, void *stream);
+                      int64_t s, int kp1, int mm_mode, const float *tau_hint, int64_t *out_idx,
+                      float *out_dist, void *ws, size_t ws_bytes, void *stream);
+/* Optional search radius per query for gem_knn_midpoints (tau_hint, may be NULL): only
+ * neighbours with distance <= tau_hint[q] are required.  gem_knn_linegraph_hint computes a valid
+ * one: the (k+1)-th smallest exact distance among the edges incident to the endpoints of the query
+ * edge (row_ptr (n+1) int64 / col int32 = symmetric CSR of the graph).  In a force-directed layout
+ * those are the true neighbours, and they are clustered in index space where a strided sample of
+ * the candidates cannot see them.  With a hint a shard-local search (multi-GPU) may return fewer
+ * than k+1 neighbours: short rows are padded with (distance +inf, index -1). */
+int gem_knn_linegraph_hint(const float *pos, const int64_t *row_ptr, const int32_t *col, const int32_t *edges,
+                           const int64_t *samp, int64_t s, int d, int kp1, float *tau_hint, void *stream);
 /* Same contract, single exact streaming kernel (one CTA per query); the slow, simple
  * implementation used as in-library cross-check and as overflow fallback. */
 int gem_knn_midpoints_exact(const float *mid, int64_t e, int64_t idx_offset, int d, const float *qmid,
                             int64_t s, int kp1, int mm_mode, int64_t *out_idx, float *out_dist,
                             void *stream);
+/* Diagnostics: enable/disable the scan's event counters and report where they live inside the KNN
+ * workspace (byte offsets): stats = 8 x uint64 {0: exact re-checks rejected by the key bound,
+ * 1: accepted for insertion, 2: list inserts, 3: warp-level slow-path entries}; counts = uint32 per
+ * query (survivors published); tau = fp32 per query.  The caller zeroes the stats words. */
+int gem_knn_debug_stats(int enable, int64_t e, int d, int64_t s, int kp1, size_t *stats_offset,
+                        size_t *counts_offset, size_t *tau_offset, int *cap, int *g);
+
 /* Merge `parts` partial lists (parts, s, kp1) into (s, kp1) by (distance, index): the
  * exchange step of the edge-sharded multi-GPU KNN (after an all-gather of the partial lists). */
 int gem_topk_merge(const float *dists, const int64_t *idxs, int parts, int64_t s, int kp1,
@@ -118,9 +134,12 @@ typedef struct gem_plan {
     uint64_t seed;
     float *pos;               /* (n, ld)   in/out */
     const int32_t *edges;     /* (e, 2) */
+    const int64_t *row_ptr;   /* (n+1) symmetric CSR offsets, or NULL (no line-graph bound) */
+    const int32_t *col;       /* (2e)  symmetric CSR columns, or NULL */
     float *force;             /* (n, ld)   scratch */
     float *mid;               /* (e, mld)  scratch */
     float *qmid;              /* (s, mld)  scratch */
+    float *tau_hint;          /* (s)       scratch, or NULL */
     int64_t *samp;            /* (s)       out: the sample used (or in, when external_sample) */
     int64_t *knn_idx;         /* (s, kp1)  out */
     float *knn_dist;          /* (s, kp1)  out */
