@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(kThreads) knn_exact_kernel(const float *__rest
 // phase 3  knn_select_kernel   : exact top-(k+1) by (distance, index) among <= G*(k+1) survivors
 constexpr int kQ = 8;                       // queries per lane -> 256 queries per warp pass
 constexpr int kQB = 32 * kQ;                // query block
-constexpr int kTile = 512;                  // candidates per smem stage
+constexpr int kTile = 768;                  // candidates per smem stage (multiple of 8 warps x 3-candidate groups)
 constexpr int kStages = 4;
 constexpr float kSlack = 3.814697265625e-06f;   // 2^-18, see DESIGN.md (filter error budget)
 constexpr int kSurvMax = 1024;
@@ -369,6 +369,13 @@ constexpr int kMaxFastKp1 = 64;
 
 __device__ __forceinline__ void cand_xyzn(const float4 &c, float &x, float &y, float &z, float &n) { x = c.x; y = c.y; z = c.z; n = c.w; }
 __device__ __forceinline__ void cand_xyzn(const float2 &c, float &x, float &y, float &z, float &n) { x = c.x; y = c.y; z = 0.f; n = c.x * c.x + c.y * c.y; }
+
+// 3-input minimum: one FMNMX3 on sm_100a (ptxas does not fuse fminf(fminf(a,b),c) by itself)
+__device__ __forceinline__ float min3f(float a, float b, float c) {
+    float d;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
 
 // conservative filter threshold for "distance <= ta": with U = largest fp32 whose sqrt_rn is <= ta,
 //   fma(a0,y0,fma(a1,y1,fma(a2,y2,yn*(1-c)))) <= U - qn + c*qn      (right side rounded up)
@@ -574,165 +581,231 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
 }
 
 // dynamic shared memory of the scan: [tiles kStages*kTile CandT][lists kQB*kp1 u64][bound kQB u64]
-//                                    [ltheta kQB f32][lqn kQB f32][lcount kQB i32][lock kQB i32][wslot kQB i32]
+//                                    [lqpar kQB float4][ltheta kQB f32][lcount kQB i32][lock kQB i32][wslot kQB i32]
 __host__ __device__ inline size_t scan_smem_bytes(int cand_bytes, int kp1) {
-    return (size_t)kStages * kTile * cand_bytes + (size_t)kQB * kp1 * 8 + (size_t)kQB * 8 + (size_t)kQB * 4 * 5;
+    return (size_t)kStages * kTile * cand_bytes + (size_t)kQB * kp1 * 8 + (size_t)kQB * 8 + (size_t)kQB * 16 +
+           (size_t)kQB * 4 * 4;
 }
 
+struct ScanShared {
+    uint64_t *lists;
+    volatile uint64_t *bound;        // accept iff key < bound[q]
+    float4 *lqpar;                   // (a0,a1,a2,qn) of the CTA's queries
+    volatile float *ltheta;          // current filter threshold per query (only ever decreases)
+    int *lcount, *lock, *wslot;
+};
+template <int CandBytes>
+__device__ __forceinline__ ScanShared scan_shared(unsigned char *smem_raw, int kp1) {
+    ScanShared S;
+    S.lists = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kStages * kTile * CandBytes);
+    S.bound = S.lists + (size_t)kQB * kp1;
+    S.lqpar = reinterpret_cast<float4 *>(const_cast<uint64_t *>(S.bound) + kQB);
+    S.ltheta = reinterpret_cast<volatile float *>(S.lqpar + kQB);
+    S.lcount = reinterpret_cast<int *>(const_cast<float *>(S.ltheta) + kQB);
+    S.lock = S.lcount + kQB;
+    S.wslot = S.lock + kQB;
+    return S;
+}
+
+// Rare path, out of line: candidate (x,y,z,n) with global id `idx` passed the fp32 filter for query
+// slot ql of this CTA; re-evaluate it in the exact cdist chain and insert into the CTA's list.
 template <int D>
-__global__ void __launch_bounds__(kThreads, 2) knn_scan_kernel(const typename MidT<D>::T *__restrict__ mid, int64_t e,
-                                                               const float *__restrict__ qmid, int s, int kp1,
-                                                               const float *__restrict__ theta,
-                                                               const float *__restrict__ tau,
-                                                               uint32_t *__restrict__ counts,
-                                                               uint64_t *__restrict__ keys, int cap,
-                                                               unsigned long long *__restrict__ stats) {
+__device__ __noinline__ void scan_insert(unsigned char *smem_raw, int kp1, int ql, float x, float y, float z, float n,
+                                         uint32_t idx, unsigned long long *stats) {
+    const ScanShared S = scan_shared<sizeof(typename MidT<D>::T)>(smem_raw, kp1);
+    const float4 qv = S.lqpar[ql];
+    QueryPar p;
+    p.a0 = qv.x; p.a1 = qv.y; p.a2 = qv.z; p.qn = qv.w;
+    const uint64_t key = make_key(chain_mm(p, x, y, z, n, D), idx);
+    bool pending = key < S.bound[ql];
+    if (stats) atomicAdd(stats + (pending ? 1 : 0), 1ull);
+    while (pending) {                                       // canonical SIMT-safe lock: work inside the loop
+        if (atomicCAS(&S.lock[ql], 0, 1) == 0) {
+            __threadfence_block();
+            if (key < S.bound[ql]) {
+                uint64_t *lst = S.lists + (size_t)ql * kp1;
+                const int nl = S.lcount[ql];
+                if (nl < kp1) {
+                    lst[nl] = key;
+                    S.lcount[ql] = nl + 1;
+                } else {
+                    lst[S.wslot[ql]] = key;                 // replace the current worst
+                }
+                if (nl + 1 >= kp1) {                        // list full: its worst key becomes the bound
+                    uint64_t worst = lst[0];
+                    int ws = 0;
+                    for (int u = 1; u < kp1; ++u) {
+                        const uint64_t ku = lst[u];
+                        if (ku > worst) { worst = ku; ws = u; }
+                    }
+                    S.wslot[ql] = ws;
+                    S.bound[ql] = worst;
+                    S.ltheta[ql] = fminf(S.ltheta[ql], filter_threshold(key_dist(worst), p.qn));
+                }
+                if (stats) atomicAdd(stats + 2, 1ull);
+            }
+            __threadfence_block();
+            atomicExch(&S.lock[ql], 0);
+            pending = false;
+        }
+    }
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Warp-specialised: warp kWarps (one elected lane) is the TMA producer, warps 0..kWarps-1 consume.
+// full[s]/empty[s] mbarrier ring of kStages tiles, so consumer warps drift apart by up to
+// kStages-1 tiles instead of meeting at a CTA barrier every tile; tiles are handed out by a global
+// counter (dynamic scheduling: a CTA slowed down by a hub's tie set simply takes fewer tiles).
+constexpr int kScanThreads = kThreads + 32;
+template <int D>
+__global__ void __launch_bounds__(kScanThreads, 2) knn_scan_kernel(const typename MidT<D>::T *__restrict__ mid, int64_t e,
+                                                                   const float *__restrict__ qmid, int s, int kp1,
+                                                                   const float *__restrict__ theta,
+                                                                   const float *__restrict__ tau,
+                                                                   uint32_t *__restrict__ counts,
+                                                                   uint64_t *__restrict__ keys, int cap,
+                                                                   uint32_t *__restrict__ tile_counter,
+                                                                   unsigned long long *__restrict__ stats) {
     using CandT = typename MidT<D>::T;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     CandT *tiles = reinterpret_cast<CandT *>(smem_raw);
-    uint64_t *lists = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kStages * kTile * sizeof(CandT));
-    volatile uint64_t *bound = lists + (size_t)kQB * kp1;        // accept iff key < bound[q]
-    volatile float *ltheta = reinterpret_cast<volatile float *>(const_cast<uint64_t *>(bound) + kQB);
-    float *lqn = const_cast<float *>(ltheta) + kQB;
-    int *lcount = reinterpret_cast<int *>(lqn + kQB);
-    int *lock = lcount + kQB;
-    int *wslot = lock + kQB;
+    const ScanShared S = scan_shared<sizeof(CandT)>(smem_raw, kp1);
     __shared__ __align__(8) uint64_t full_bar[kStages];
+    __shared__ __align__(8) uint64_t empty_bar[kStages];
+    __shared__ int tile_id[kStages];                        // -1: no more tiles
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int qb = blockIdx.y;
-    const int g = gridDim.x;
     const int64_t ntiles_all = (e + kTile - 1) / kTile;
-    // interleaved tiles: CTA b owns tiles b, b+g, b+2g, ...
-    const int ntiles = (int)((ntiles_all > blockIdx.x) ? (ntiles_all - blockIdx.x + g - 1) / g : 0);
 
-    // per-query state of this CTA
-    {
+    if (threadIdx.x < kQB) {   // per-query state of this CTA
         const int q = qb * kQB + threadIdx.x;
-        float ta = -1.f, th = -kInf, qn = 0.f;
-        if (q < s) { ta = tau[q]; th = theta[q]; qn = load_query<D>(qmid, q).qn; }
-        // initial bound: every key whose distance is <= tau  (key < (tau_bits+1) << 32)
-        const uint64_t b0 = (q < s) ? (((uint64_t)__float_as_uint(ta) + 1ull) << 32) : 0ull;
-        bound[threadIdx.x] = b0;
-        ltheta[threadIdx.x] = th;
-        lqn[threadIdx.x] = qn;
-        lcount[threadIdx.x] = 0;
-        lock[threadIdx.x] = 0;
-        wslot[threadIdx.x] = 0;
-    }
-
-    float a0[kQ], a1[kQ], a2[kQ], th[kQ];
-#pragma unroll
-    for (int i = 0; i < kQ; ++i) {
-        const int q = qb * kQB + i * 32 + lane;
+        float ta = -1.f, th = -kInf;
+        float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (q < s) {
+            ta = tau[q]; th = theta[q];
             const QueryPar p = load_query<D>(qmid, q);
-            a0[i] = p.a0; a1[i] = p.a1; a2[i] = p.a2; th[i] = theta[q];
-        } else { a0[i] = a1[i] = a2[i] = 0.f; th[i] = -kInf; }
-    }
-
-    auto issue = [&](int t) {                               // thread 0 only
-        if (t >= ntiles) return;
-        const int64_t base = ((int64_t)blockIdx.x + (int64_t)t * g) * kTile;
-        const int cnt = (int)min((int64_t)kTile, e - base);
-        CandT *dst = tiles + (t % kStages) * kTile;
-        int cnt_tma = cnt;
-        if (sizeof(CandT) == 8 && (cnt & 1)) {              // keep the bulk size a multiple of 16 B
-            cnt_tma = cnt - 1;
-            dst[cnt - 1] = mid[base + cnt - 1];
+            qv = make_float4(p.a0, p.a1, p.a2, p.qn);
         }
-        const uint32_t bytes = (uint32_t)cnt_tma * (uint32_t)sizeof(CandT);
-        mbar_expect_tx(&full_bar[t % kStages], bytes);
-        if (bytes) tma_bulk_g2s(dst, mid + base, bytes, &full_bar[t % kStages]);
-    };
-
+        // initial bound: every key whose distance is <= tau  (key < (tau_bits+1) << 32)
+        S.bound[threadIdx.x] = (q < s) ? (((uint64_t)__float_as_uint(ta) + 1ull) << 32) : 0ull;
+        S.lqpar[threadIdx.x] = qv;
+        S.ltheta[threadIdx.x] = th;
+        S.lcount[threadIdx.x] = 0;
+        S.lock[threadIdx.x] = 0;
+        S.wslot[threadIdx.x] = 0;
+    }
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kStages; ++i) mbar_init(&full_bar[i], 1);
+        for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], kWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
-    if (threadIdx.x == 0)
-        for (int t = 0; t < kStages - 1; ++t) issue(t);
-    __syncthreads();
 
-    for (int it = 0; it < ntiles; ++it) {
-        if (threadIdx.x == 0) issue(it + kStages - 1);      // stage freed by the barrier closing it-1
-        // pick up thresholds tightened by other warps
-#pragma unroll
-        for (int i = 0; i < kQ; ++i) th[i] = fminf(th[i], ltheta[i * 32 + lane]);
-        mbar_wait(&full_bar[it % kStages], (uint32_t)((it / kStages) & 1));
-        const int64_t base = ((int64_t)blockIdx.x + (int64_t)it * g) * kTile;
-        const int cnt = (int)min((int64_t)kTile, e - base);
-        const CandT *tile = tiles + (it % kStages) * kTile;
-#pragma unroll 2
-        for (int c = warp; c < cnt; c += kWarps) {
-            float x, y, z, n;
-            cand_xyzn(tile[c], x, y, z, n);                 // one broadcast LDS per candidate
-            const float np = __fmul_rn(n, 1.0f - kSlack);
-            float f[kQ];
-            bool any = false;
-#pragma unroll
-            for (int i = 0; i < kQ; ++i) {
-                f[i] = (D == 3) ? fmaf(a0[i], x, fmaf(a1[i], y, fmaf(a2[i], z, np)))
-                                : fmaf(a0[i], x, fmaf(a1[i], y, np));
-                any |= (f[i] <= th[i]);
+    if (warp == kWarps) {
+        // ===== producer =====
+        if (lane == 0) {
+            for (int it = 0;; ++it) {
+                const int st = it % kStages;
+                mbar_wait(&empty_bar[st], (uint32_t)(((it / kStages) & 1) ^ 1));   // first pass: free
+                const uint32_t t = atomicAdd(tile_counter + qb, 1u);
+                if ((int64_t)t >= ntiles_all) {
+                    tile_id[st] = -1;
+                    mbar_arrive(&full_bar[st]);
+                    break;
+                }
+                const int64_t base = (int64_t)t * kTile;
+                const int cnt = (int)min((int64_t)kTile, e - base);
+                CandT *dst = tiles + st * kTile;
+                int cnt_tma = cnt;
+                if (sizeof(CandT) == 8 && (cnt & 1)) {      // keep the bulk size a multiple of 16 B
+                    cnt_tma = cnt - 1;
+                    dst[cnt - 1] = mid[base + cnt - 1];
+                }
+                tile_id[st] = (int)t;
+                const uint32_t bytes = (uint32_t)cnt_tma * (uint32_t)sizeof(CandT);
+                mbar_expect_tx(&full_bar[st], bytes);       // release: tile_id / tail element visible to waiters
+                if (bytes) tma_bulk_g2s(dst, mid + base, bytes, &full_bar[st]);
             }
-            if (any) {                                      // rare: exact re-check in cdist arithmetic
-                if (stats && lane == 0) atomicAdd(stats + 3, 1ull);
+        }
+    } else {
+        // ===== consumers =====
+        float a0[kQ], a1[kQ], a2[kQ], th[kQ];
+#pragma unroll
+        for (int i = 0; i < kQ; ++i) {
+            const float4 qv = S.lqpar[i * 32 + lane];
+            a0[i] = qv.x; a1[i] = qv.y; a2[i] = qv.z; th[i] = S.ltheta[i * 32 + lane];
+        }
+        constexpr int kGroup = 3;                           // candidates folded into one min3 + compare
+        static_assert(kTile % (kWarps * kGroup) == 0, "tile must hold whole groups");
+        for (int it = 0;; ++it) {
+            const int st = it % kStages;
+            mbar_wait(&full_bar[st], (uint32_t)((it / kStages) & 1));
+            const int t = tile_id[st];
+            if (t < 0) break;
+#pragma unroll
+            for (int i = 0; i < kQ; ++i) th[i] = fminf(th[i], S.ltheta[i * 32 + lane]);   // tightened by other warps
+            const int64_t base = (int64_t)t * kTile;
+            const int cnt = (int)min((int64_t)kTile, e - base);
+            const CandT *tile = tiles + st * kTile;
+            // warp w visits candidates w, w+8, w+16, ... in groups of kGroup; slots past cnt are masked
+            for (int c0 = warp; c0 < cnt; c0 += kWarps * kGroup) {
+                float x[kGroup], y[kGroup], z[kGroup], n[kGroup], np[kGroup];
+#pragma unroll
+                for (int j = 0; j < kGroup; ++j) {
+                    const int c = c0 + j * kWarps;          // c < kTile always
+                    cand_xyzn(tile[c], x[j], y[j], z[j], n[j]);
+                    np[j] = (c < cnt) ? __fmul_rn(n[j], 1.0f - kSlack) : kInf;
+                }
+                bool any = false;
 #pragma unroll
                 for (int i = 0; i < kQ; ++i) {
-                    if (f[i] <= th[i]) {
-                        const int ql = i * 32 + lane;       // query slot in this CTA (a lane owns its slots)
-                        QueryPar p;
-                        p.a0 = a0[i]; p.a1 = a1[i]; p.a2 = a2[i]; p.qn = lqn[ql];
-                        const uint64_t key = make_key(chain_mm(p, x, y, z, n, D), (uint32_t)(base + c));
-                        bool pending = key < bound[ql];
-                        if (stats) atomicAdd(stats + (pending ? 1 : 0), 1ull);
-                        while (pending) {                   // canonical SIMT-safe lock: work inside the loop
-                            if (atomicCAS(&lock[ql], 0, 1) == 0) {
-                                __threadfence_block();
-                                if (key < bound[ql]) {
-                                    uint64_t *lst = lists + (size_t)ql * kp1;
-                                    const int nl = lcount[ql];
-                                    if (nl < kp1) {
-                                        lst[nl] = key;
-                                        lcount[ql] = nl + 1;
-                                    } else {
-                                        lst[wslot[ql]] = key;   // replace the current worst
-                                    }
-                                    if (nl + 1 >= kp1) {        // list full: its worst key becomes the bound
-                                        uint64_t worst = lst[0];
-                                        int ws = 0;
-                                        for (int u = 1; u < kp1; ++u) {
-                                            const uint64_t ku = lst[u];
-                                            if (ku > worst) { worst = ku; ws = u; }
-                                        }
-                                        wslot[ql] = ws;
-                                        bound[ql] = worst;
-                                        ltheta[ql] = fminf(ltheta[ql], filter_threshold(key_dist(worst), p.qn));
-                                    }
-                                    if (stats) atomicAdd(stats + 2, 1ull);
-                                }
-                                __threadfence_block();
-                                atomicExch(&lock[ql], 0);
-                                pending = false;
+                    float f[kGroup];
+#pragma unroll
+                    for (int j = 0; j < kGroup; ++j)
+                        f[j] = (D == 3) ? fmaf(a0[i], x[j], fmaf(a1[i], y[j], fmaf(a2[i], z[j], np[j])))
+                                        : fmaf(a0[i], x[j], fmaf(a1[i], y[j], np[j]));
+                    any |= (min3f(f[0], f[1], f[2]) <= th[i]);      // 1 FMNMX3 + 1 FSETP per 3 pairs
+                }
+                if (any) {                                  // rare: find the (query, candidate) pairs that passed
+                    if (stats && lane == 0) atomicAdd(stats + 3, 1ull);
+#pragma unroll
+                    for (int j = 0; j < kGroup; ++j) asm volatile("" : "+f"(np[j]));   // recompute below, keep no predicates alive
+#pragma unroll
+                    for (int i = 0; i < kQ; ++i) {
+                        float f[kGroup];
+#pragma unroll
+                        for (int j = 0; j < kGroup; ++j)
+                            f[j] = (D == 3) ? fmaf(a0[i], x[j], fmaf(a1[i], y[j], fmaf(a2[i], z[j], np[j])))
+                                            : fmaf(a0[i], x[j], fmaf(a1[i], y[j], np[j]));
+                        if (min3f(f[0], f[1], f[2]) <= th[i]) {
+                            const int ql = i * 32 + lane;
+#pragma unroll
+                            for (int j = 0; j < kGroup; ++j) {
+                                const int c = c0 + j * kWarps;
+                                if (f[j] <= th[i] && c < cnt)
+                                    scan_insert<D>(smem_raw, kp1, ql, x[j], y[j], z[j], n[j], (uint32_t)(base + c), stats);
                             }
+                            th[i] = fminf(th[i], S.ltheta[ql]);
                         }
-                        th[i] = fminf(th[i], ltheta[ql]);
                     }
                 }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[st]);     // this warp is done with the stage
         }
-        __syncthreads();
     }
+    __syncthreads();
     // publish this CTA's survivors: at most kp1 per query, so counts[q] <= gridDim.x * kp1 <= cap
-    {
+    if (threadIdx.x < kQB) {
         const int q = qb * kQB + threadIdx.x;
-        const int nl = lcount[threadIdx.x];
+        const int nl = S.lcount[threadIdx.x];
         if (q < s && nl > 0) {
             const uint32_t slot = atomicAdd(counts + q, (uint32_t)nl);
-            const uint64_t *lst = lists + (size_t)threadIdx.x * kp1;
+            const uint64_t *lst = S.lists + (size_t)threadIdx.x * kp1;
             for (int u = 0; u < nl; ++u)
                 if (slot + u < (uint32_t)cap) keys[(int64_t)q * cap + slot + u] = lst[u];
         }
@@ -1143,13 +1216,13 @@ KnnLayout knn_layout(int64_t e, int64_t s, int kp1) {
     int cap = (L.g * kp1 + 255) / 256 * 256;          // every CTA publishes at most kp1 keys per query
     if (cap < 1024) cap = 1024;
     L.cap = cap;
-    L.sb = s < 1024 ? s : 1024;
+    L.sb = s < 1024 ? s : 1024;                          // <= 4 query blocks per batch (<= 64 tile counters)
     if (L.sb < 1) L.sb = 1;
     size_t o = 0;
     L.off_chunkmin = o; o = align_up(o + (size_t)L.sb * L.g * sizeof(float), 256);
     L.off_theta = o;    o = align_up(o + (size_t)L.sb * sizeof(float), 256);
     L.off_tau = o;      o = align_up(o + (size_t)L.sb * sizeof(float), 256);
-    L.off_counts = o;   o = align_up(o + (size_t)L.sb * sizeof(uint32_t), 256);
+    L.off_counts = o;   o = align_up(o + ((size_t)L.sb + 64) * sizeof(uint32_t), 256);   // + tile counters (one per query block)
     L.off_stats = o;    o = align_up(o + 8 * sizeof(unsigned long long), 256);
     L.off_keys = o;     o = align_up(o + (size_t)L.sb * L.cap * sizeof(uint64_t), 256);
     L.total = o;
@@ -1175,7 +1248,7 @@ int knn_fast(const float *mid, int64_t e, int64_t idx_offset, const float *qmid,
     for (int64_t q0 = 0; q0 < s; q0 += L.sb) {
         const int sb = (int)((s - q0) < L.sb ? (s - q0) : L.sb);
         const float *qm = qmid + q0 * mld;
-        GEM_CUDA(cudaMemsetAsync(counts, 0, (size_t)sb * sizeof(uint32_t), st));
+        GEM_CUDA(cudaMemsetAsync(counts, 0, ((size_t)L.sb + 64) * sizeof(uint32_t), st));   // counts + tile counters
         knn_bound_kernel<D><<<L.g, kThreads, 0, st>>>(reinterpret_cast<const CandT *>(mid), e, qm, sb,
                                                       L.tiles_per_cta, chunkmin);
         GEM_CHECK_LAUNCH();
@@ -1185,8 +1258,8 @@ int knn_fast(const float *mid, int64_t e, int64_t idx_offset, const float *qmid,
         GEM_CHECK_LAUNCH();
         stage_mark();                                                   // GEM_STAGE_KNN_THRESHOLD
         dim3 grid(L.g, (sb + kQB - 1) / kQB);
-        knn_scan_kernel<D><<<grid, kThreads, scan_smem, st>>>(reinterpret_cast<const CandT *>(mid), e, qm, sb, kp1,
-                                                              theta, tau, counts, keys, L.cap,
+        knn_scan_kernel<D><<<grid, kScanThreads, scan_smem, st>>>(reinterpret_cast<const CandT *>(mid), e, qm, sb, kp1,
+                                                              theta, tau, counts, keys, L.cap, counts + L.sb,
                                                               g_knn_stats ? reinterpret_cast<unsigned long long *>(w + L.off_stats) : nullptr);
         GEM_CHECK_LAUNCH();
         stage_mark();                                                   // GEM_STAGE_KNN_SCAN
