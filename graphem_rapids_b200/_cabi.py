@@ -66,7 +66,7 @@ SIGNATURES = {
     "gem_pack_points": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "gem_check_line_intersections": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
                                              c_void_p, c_void_p]),
-    "gem_fp32_peak_probe": (c_int, [POINTER(c_double), c_void_p]),
+    "gem_fp32_peak_probe": (c_int, [POINTER(c_double), POINTER(c_double), c_void_p]),
 }
 
 

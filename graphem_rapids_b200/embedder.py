@@ -315,9 +315,11 @@ class GraphEmbedderPyTorch:
 
     def fp32_peak_flops(self) -> float:
         """Measured FP32 FMA throughput of this device in flop/s (gem_fp32_peak_probe)."""
-        out = ctypes.c_double(0.0)
+        out, out2 = ctypes.c_double(0.0), ctypes.c_double(0.0)
         with torch.cuda.device(self.device):
-            _cabi.check(self._lib.gem_fp32_peak_probe(ctypes.byref(out), self._stream()), "gem_fp32_peak_probe")
+            _cabi.check(self._lib.gem_fp32_peak_probe(ctypes.byref(out), ctypes.byref(out2), self._stream()),
+                        "gem_fp32_peak_probe")
+        self.fp32_peak_flops_packed = float(out2.value)
         return float(out.value)
 
     def _run_graph(self, num_iterations: int) -> bool:

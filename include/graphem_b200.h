@@ -178,8 +178,9 @@ int gem_check_line_intersections(const float *p1, const float *p2, const float *
                                  uint8_t *out, void *stream);
 
 /* Measured FP32 FMA throughput of the device (dependent-chain-free FFMA loop), for the
- * roofline denominator of the KNN kernel: writes flop/s to *flops_host.  Synchronises. */
-int gem_fp32_peak_probe(double *flops_host, void *stream);
+ * roofline denominator of the KNN kernel: writes flop/s of scalar FFMA to *flops_host and of the
+ * packed FFMA2 (fma.rn.f32x2) form to *flops2_host (may be NULL).  Synchronises. */
+int gem_fp32_peak_probe(double *flops_host, double *flops2_host, void *stream);
 
 #ifdef __cplusplus
 }

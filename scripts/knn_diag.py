@@ -34,3 +34,5 @@ for it in range(int(sys.argv[2]) if len(sys.argv) > 2 else 8):
           f"spring {ms['spring_mid']:.3f} upd {ms['update']:.3f} | rejected {stats[0]} accepted {stats[1]} inserts {stats[2]} warp-slow {stats[3]} | "
           f"counts mean {counts.mean():.0f} max {counts.max()} | tau/d11 ratio median {np.median(tau / np.maximum(kd, 1e-30)):.2f} max {np.max(tau / np.maximum(kd, 1e-30)):.3g} "
           f"| |pos| med {r.median():.3g} max {r.max():.3g}")
+pk = emb.fp32_peak_flops()
+print(f"fp32 peak: FFMA {pk/1e12:.1f} TFLOP/s, FFMA2 {emb.fp32_peak_flops_packed/1e12:.1f} TFLOP/s")
