@@ -58,6 +58,8 @@ SIGNATURES = {
     "gem_topk_merge": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "gem_intersection_forces": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64,
                                         c_int, c_float, c_void_p, c_void_p]),
+    "gem_intersection_forces_range": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64,
+                                              c_int, c_float, c_int64, c_int64, c_void_p, c_void_p]),
     "gem_update_workspace_bytes": (c_int, [c_int64, c_int, POINTER(c_size_t)]),
     "gem_update_positions": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p,
                                      c_int, c_void_p]),

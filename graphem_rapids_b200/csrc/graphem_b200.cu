@@ -937,7 +937,8 @@ __global__ void __launch_bounds__(kThreads) intersection_kernel(const float *__r
                                                                 const int2 *__restrict__ edges,
                                                                 const int64_t *__restrict__ samp,
                                                                 const int64_t *__restrict__ knn_full, int64_t s, int kp1,
-                                                                float k_inter, float *__restrict__ force) {
+                                                                float k_inter, int v_begin, int v_end,
+                                                                float *__restrict__ force) {
     const int k = kp1 - 1;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= s * k) return;
@@ -945,7 +946,7 @@ __global__ void __launch_bounds__(kThreads) intersection_kernel(const float *__r
     const int c = (int)(t % k);
     const int64_t i = samp[r];                                   // :668
     const int64_t j = knn_full[r * kp1 + 1 + c];                 // :421 column 0 dropped, :669
-    if (!(i < j)) return;                                        // :672
+    if (!(i < j)) return;                                        // :672  (also drops the -1 padding of a short list)
     const int2 ei = edges[i], ej = edges[j];                     // :681-682
     if (ei.x == ej.x || ei.x == ej.y || ei.y == ej.x || ei.y == ej.y) return;   // :685-692
     const Vec<D> p1 = Vec<D>::load(pos, ei.x), p2 = Vec<D>::load(pos, ei.y);    // :702-705
@@ -963,7 +964,8 @@ __global__ void __launch_bounds__(kThreads) intersection_kernel(const float *__r
         const Vec<D> diff = v[u] - cen;
         const float dist = norm2(diff) + 1e-6f;
         const Vec<D> rep = (k_inter * diff) / (dist * dist);
-        rep.red_add(force, vid[u]);
+        // vertex-sliced accumulation (multi-GPU: a rank adds only into the vertex range it owns)
+        if (vid[u] >= v_begin && vid[u] < v_end) rep.red_add(force, vid[u] - v_begin);
     }
 }
 
@@ -971,8 +973,8 @@ __global__ void __launch_bounds__(kThreads) intersection_generic_kernel(const fl
                                                                         const int2 *__restrict__ edges,
                                                                         const int64_t *__restrict__ samp,
                                                                         const int64_t *__restrict__ knn_full, int64_t s,
-                                                                        int kp1, int d, float k_inter,
-                                                                        float *__restrict__ force) {
+                                                                        int kp1, int d, float k_inter, int v_begin,
+                                                                        int v_end, float *__restrict__ force) {
     const int k = kp1 - 1;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= s * k) return;
@@ -993,6 +995,7 @@ __global__ void __launch_bounds__(kThreads) intersection_generic_kernel(const fl
     const float *v[4] = {p1, p2, q1, q2};
     const int vid[4] = {ei.x, ei.y, ej.x, ej.y};
     for (int u = 0; u < 4; ++u) {
+        if (vid[u] < v_begin || vid[u] >= v_end) continue;
         float nsq = 0.f;
         for (int a = 0; a < d; ++a) {
             const float cen = __fdiv_rn(((p1[a] + p2[a]) + q1[a]) + q2[a], 4.0f);
@@ -1003,7 +1006,7 @@ __global__ void __launch_bounds__(kThreads) intersection_generic_kernel(const fl
         const float dd = dist * dist;
         for (int a = 0; a < d; ++a) {
             const float cen = __fdiv_rn(((p1[a] + p2[a]) + q1[a]) + q2[a], 4.0f);
-            atomicAdd(force + (int64_t)vid[u] * d + a, __fdiv_rn(k_inter * (v[u][a] - cen), dd));
+            atomicAdd(force + (int64_t)(vid[u] - v_begin) * d + a, __fdiv_rn(k_inter * (v[u][a] - cen), dd));
         }
     }
 }
@@ -1476,15 +1479,24 @@ int gem_topk_merge(const float *dists, const int64_t *idxs, int parts, int64_t s
 
 int gem_intersection_forces(const float *pos, const int32_t *edges, int64_t n, int d, const int64_t *samp,
                             const int64_t *knn_full, int64_t s, int kp1, float k_inter, float *force, void *stream) {
+    return gem_intersection_forces_range(pos, edges, n, d, samp, knn_full, s, kp1, k_inter, 0, n, force, stream);
+}
+
+int gem_intersection_forces_range(const float *pos, const int32_t *edges, int64_t n, int d, const int64_t *samp,
+                                  const int64_t *knn_full, int64_t s, int kp1, float k_inter, int64_t v_begin,
+                                  int64_t v_end, float *force, void *stream) {
     if (!pos || !edges || !samp || !knn_full || !force || n <= 0 || d < 2 || s <= 0 || kp1 <= 0) return GEM_E_BADARG;
+    if (v_begin < 0 || v_end > n || v_begin > v_end) return GEM_E_BADARG;
+    if (v_begin == v_end) return GEM_OK;
+    const int vb = (int)v_begin, ve = (int)v_end;
     const int64_t pairs = s * (kp1 - 1);
     if (pairs == 0) return GEM_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const int2 *ed = reinterpret_cast<const int2 *>(edges);
     const int grid = (int)((pairs + kThreads - 1) / kThreads);
-    if (d == 2) intersection_kernel<2><<<grid, kThreads, 0, st>>>(pos, ed, samp, knn_full, s, kp1, k_inter, force);
-    else if (d == 3) intersection_kernel<3><<<grid, kThreads, 0, st>>>(pos, ed, samp, knn_full, s, kp1, k_inter, force);
-    else intersection_generic_kernel<<<grid, kThreads, 0, st>>>(pos, ed, samp, knn_full, s, kp1, d, k_inter, force);
+    if (d == 2) intersection_kernel<2><<<grid, kThreads, 0, st>>>(pos, ed, samp, knn_full, s, kp1, k_inter, vb, ve, force);
+    else if (d == 3) intersection_kernel<3><<<grid, kThreads, 0, st>>>(pos, ed, samp, knn_full, s, kp1, k_inter, vb, ve, force);
+    else intersection_generic_kernel<<<grid, kThreads, 0, st>>>(pos, ed, samp, knn_full, s, kp1, d, k_inter, vb, ve, force);
     GEM_CHECK_LAUNCH();
     return GEM_OK;
 }

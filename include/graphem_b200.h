@@ -113,6 +113,12 @@ int gem_topk_merge(const float *dists, const int64_t *idxs, int parts, int64_t s
 int gem_intersection_forces(const float *pos, const int32_t *edges, int64_t n, int d,
                             const int64_t *samp, const int64_t *knn_full, int64_t s, int kp1,
                             float k_inter, float *force, void *stream);
+/* Vertex-sliced variant for the multi-GPU path (every rank evaluates all <= s*k pairs from the
+ * replicated positions but accumulates only into the vertex range [v_begin, v_end) it owns):
+ * `force` points at row v_begin of the accumulator, i.e. it is a (v_end - v_begin, ld) slice. */
+int gem_intersection_forces_range(const float *pos, const int32_t *edges, int64_t n, int d,
+                                  const int64_t *samp, const int64_t *knn_full, int64_t s, int kp1,
+                                  float k_inter, int64_t v_begin, int64_t v_end, float *force, void *stream);
 
 /* (d) position update.  Replaces the tail of update_positions (:796-804):
  * new = pos + (f_spring + f_inter); new -= mean; new /= (unbiased std + 1e-6).
