@@ -331,7 +331,7 @@ def run_b200(args, w):
 
     ms_per_step = total_ms / K
     value = E / (ms_per_step * 1e-3)
-    launches_per_step = 11 if world == 1 else 13
+    launches_per_step = 11 if world == 1 else 12        # kernels of libgraphem_b200.so per iteration (torch/NCCL kernels not counted)
     line = {
         "metric": METRIC, "value": value, "unit": "edge-updates/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,

@@ -13,6 +13,7 @@ from ctypes import (POINTER, Structure, c_char_p, c_double, c_float, c_int, c_in
 from . import build as _build
 
 _lib = None
+ABI_VERSION = 2
 STAGE_NAMES = ["sample", "spring_mid", "query_mid", "knn_bound", "knn_threshold", "knn_scan", "knn_select",
                "knn_fallback", "intersect", "update"]
 _inited_devices = set()
@@ -26,6 +27,7 @@ class GemPlan(Structure):
         ("k_attr", c_float), ("l_min", c_float), ("k_inter", c_float),
         ("seed", c_uint64),
         ("pos", c_void_p), ("edges", c_void_p), ("row_ptr", c_void_p), ("col", c_void_p),
+        ("up_ptr", c_void_p), ("hubs", c_void_p), ("n_hubs", c_int64),
         ("force", c_void_p), ("mid", c_void_p),
         ("qmid", c_void_p), ("tau_hint", c_void_p), ("samp", c_void_p), ("knn_idx", c_void_p), ("knn_dist", c_void_p),
         ("iter_counter", c_void_p),
@@ -44,11 +46,16 @@ SIGNATURES = {
     "gem_mid_pitch": (c_int, [c_int]),
     "gem_spring_midpoints": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_float,
                                      c_void_p, c_void_p, c_void_p]),
+    "gem_hub_degree": (c_int, []),
+    "gem_spring_midpoints_csr": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64,
+                                         c_int, c_float, c_float, c_void_p, c_void_p, c_int64, c_void_p]),
     "gem_sample_edges": (c_int, [c_uint64, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p]),
     "gem_query_midpoints": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "gem_knn_workspace_bytes": (c_int, [c_int64, c_int, c_int64, c_int, POINTER(c_size_t)]),
     "gem_knn_midpoints": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_int, c_int, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "gem_knn_midpoints_shard": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_int64, c_int, c_int,
+                                        c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "gem_knn_linegraph_hint": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int,
                                        c_void_p, c_void_p]),
     "gem_knn_midpoints_exact": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_int, c_int,
@@ -56,6 +63,8 @@ SIGNATURES = {
     "gem_knn_debug_stats": (c_int, [c_int, c_int64, c_int, c_int64, c_int, POINTER(c_size_t), POINTER(c_size_t),
                                     POINTER(c_size_t), POINTER(c_int), POINTER(c_int)]),
     "gem_topk_merge": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    "gem_topk_merge_strided": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int, c_void_p,
+                                       c_void_p, c_void_p]),
     "gem_intersection_forces": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64,
                                         c_int, c_float, c_void_p, c_void_p]),
     "gem_intersection_forces_range": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64,
@@ -94,7 +103,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the library lacks a declared symbol
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.gem_abi_version() != 1:
+    if lib.gem_abi_version() != ABI_VERSION:
         raise ImportError("graphem_rapids_b200: ABI version mismatch between header and library")
     _lib = lib
     return lib

@@ -100,6 +100,9 @@ __device__ __forceinline__ Vec<2> operator*(float s, Vec<2> a) { return {s * a.x
 __device__ __forceinline__ Vec<3> operator*(float s, Vec<3> a) { return {s * a.x, s * a.y, s * a.z}; }
 __device__ __forceinline__ Vec<2> operator/(Vec<2> a, float s) { return {__fdiv_rn(a.x, s), __fdiv_rn(a.y, s)}; }
 __device__ __forceinline__ Vec<3> operator/(Vec<3> a, float s) { return {__fdiv_rn(a.x, s), __fdiv_rn(a.y, s), __fdiv_rn(a.z, s)}; }
+// (p1+p2)/2.0 of :785 -- multiplying by 0.5 is the same correctly rounded value, without the IEEE divide sequence
+__device__ __forceinline__ Vec<2> half_sum(Vec<2> a, Vec<2> b) { return {0.5f * (a.x + b.x), 0.5f * (a.y + b.y)}; }
+__device__ __forceinline__ Vec<3> half_sum(Vec<3> a, Vec<3> b) { return {0.5f * (a.x + b.x), 0.5f * (a.y + b.y), 0.5f * (a.z + b.z)}; }
 __device__ __forceinline__ Vec<2> neg(Vec<2> a) { return {-a.x, -a.y}; }
 __device__ __forceinline__ Vec<3> neg(Vec<3> a) { return {-a.x, -a.y, -a.z}; }
 // torch.norm(dim=1) on CPU == sqrt_rn(fma(z,z,fma(y,y,x*x)))  [probed]
@@ -137,9 +140,135 @@ __global__ void __launch_bounds__(kThreads) spring_mid_kernel(const float *__res
         ef.red_add(force, ed.x);                                 // :633
         neg(ef).red_add(force, ed.y);                            // :634
         if (mid != nullptr) {
-            const Vec<D> m = (p1 + p2) / 2.0f;                   // :785
+            const Vec<D> m = half_sum(p1, p2);                   // :785
             mid[i] = make_mid(m);
         }
+    }
+}
+
+// ---- vertex-parallel ("pull") form over the symmetric CSR: no atomics, no memset --------------
+// A group of kGrp lanes owns one vertex v and walks its row; every incident edge {v,w} contributes
+//   fm * ((pos[w]-pos[v]) / dist)     (= +ef when v is the edge's first endpoint, -ef when it is the second:
+//                                        the two expressions are bit-identical)
+// and the entries with w > v are exactly the edges (v,w) of the sorted edge list, ids
+// up_ptr[v] .. up_ptr[v+1]-1 in column order, so the same pass writes their midpoints.  Each edge
+// force is evaluated twice (once per endpoint), which costs arithmetic the kernel has to spare and
+// removes 2E scattered red.global.add.v4 plus the zero-fill of the accumulator.  Rows longer than
+// kHubDeg (hubs of preferential-attachment graphs) are left to one CTA each (blocks >= main_blocks).
+constexpr int kGrp = 4;
+constexpr int kHubDeg = 128;
+
+// The pull form evaluates every edge twice, so its arithmetic matters: sqrt and 1/x come from the
+// SFU (sqrt.approx / rcp.approx, <= 1 ulp each) instead of the ~40-instruction IEEE sequences of
+// __fsqrt_rn + 3 x __fdiv_rn.  Forces only have to match the reference to 1e-5 relative (their
+// summation order differs from torch's anyway); everything the KNN sees -- the midpoints -- stays exact.
+// (.ftz: one MUFU each; a squared length below 2^-126 counts as 0, which the +1e-6 absorbs)
+__device__ __forceinline__ float sqrt_fast(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float nsq(Vec<2> a) { return fmaf(a.y, a.y, a.x * a.x); }
+__device__ __forceinline__ float nsq(Vec<3> a) { return fmaf(a.z, a.z, fmaf(a.y, a.y, a.x * a.x)); }
+template <int D>
+__device__ __forceinline__ Vec<D> spring_term(const Vec<D> &pv, const Vec<D> &pw, float neg_k_attr, float l_min) {
+    const Vec<D> diff = pw - pv;                              // :622
+    const float dist = sqrt_fast(nsq(diff)) + 1e-6f;          // :623
+    const float fm = neg_k_attr * (dist - l_min);             // :626
+    return (fm * rcp_fast(dist)) * diff;                      // :629
+}
+template <int D> __device__ __forceinline__ Vec<D> vzero();
+template <> __device__ __forceinline__ Vec<2> vzero<2>() { return {0.f, 0.f}; }
+template <> __device__ __forceinline__ Vec<3> vzero<3>() { return {0.f, 0.f, 0.f}; }
+__device__ __forceinline__ void vec_to3(Vec<2> a, float *t) { t[0] = a.x; t[1] = a.y; t[2] = 0.f; }
+__device__ __forceinline__ void vec_to3(Vec<3> a, float *t) { t[0] = a.x; t[1] = a.y; t[2] = a.z; }
+template <int D> __device__ __forceinline__ Vec<D> vec_from3(const float *t);
+template <> __device__ __forceinline__ Vec<2> vec_from3<2>(const float *t) { return {t[0], t[1]}; }
+template <> __device__ __forceinline__ Vec<3> vec_from3<3>(const float *t) { return {t[0], t[1], t[2]}; }
+__device__ __forceinline__ Vec<2> shfl_xor_vec(Vec<2> a, int m) {
+    return {__shfl_xor_sync(0xffffffffu, a.x, m), __shfl_xor_sync(0xffffffffu, a.y, m)};
+}
+__device__ __forceinline__ Vec<3> shfl_xor_vec(Vec<3> a, int m) {
+    return {__shfl_xor_sync(0xffffffffu, a.x, m), __shfl_xor_sync(0xffffffffu, a.y, m), __shfl_xor_sync(0xffffffffu, a.z, m)};
+}
+
+template <int D>
+__global__ void __launch_bounds__(kThreads) spring_csr_kernel(const float *__restrict__ pos,
+                                                              const int64_t *__restrict__ row_ptr,
+                                                              const int32_t *__restrict__ col,
+                                                              const int64_t *__restrict__ up_ptr, int64_t v_begin,
+                                                              int64_t v_end, const int32_t *__restrict__ hubs,
+                                                              int n_hub_blocks, float neg_k_attr, float l_min,
+                                                              float *__restrict__ force,
+                                                              typename MidT<D>::T *__restrict__ mid, int64_t mid_base) {
+    if ((int)blockIdx.x < n_hub_blocks) {
+        // ---- one CTA per hub row; scheduled first so the long rows overlap the bulk of the work
+        const int64_t v = hubs[blockIdx.x];
+        const int64_t r0 = row_ptr[v], deg = row_ptr[v + 1] - r0;
+        const int64_t up0 = up_ptr[v], lo = deg - (up_ptr[v + 1] - up0);
+        const Vec<D> pv = Vec<D>::load(pos, v);
+        Vec<D> acc = vzero<D>();
+        for (int64_t t = threadIdx.x; t < deg; t += kThreads) {
+            const int w = __ldcs(col + r0 + t);
+            const Vec<D> pw = Vec<D>::load(pos, w);
+            acc = acc + spring_term<D>(pv, pw, neg_k_attr, l_min);
+            if (mid != nullptr && t >= lo) mid[up0 + (t - lo) - mid_base] = make_mid(half_sum(pv, pw));   // :785
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc = acc + shfl_xor_vec(acc, o);
+        __shared__ float red[kWarps][4];
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        if (lane == 0) vec_to3(acc, red[warp]);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t[3] = {0.f, 0.f, 0.f};
+            for (int w = 0; w < kWarps; ++w)
+                for (int j = 0; j < 3; ++j) t[j] += red[w][j];
+            vec_from3<D>(t).store(force, v - v_begin);
+        }
+        return;
+    }
+    const int g = threadIdx.x & (kGrp - 1);
+    const int mb = (int)blockIdx.x - n_hub_blocks;
+    const int64_t stride = ((int64_t)(gridDim.x - n_hub_blocks) * kThreads) / kGrp;
+    const int64_t nv = v_end - v_begin;
+    // every lane of a warp runs the same number of outer iterations (the shuffles need all 32 lanes)
+    const int64_t first = ((int64_t)mb * kThreads + threadIdx.x) / kGrp;
+    const int64_t warp_first = ((int64_t)mb * kThreads + (threadIdx.x & ~31)) / kGrp;
+    for (int64_t base = warp_first, i = first; base < nv; base += stride, i += stride) {
+        const bool valid = i < nv;
+        const int64_t v = v_begin + (valid ? i : 0);
+        int deg = 0, lo = 0;
+        const int32_t *cp = col;
+        typename MidT<D>::T *mp = mid;
+        Vec<D> pv = vzero<D>();
+        bool hub = false;
+        if (valid) {
+            const int64_t r0 = row_ptr[v], up0 = up_ptr[v];
+            const int64_t dl = row_ptr[v + 1] - r0;
+            hub = dl > kHubDeg;
+            deg = hub ? 0 : (int)dl;
+            lo = deg - (int)(up_ptr[v + 1] - up0);
+            cp = col + r0;
+            mp = mid + (up0 - lo - mid_base);                     // row entry t >= lo is edge up0 + t - lo
+            pv = Vec<D>::load(pos, v);
+        }
+        Vec<D> acc = vzero<D>();
+        // two entries per lane and trip: both column loads, then both position gathers, are in flight together
+        for (int t = g; t < deg; t += 2 * kGrp) {
+            const int t2 = t + kGrp;
+            const bool two = t2 < deg;
+            const int w1 = __ldcs(cp + t);                       // streamed once
+            const int w2 = two ? __ldcs(cp + t2) : w1;
+            const Vec<D> p1 = Vec<D>::load(pos, w1);
+            const Vec<D> p2 = Vec<D>::load(pos, w2);
+            acc = acc + spring_term<D>(pv, p1, neg_k_attr, l_min);
+            if (mid != nullptr && t >= lo) mp[t] = make_mid(half_sum(pv, p1));      // :785
+            if (two) {
+                acc = acc + spring_term<D>(pv, p2, neg_k_attr, l_min);
+                if (mid != nullptr && t2 >= lo) mp[t2] = make_mid(half_sum(pv, p2));
+            }
+        }
+        acc = acc + shfl_xor_vec(acc, 1);
+        acc = acc + shfl_xor_vec(acc, 2);
+        if (valid && !hub && g == 0) acc.store(force, v - v_begin);  // isolated vertices get their zero here
     }
 }
 
@@ -227,7 +356,7 @@ __global__ void query_mid_kernel(const float *__restrict__ pos, const int2 *__re
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= s) return;
     const int2 ed = edges[samp[i]];
-    const Vec<D> m = (Vec<D>::load(pos, ed.x) + Vec<D>::load(pos, ed.y)) / 2.0f;
+    const Vec<D> m = half_sum(Vec<D>::load(pos, ed.x), Vec<D>::load(pos, ed.y));
     qmid[i] = make_mid(m);
 }
 __global__ void query_mid_generic_kernel(const float *__restrict__ pos, const int2 *__restrict__ edges,
@@ -343,10 +472,11 @@ __global__ void __launch_bounds__(kThreads) knn_exact_kernel(const float *__rest
             if (s_nbest == kp1) thr = best[kp1 - 1];
         }
     }
+    const int nfound = s_nbest;              // < kp1 only for a shard-local search over fewer than kp1 candidates
     for (int r = threadIdx.x; r < kp1; r += blockDim.x) {
-        const uint64_t k = best[r];
-        out_idx[q * kp1 + r] = idx_offset + (int64_t)(uint32_t)k;
-        out_dist[q * kp1 + r] = key_dist(k);
+        const uint64_t k = best[r < nfound ? r : 0];
+        out_idx[q * kp1 + r] = r < nfound ? idx_offset + (int64_t)(uint32_t)k : -1;
+        out_dist[q * kp1 + r] = r < nfound ? key_dist(k) : kInf;
     }
 }
 
@@ -477,7 +607,7 @@ __global__ void __launch_bounds__(kThreads) knn_linegraph_hint_kernel(const floa
     const int q = blockIdx.x * kWarps + (threadIdx.x >> 5);
     if (q >= s) return;
     const int2 ed = edges[samp[q]];
-    const Vec<D> mq = (Vec<D>::load(pos, ed.x) + Vec<D>::load(pos, ed.y)) / 2.0f;
+    const Vec<D> mq = half_sum(Vec<D>::load(pos, ed.x), Vec<D>::load(pos, ed.y));
     QueryPar qp;
     qp.a0 = -2.f * mq.x; qp.a1 = -2.f * mq.y;
     if (D == 3) { const Vec<3> &m3 = reinterpret_cast<const Vec<3> &>(mq); qp.a2 = -2.f * m3.z; } else qp.a2 = 0.f;
@@ -496,7 +626,7 @@ __global__ void __launch_bounds__(kThreads) knn_linegraph_hint_kernel(const floa
         if (t < deg) {
             const int w = col[r0 + t];
             if (!(side == 1 && w == other)) {
-                const Vec<D> m = (Vec<D>::load(pos, min(a, w)) + Vec<D>::load(pos, max(a, w))) / 2.0f;
+                const Vec<D> m = half_sum(Vec<D>::load(pos, min(a, w)), Vec<D>::load(pos, max(a, w)));
                 float x, y, z, n;
                 cand_xyzn(make_mid(m), x, y, z, n);
                 const float d2 = chain_mm(qp, x, y, z, n, D);
@@ -898,7 +1028,8 @@ __global__ void __launch_bounds__(kThreads) knn_select_kernel(const uint32_t *__
 
 // merge `parts` sorted partial lists per query by (distance, index); total <= kMaxKp1 * 8
 __global__ void __launch_bounds__(kThreads) topk_merge_kernel(const float *__restrict__ dists,
-                                                              const int64_t *__restrict__ idxs, int parts, int64_t s,
+                                                              const int64_t *__restrict__ idxs, int64_t dist_stride,
+                                                              int64_t idx_stride, int parts, int64_t s,
                                                               int kp1, int64_t *__restrict__ out_idx,
                                                               float *__restrict__ out_dist) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -908,8 +1039,8 @@ __global__ void __launch_bounds__(kThreads) topk_merge_kernel(const float *__res
     const int64_t q = blockIdx.x;
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
         const int p = i / kp1, r = i % kp1;
-        sd[i] = dists[((int64_t)p * s + q) * kp1 + r] + 0.f;
-        si[i] = idxs[((int64_t)p * s + q) * kp1 + r];
+        sd[i] = dists[(int64_t)p * dist_stride + q * kp1 + r] + 0.f;
+        si[i] = idxs[(int64_t)p * idx_stride + q * kp1 + r];
     }
     __syncthreads();
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
@@ -1077,10 +1208,20 @@ __global__ void __launch_bounds__(kThreads) update_pass1_kernel(float *__restric
     __syncthreads();
     if (s_last) {                                      // fixed-order final reduction: deterministic
         __threadfence();
-        if (threadIdx.x < 2 * LD) {
-            double acc = 0.0;
-            for (unsigned int b = 0; b < gridDim.x; ++b) acc += partials[(int64_t)b * 2 * LD + threadIdx.x];
-            sums[threadIdx.x] = acc;
+        // all threads take part: thread t sums the partials of column t % (2*LD) over blocks t/(2*LD), +stride, ...
+        // (a single thread per column walking ~1200 L2-resident partials was a 20 us serial tail)
+        constexpr int kCols = 2 * LD, kLanes = kThreads / kCols;
+        __shared__ double fin[kLanes][kCols];
+        const int c = threadIdx.x % kCols, l = threadIdx.x / kCols;
+        double acc = 0.0;
+        for (unsigned int b = l; b < gridDim.x; b += kLanes) acc += partials[(int64_t)b * kCols + c];
+        fin[l][c] = acc;
+        __syncthreads();
+        if (threadIdx.x < kCols) {
+            double t = 0.0;
+#pragma unroll 8
+            for (int i = 0; i < kLanes; ++i) t += fin[i][threadIdx.x];
+            sums[threadIdx.x] = t;
         }
         if (threadIdx.x == 0) *ticket = 0;
     }
@@ -1099,12 +1240,17 @@ __global__ void __launch_bounds__(kThreads) update_pass2_kernel(float *__restric
                                                                 int d, const void *__restrict__ ws) {
     using VT = typename std::conditional<LD == 2, float2, float4>::type;
     const double *sums = reinterpret_cast<const double *>(ws);
+    // the fp64 divide / sqrt of the column statistics once per CTA, not once per thread
+    __shared__ float s_mean[LD], s_sd[LD];
+    if (threadIdx.x < LD) {
+        float m = 0.f, sdv = 1.f;
+        if ((int)threadIdx.x < d) col_stats(sums, LD, threadIdx.x, n_total, m, sdv);
+        s_mean[threadIdx.x] = m; s_sd[threadIdx.x] = sdv;
+    }
+    __syncthreads();
     float mean[LD], sd[LD];
 #pragma unroll
-    for (int j = 0; j < LD; ++j) {
-        if (j < d) col_stats(sums, LD, j, n_total, mean[j], sd[j]);
-        else { mean[j] = 0.f; sd[j] = 1.f; }
-    }
+    for (int j = 0; j < LD; ++j) { mean[j] = s_mean[j]; sd[j] = s_sd[j]; }
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += stride) {
         VT p = reinterpret_cast<VT *>(pos)[v];
@@ -1378,6 +1524,36 @@ int gem_spring_midpoints(const float *pos, const int32_t *edges, int64_t n, int6
     return GEM_OK;
 }
 
+int gem_hub_degree(void) { return kHubDeg; }
+
+int gem_spring_midpoints_csr(const float *pos, const int64_t *row_ptr, const int32_t *col, const int64_t *up_ptr,
+                             int64_t v_begin, int64_t v_end, const int32_t *hubs, int64_t n_hubs, int d, float k_attr,
+                             float l_min, float *force, float *mid, int64_t mid_base, void *stream) {
+    if (!pos || !row_ptr || !col || !up_ptr || !force || v_begin < 0 || v_end < v_begin || n_hubs < 0 ||
+        (n_hubs > 0 && !hubs) || (d != 2 && d != 3))
+        return GEM_E_BADARG;
+    if (v_end == v_begin) return GEM_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    // resident CTAs per SM from the occupancy calculator: a grid-stride kernel sized past that runs a ragged second wave
+    static int occ[2] = {0, 0};
+    int &oc = occ[d - 2];
+    if (oc == 0) {
+        if (d == 2) GEM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oc, spring_csr_kernel<2>, kThreads, 0));
+        else GEM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oc, spring_csr_kernel<3>, kThreads, 0));
+        if (oc < 1) oc = 1;
+    }
+    const int main_blocks = grid_for((v_end - v_begin) * kGrp, oc);
+    const int grid = main_blocks + (int)n_hubs;
+    if (d == 2)
+        spring_csr_kernel<2><<<grid, kThreads, 0, st>>>(pos, row_ptr, col, up_ptr, v_begin, v_end, hubs, (int)n_hubs, -k_attr,
+                                                        l_min, force, reinterpret_cast<float2 *>(mid), mid_base);
+    else
+        spring_csr_kernel<3><<<grid, kThreads, 0, st>>>(pos, row_ptr, col, up_ptr, v_begin, v_end, hubs, (int)n_hubs, -k_attr,
+                                                        l_min, force, reinterpret_cast<float4 *>(mid), mid_base);
+    GEM_CHECK_LAUNCH();
+    return GEM_OK;
+}
+
 int gem_sample_edges(uint64_t seed, int64_t *iter_counter, int bump_counter, int64_t e, int64_t s, int64_t *samp,
                      void *stream) {
     if (!samp || e <= 0 || s <= 0) return GEM_E_BADARG;
@@ -1449,15 +1625,39 @@ int gem_knn_linegraph_hint(const float *pos, const int64_t *row_ptr, const int32
 int gem_knn_midpoints(const float *mid, int64_t e, int64_t idx_offset, int d, const float *qmid, int64_t s, int kp1,
                       int mm_mode, const float *tau_hint, int64_t *out_idx, float *out_dist, void *ws, size_t ws_bytes,
                       void *stream) {
-    if (!mid || !qmid || !out_idx || !out_dist || e <= 0 || s <= 0 || d <= 0 || kp1 <= 0) return GEM_E_BADARG;
-    if (kp1 > e) return GEM_E_KRANGE;
-    const int mm = resolve_mm_mode(mm_mode, s, e);
+    return gem_knn_midpoints_shard(mid, e, e, idx_offset, d, qmid, s, kp1, mm_mode, tau_hint, out_idx, out_dist, ws,
+                                   ws_bytes, stream);
+}
+
+__global__ void knn_fill_empty_kernel(int64_t *__restrict__ out_idx, float *__restrict__ out_dist, int64_t total) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < total) { out_idx[i] = -1; out_dist[i] = kInf; }
+}
+
+int gem_knn_midpoints_shard(const float *mid, int64_t e, int64_t e_total, int64_t idx_offset, int d, const float *qmid,
+                            int64_t s, int kp1, int mm_mode, const float *tau_hint, int64_t *out_idx, float *out_dist,
+                            void *ws, size_t ws_bytes, void *stream) {
+    if (!qmid || !out_idx || !out_dist || e < 0 || e_total < e || s <= 0 || d <= 0 || kp1 <= 0) return GEM_E_BADARG;
+    if (kp1 > e_total) return GEM_E_KRANGE;            // the reference's torch.topk error (:583) is about ALL candidates
+    const int mm = resolve_mm_mode(mm_mode, s, e_total);
+    if (e == 0) {                                      // a rank that owns no edges: all rows are padding
+        for (int i = 0; i < 5; ++i) stage_mark();
+        knn_fill_empty_kernel<<<(unsigned)((s * kp1 + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+            out_idx, out_dist, s * kp1);
+        GEM_CHECK_LAUNCH();
+        return GEM_OK;
+    }
+    if (!mid) return GEM_E_BADARG;
     // tiny problems, generic d, direct-mode arithmetic and huge k go to the exact streaming kernel
-    if (!mm || (d != 2 && d != 3) || e < 2048 || kp1 > kMaxFastKp1) {
+    if (!mm || (d != 2 && d != 3) || e < 2048 || kp1 > kMaxFastKp1 || kp1 > e) {
         for (int i = 0; i < 4; ++i) stage_mark();       // bound/threshold/scan/select are not run
-        const int rc = gem_knn_midpoints_exact(mid, e, idx_offset, d, qmid, s, kp1, mm, out_idx, out_dist, stream);
+        if (kp1 > kMaxKp1 || e >= ((int64_t)1 << 32)) return GEM_E_BADARG;
+        const size_t smem = ((size_t)kp1 + kThreads) * sizeof(uint64_t) + (size_t)mid_pitch(d) * sizeof(float);
+        knn_exact_kernel<<<(unsigned)s, kThreads, smem, (cudaStream_t)stream>>>(mid, e, idx_offset, d, qmid, kp1, mm, nullptr,
+                                                                                 out_idx, out_dist);
+        GEM_CHECK_LAUNCH();
         stage_mark();                                   // all of the KNN time lands in GEM_STAGE_KNN_FALLBACK
-        return rc;
+        return GEM_OK;
     }
     if (e >= ((int64_t)1 << 32)) return GEM_E_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
@@ -1467,12 +1667,18 @@ int gem_knn_midpoints(const float *mid, int64_t e, int64_t idx_offset, int d, co
 
 int gem_topk_merge(const float *dists, const int64_t *idxs, int parts, int64_t s, int kp1, int64_t *out_idx,
                    float *out_dist, void *stream) {
+    return gem_topk_merge_strided(dists, idxs, s * kp1, s * kp1, parts, s, kp1, out_idx, out_dist, stream);
+}
+
+int gem_topk_merge_strided(const float *dists, const int64_t *idxs, int64_t dist_stride, int64_t idx_stride, int parts,
+                           int64_t s, int kp1, int64_t *out_idx, float *out_dist, void *stream) {
     if (!dists || !idxs || !out_idx || !out_dist || parts <= 0 || s <= 0 || kp1 <= 0) return GEM_E_BADARG;
     const int total = parts * kp1;
     if (total > 8 * kMaxKp1) return GEM_E_BADARG;
     const size_t smem = (((size_t)total * 4 + 15) / 16) * 16 + (size_t)total * 8;
     if (smem > 48 * 1024) return GEM_E_BADARG;
-    topk_merge_kernel<<<(unsigned)s, kThreads, smem, (cudaStream_t)stream>>>(dists, idxs, parts, s, kp1, out_idx, out_dist);
+    topk_merge_kernel<<<(unsigned)s, kThreads, smem, (cudaStream_t)stream>>>(dists, idxs, dist_stride, idx_stride, parts, s, kp1,
+                                                                             out_idx, out_dist);
     GEM_CHECK_LAUNCH();
     return GEM_OK;
 }
@@ -1554,7 +1760,11 @@ int gem_layout_step(const gem_plan *p, void *stream) {
         if (rc) return rc;
     }
     stage_mark();                                                       // GEM_STAGE_SAMPLE
-    rc = gem_spring_midpoints(p->pos, p->edges, p->n, p->e, p->d, p->k_attr, p->l_min, p->force, p->mid, stream);
+    if (p->row_ptr && p->col && p->up_ptr && (p->d == 2 || p->d == 3))
+        rc = gem_spring_midpoints_csr(p->pos, p->row_ptr, p->col, p->up_ptr, 0, p->n, p->hubs, p->n_hubs, p->d, p->k_attr,
+                                      p->l_min, p->force, p->mid, 0, stream);
+    else
+        rc = gem_spring_midpoints(p->pos, p->edges, p->n, p->e, p->d, p->k_attr, p->l_min, p->force, p->mid, stream);
     if (rc) return rc;
     stage_mark();                                                       // GEM_STAGE_SPRING
     rc = gem_query_midpoints(p->pos, p->edges, p->samp, p->s, p->d, p->qmid, stream);

@@ -24,6 +24,7 @@ import scipy.sparse as sp
 import torch
 
 from . import _cabi
+from .partition import build_layout
 
 logger = logging.getLogger(__name__)
 
@@ -104,18 +105,18 @@ class GraphEmbedderPyTorch:
         if self.n >= 2 ** 31:
             raise ValueError("graphem_rapids_b200 stores edge endpoints as int32: n must be < 2^31")
         self.edges = torch.tensor(edges, device=self.device, dtype=torch.long).reshape(-1, 2)   # :159
-        self._edges32 = self.edges.to(torch.int32).contiguous()
-        # symmetric CSR of the graph (for the line-graph bound of the KNN)
-        if self.n_edges > 0:
-            e_np = np.asarray(edges, dtype=np.int64)
-            sym = sp.csr_matrix((np.ones(2 * len(e_np), dtype=np.int8),
-                                 (np.concatenate([e_np[:, 0], e_np[:, 1]]), np.concatenate([e_np[:, 1], e_np[:, 0]]))),
-                                shape=(self.n, self.n))
-            sym.sort_indices()
-            self._row_ptr = torch.from_numpy(sym.indptr.astype(np.int64)).to(self.device)
-            self._col = torch.from_numpy(sym.indices.astype(np.int32)).to(self.device)
-        else:
-            self._row_ptr = self._col = None
+        # device-side graph arrays (partition.py): padded vertex numbering (identity on one GPU),
+        # int32 edge endpoints, symmetric CSR + per-vertex upper-edge offsets for the pull kernels
+        self._world, self._rank = self._world_and_rank()
+        self._layout = build_layout(np.asarray(edges, dtype=np.int64).reshape(-1, 2), self.n, self._world,
+                                    hub_degree=int(self._lib.gem_hub_degree()))
+        L = self._layout
+        self._edges32 = torch.from_numpy(L.edges32).to(self.device).contiguous()
+        self._row_ptr = torch.from_numpy(L.row_ptr).to(self.device)
+        self._col = torch.from_numpy(L.col).to(self.device)
+        self._up_ptr = torch.from_numpy(L.up_ptr).to(self.device)
+        self._hubs = torch.from_numpy(L.hubs[self._rank]).to(self.device)
+        self._pad_index = None if L.n_pad == self.n else torch.from_numpy(L.pad_of).to(self.device)
 
         self._has_pykeops = False                               # the PyKeOps branch (:247-258) is removed
         if self.batch_size is None:
@@ -131,7 +132,7 @@ class GraphEmbedderPyTorch:
             self.logger.info("Initialized GraphEmbedderPyTorch (B200 kernels) on %s", self.device)
             self.logger.info("Graph: %d vertices, %d edges, %dD", self.n, self.n_edges, self.n_components)
 
-        self._pos = torch.zeros((self.n, self._ld), device=self.device, dtype=torch.float32)
+        self._pos = torch.zeros((self._layout.n_pad, self._ld), device=self.device, dtype=torch.float32)
         if initial_positions is not None:
             self.positions = initial_positions
         else:
@@ -170,20 +171,33 @@ class GraphEmbedderPyTorch:
         return max(1, min(int(self.batch_size), int(n_query)))
 
     # ------------------------------------------------------------------ state
+    def _world_and_rank(self):
+        """(world size, rank) of the vertex partition: (1, 0) here; ShardedGraphEmbedder overrides."""
+        return 1, 0
+
     @property
     def _positions(self):
-        """(n, d) view of the padded device buffer (reference attribute `_positions`)."""
-        return self._pos[:, : self.n_components]
+        """(n, d) positions on the device (reference attribute `_positions`): a view of the padded
+        buffer on one GPU, a gather of the valid rows when the vertex numbering is padded."""
+        if self._pad_index is None:
+            return self._pos[:, : self.n_components]
+        return self._pos[self._pad_index][:, : self.n_components]
 
     @_positions.setter
     def _positions(self, value):
         value = torch.as_tensor(value).to(device=self.device, dtype=torch.float32)
         if value.shape != (self.n, self.n_components):
             raise ValueError(f"positions must have shape {(self.n, self.n_components)}, got {tuple(value.shape)}")
-        buf = torch.zeros((self.n, self._ld), device=self.device, dtype=torch.float32)
-        buf[:, : self.n_components] = value
-        self._pos = buf
-        self._graph = None
+        buf = torch.zeros((self._layout.n_pad, self._ld), device=self.device, dtype=torch.float32)
+        if self._pad_index is None:
+            buf[:, : self.n_components] = value
+        else:
+            buf[self._pad_index, : self.n_components] = value
+        if getattr(self, "_pos", None) is not None and self._pos.shape == buf.shape:
+            self._pos.copy_(buf)            # keep the address: captured CUDA graphs stay valid
+        else:
+            self._pos = buf
+            self._graph = None
 
     @property
     def positions(self):
@@ -261,8 +275,12 @@ class GraphEmbedderPyTorch:
         p.seed = self._sampler_seed & (2 ** 64 - 1)
         p.pos = self._pos.data_ptr()
         p.edges = self._edges32.data_ptr()
-        p.row_ptr = self._row_ptr.data_ptr() if self._row_ptr is not None else None
-        p.col = self._col.data_ptr() if self._col is not None else None
+        p.row_ptr = self._row_ptr.data_ptr()
+        p.col = self._col.data_ptr() if self.n_edges > 0 else None
+        if self._layout.sorted_edges:                       # precondition of the vertex-parallel spring kernel
+            p.up_ptr = self._up_ptr.data_ptr()
+            p.hubs = self._hubs.data_ptr() if self._hubs.numel() > 0 else None
+            p.n_hubs = int(self._hubs.numel())
         p.tau_hint = b["tau_hint"].data_ptr()
         p.force = b["force"].data_ptr()
         p.mid = b["mid"].data_ptr()
@@ -373,27 +391,33 @@ class GraphEmbedderPyTorch:
         d = self.n_components
         if tuple(host_positions.shape) != (self.n, d) or host_positions.dtype != torch.float32:
             raise ValueError(f"expected an fp32 tensor of shape {(self.n, d)}")
-        if self._ld == d:
+        if self._ld == d and self._pad_index is None:
             self._pos.copy_(host_positions, non_blocking=True)
-        else:
-            stage = self._bufs.get("h2d_stage")
-            if stage is None or stage.shape != host_positions.shape:
-                stage = torch.empty((self.n, d), device=self.device, dtype=torch.float32)
-                self._bufs["h2d_stage"] = stage
-            stage.copy_(host_positions, non_blocking=True)
+            return
+        stage = self._bufs.get("h2d_stage")
+        if stage is None or stage.shape != host_positions.shape:
+            stage = torch.empty((self.n, d), device=self.device, dtype=torch.float32)
+            self._bufs["h2d_stage"] = stage
+        stage.copy_(host_positions, non_blocking=True)
+        if self._pad_index is None:
             self._pos[:, :d].copy_(stage)
+        else:
+            self._pos[self._pad_index, :d] = stage
 
     def read_positions(self, out: torch.Tensor):
         """D2H of the current positions into an (n, d) fp32 host tensor, then stream sync."""
         d = self.n_components
-        if self._ld == d:
+        if self._ld == d and self._pad_index is None:
             out.copy_(self._pos, non_blocking=True)
         else:
             stage = self._bufs.get("d2h_stage")
             if stage is None or stage.shape != out.shape:
                 stage = torch.empty((self.n, d), device=self.device, dtype=torch.float32)
                 self._bufs["d2h_stage"] = stage
-            stage.copy_(self._pos[:, :d])
+            if self._pad_index is None:
+                stage.copy_(self._pos[:, :d])
+            else:
+                stage.copy_(self._pos[self._pad_index][:, :d])
             out.copy_(stage, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         return out
@@ -422,28 +446,38 @@ class GraphEmbedderPyTorch:
             return self._edges32
         return edges.to(device=self.device, dtype=torch.int32).contiguous()
 
-    def _compute_spring_forces(self, positions, edges):
-        """embedder_pytorch.py:595-636 -> (n, d) tensor."""
+    def _spring_stage(self, positions, edges, want_mid):
+        """(force (n,d), mid (e,d) or None) by the stage kernel the iteration itself would use:
+        the vertex-parallel CSR kernel for the object's own (sorted) edge list and d in {2,3},
+        the edge-parallel kernel for any other edge tensor / dimension."""
+        d = int(self.n_components)
+        use_csr = (edges is self.edges and self._layout.sorted_edges and d in (2, 3) and self._pad_index is None
+                   and positions.shape[0] == self.n and self.n_edges > 0)
         pos = self._pad_rows(positions)
+        n_rows = pos.shape[0]
         e32 = self._edges_as_int32(edges)
         force = torch.empty_like(pos)
+        mid = torch.zeros((e32.shape[0] + 1, self._mld), device=self.device, dtype=torch.float32) if want_mid else None
         with torch.cuda.device(self.device):
-            _cabi.check(self._lib.gem_spring_midpoints(_ptr(pos), _ptr(e32), pos.shape[0], e32.shape[0],
-                                                       int(self.n_components), float(self.k_attr), float(self.L_min),
-                                                       _ptr(force), None, self._stream()), "gem_spring_midpoints")
-        return force[:, : self.n_components]
+            if use_csr:
+                _cabi.check(self._lib.gem_spring_midpoints_csr(
+                    _ptr(pos), _ptr(self._row_ptr), _ptr(self._col), _ptr(self._up_ptr), 0, n_rows,
+                    _ptr(self._hubs) if self._hubs.numel() else None, int(self._hubs.numel()), d,
+                    float(self.k_attr), float(self.L_min), _ptr(force), _ptr(mid), 0, self._stream()),
+                    "gem_spring_midpoints_csr")
+            else:
+                _cabi.check(self._lib.gem_spring_midpoints(_ptr(pos), _ptr(e32), n_rows, e32.shape[0], d,
+                                                           float(self.k_attr), float(self.L_min), _ptr(force),
+                                                           _ptr(mid), self._stream()), "gem_spring_midpoints")
+        return force[:, :d], (mid[:-1, :d] if want_mid else None)
+
+    def _compute_spring_forces(self, positions, edges):
+        """embedder_pytorch.py:595-636 -> (n, d) tensor."""
+        return self._spring_stage(positions, edges, False)[0]
 
     def _compute_midpoints(self, positions, edges):
         """The expression at embedder_pytorch.py:785 -> (e, d) tensor (extension, used by tests)."""
-        pos = self._pad_rows(positions)
-        e32 = self._edges_as_int32(edges)
-        force = torch.empty_like(pos)
-        mid = torch.zeros((e32.shape[0] + 1, self._mld), device=self.device, dtype=torch.float32)
-        with torch.cuda.device(self.device):
-            _cabi.check(self._lib.gem_spring_midpoints(_ptr(pos), _ptr(e32), pos.shape[0], e32.shape[0],
-                                                       int(self.n_components), float(self.k_attr), float(self.L_min),
-                                                       _ptr(force), _ptr(mid), self._stream()), "gem_spring_midpoints")
-        return mid[:-1, : self.n_components]
+        return self._spring_stage(positions, edges, True)[1]
 
     def _knn_points(self, query, reference, k, exact=False, return_distances=False):
         query = query.to(device=self.device, dtype=torch.float32).contiguous()

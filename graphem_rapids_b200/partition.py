@@ -1,0 +1,129 @@
+"""Host-side graph layout for the CUDA path (numpy only; no torch, no CUDA -- unit-tested on CPU).
+
+The device works on a *padded vertex numbering*: with G ranks, rank r owns a contiguous range of
+original vertex ids [v_lo[r], v_hi[r]) and stores it at rows [r*slice, r*slice + len_r) of every
+per-vertex array, `slice` = the longest range.  Rows r*slice + len_r .. (r+1)*slice - 1 are dummies
+(degree 0, position 0, never referenced).  This makes every rank's block the same size, so the
+position all-gather of the multi-GPU iteration is one in-place equal-chunk collective and needs
+no unpacking.  With G = 1 the mapping is the identity and there are no dummies.
+
+Edge ids are NOT renumbered: the edge list stays in the reference's order
+(embedder_pytorch.py:220-245, nonzero() order of the upper triangle), because edge ids are what
+the sampler draws and what the KNN returns.  The mapping is monotonic, so an (i,j)-sorted edge list
+stays sorted, and rank r's vertices are the first endpoints of the contiguous edge range
+[up_ptr[v_lo[r]], up_ptr[v_hi[r]]).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List
+
+import numpy as np
+
+
+def edges_sorted_by_ij(edges: np.ndarray) -> bool:
+    """True when the (E,2) list is strictly increasing in (i, j) with i < j (CSR nonzero() order
+    of a canonical matrix) -- the precondition of the vertex-parallel spring kernel."""
+    if len(edges) == 0:
+        return True
+    e = np.asarray(edges, dtype=np.int64)
+    if not np.all(e[:, 0] < e[:, 1]):
+        return False
+    key = e[:, 0] * (int(e.max()) + 1) + e[:, 1]
+    return bool(np.all(key[1:] > key[:-1]))
+
+
+@dataclass
+class GraphLayout:
+    n: int                      # true vertex count
+    n_edges: int
+    world: int
+    slice: int                  # rows per rank block
+    n_pad: int                  # world * slice
+    v_lo: np.ndarray            # (world,) original id range per rank
+    v_hi: np.ndarray
+    e_lo: np.ndarray            # (world,) edge id range whose first endpoint the rank owns
+    e_hi: np.ndarray
+    pad_of: np.ndarray          # (n,) int64: original id -> padded row
+    edges32: np.ndarray         # (E,2) int32, padded ids
+    row_ptr: np.ndarray         # (n_pad+1,) int64  symmetric CSR in padded ids
+    col: np.ndarray             # (2E,) int32, ascending per row
+    up_ptr: np.ndarray          # (n_pad+1,) int64: #edges with first endpoint < row
+    hubs: List[np.ndarray] = field(default_factory=list)   # per rank: padded ids with degree > hub_degree
+    sorted_edges: bool = True
+
+    def rank_rows(self, r: int):
+        """[begin, end) of the rank's VALID rows in padded numbering."""
+        b = r * self.slice
+        return b, b + int(self.v_hi[r] - self.v_lo[r])
+
+    def pad_positions(self, pos: np.ndarray, ld: int) -> np.ndarray:
+        out = np.zeros((self.n_pad, ld), dtype=np.float32)
+        out[self.pad_of, : pos.shape[1]] = pos
+        return out
+
+
+def balanced_vertex_ranges(deg: np.ndarray, up: np.ndarray, world: int, w_entry: float = 1.0, w_edge: float = 10.0,
+                           w_vertex: float = 2.0):
+    """Contiguous vertex ranges with (approximately) equal cost
+        cost(v) = w_entry*deg(v) + w_edge*up(v) + w_vertex
+    (spring work ~ CSR entries, KNN work ~ owned candidate edges, update work ~ vertices; the KNN
+    scan dominates, so the owned edge count is weighted highest).  Every rank gets >= 1 vertex."""
+    n = len(deg)
+    if world > n:
+        raise ValueError(f"cannot shard {n} vertices across {world} ranks")
+    cost = w_entry * deg.astype(np.float64) + w_edge * up.astype(np.float64) + w_vertex
+    cum = np.concatenate([[0.0], np.cumsum(cost)])
+    targets = cum[-1] * np.arange(1, world) / world
+    cuts = np.searchsorted(cum, targets, side="left")
+    bounds = np.concatenate([[0], cuts, [n]]).astype(np.int64)
+    for r in range(1, world + 1):                       # strictly increasing, room for the ranks after r
+        bounds[r] = max(bounds[r], bounds[r - 1] + 1)
+    for r in range(world - 1, 0, -1):
+        bounds[r] = min(bounds[r], bounds[r + 1] - 1)
+    return bounds[:-1].copy(), bounds[1:].copy()
+
+
+def build_layout(edges: np.ndarray, n: int, world: int = 1, hub_degree: int = 128) -> GraphLayout:
+    e = np.asarray(edges, dtype=np.int64).reshape(-1, 2)
+    E = len(e)
+    is_sorted = edges_sorted_by_ij(e)
+    deg = np.bincount(e.ravel(), minlength=n).astype(np.int64) if E else np.zeros(n, np.int64)
+    up = np.bincount(e[:, 0], minlength=n).astype(np.int64) if E else np.zeros(n, np.int64)
+    if world > 1:
+        v_lo, v_hi = balanced_vertex_ranges(deg, up, world)
+    else:
+        v_lo, v_hi = np.array([0], np.int64), np.array([n], np.int64)
+    slice_rows = int((v_hi - v_lo).max())
+    n_pad = world * slice_rows
+    if n_pad >= 2 ** 31:
+        raise ValueError("padded vertex count must stay below 2^31 (int32 vertex ids on the device)")
+    pad_of = np.empty(n, dtype=np.int64)
+    for r in range(world):
+        pad_of[v_lo[r]:v_hi[r]] = r * slice_rows + np.arange(v_hi[r] - v_lo[r])
+    ep = pad_of[e] if E else e
+    # symmetric CSR in padded ids, columns ascending
+    deg_pad = np.zeros(n_pad, np.int64)
+    deg_pad[pad_of] = deg
+    up_pad = np.zeros(n_pad, np.int64)
+    up_pad[pad_of] = up
+    row_ptr = np.concatenate([[0], np.cumsum(deg_pad)]).astype(np.int64)
+    up_ptr = np.concatenate([[0], np.cumsum(up_pad)]).astype(np.int64)
+    if E:
+        src = np.concatenate([ep[:, 0], ep[:, 1]])
+        dst = np.concatenate([ep[:, 1], ep[:, 0]])
+        order = np.lexsort((dst, src))
+        col = dst[order].astype(np.int32)
+    else:
+        col = np.zeros(0, np.int32)
+    up_cum = np.concatenate([[0], np.cumsum(up)])
+    e_lo = up_cum[v_lo].astype(np.int64)
+    e_hi = up_cum[v_hi].astype(np.int64)
+    hubs = []
+    for r in range(world):
+        b = r * slice_rows
+        rows = np.arange(b, b + (v_hi[r] - v_lo[r]))
+        hubs.append(rows[deg_pad[rows] > hub_degree].astype(np.int32))
+    return GraphLayout(n=n, n_edges=E, world=world, slice=slice_rows, n_pad=n_pad, v_lo=v_lo, v_hi=v_hi, e_lo=e_lo,
+                       e_hi=e_hi, pad_of=pad_of, edges32=ep.astype(np.int32).reshape(-1, 2), row_ptr=row_ptr, col=col,
+                       up_ptr=up_ptr, hubs=hubs, sorted_edges=is_sorted)

@@ -1,0 +1,279 @@
+"""Multi-GPU layout iteration: one process per GPU, vertex-range sharding.
+
+Every rank holds the replicated positions and graph arrays and OWNS a contiguous vertex range
+(partition.py).  Because the spring stage is vertex-parallel ("pull" over the CSR), a rank
+produces the COMPLETE force of each vertex it owns -- there is no per-vertex force reduction
+across ranks -- and the midpoints of the edges whose first endpoint it owns, which are its share
+of the KNN candidates.  Per iteration the ranks exchange only
+
+    1. all-gather of the per-rank partial top-(k+1) lists   (S*(k+1)*12 bytes per rank)
+    2. all-reduce of the 2*ld column sums of the update      (tiny)
+    3. all-gather of the updated position blocks             (4*ld*N bytes in total, in place)
+
+The orchestration (`ShardedLayoutEngine`) is device-agnostic: it calls a `stages` object for the
+compute and torch.distributed for the exchanges.  The product binds it to the CUDA C ABI
+(`CudaStages`); the CPU tests bind it to the oracle under gloo to check the sharding logic.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _cabi
+from .embedder import GraphEmbedderPyTorch, _ptr
+from .partition import GraphLayout
+
+
+class ShardedLayoutEngine:
+    """One `update_positions` (embedder_pytorch.py:776-806) across the ranks of `group`."""
+
+    def __init__(self, layout: GraphLayout, rank: int, stages, *, n_components: int, n_neighbors: int,
+                 sample_size: int, group=None, inplace_allgather: bool = True,
+                 pos: Optional[torch.Tensor] = None):
+        self.L, self.rank, self.st, self.group = layout, rank, stages, group
+        self.world = layout.world
+        self.d = int(n_components)
+        self.kp1 = int(n_neighbors) + 1
+        self.S = min(int(sample_size), layout.n_edges)
+        self.inplace = inplace_allgather
+        ld, mld = stages.ld, stages.mld
+        self.vb, self.ve = layout.rank_rows(rank)                  # valid rows of this rank (padded numbering)
+        self.e_lo, self.e_hi = int(layout.e_lo[rank]), int(layout.e_hi[rank])
+        S, kp1 = max(self.S, 1), self.kp1
+        a = stages.alloc
+        self.pos = pos if pos is not None else a((layout.n_pad, ld), torch.float32)
+        self.force = a((layout.slice, ld), torch.float32)
+        self.mid = a((self.e_hi - self.e_lo + 1, mld), torch.float32)
+        self.qmid = a((S, mld), torch.float32)
+        self.tau_hint = a((S,), torch.float32)
+        self.samp = a((S,), torch.int64)
+        self.knn_idx = a((S, kp1), torch.int64)
+        self.knn_dist = a((S, kp1), torch.float32)
+        # packed partial list of one rank: [idx int64 S*kp1 | dist fp32 S*kp1 (+pad to 8 bytes)]
+        self._ib = S * kp1 * 8
+        self._nb = self._ib + (S * kp1 * 4 + 7) // 8 * 8
+        self.part = a((self._nb,), torch.uint8)
+        self.gathered = a((self.world, self._nb), torch.uint8)
+        self.part_idx = self.part[: self._ib].view(torch.int64).view(S, kp1)
+        self.part_dist = self.part[self._ib: self._ib + S * kp1 * 4].view(torch.float32).view(S, kp1)
+        self.g_idx = self.gathered[:, : self._ib].view(torch.int64).view(self.world, S, kp1)
+        self.g_dist = self.gathered[:, self._ib: self._ib + S * kp1 * 4].view(torch.float32).view(self.world, S, kp1)
+        self.stats = a((2 * ld,), torch.float64)                   # column sums | sums of squares
+        self.iteration = 0
+
+    # replicated state in / out (original vertex numbering on the host side)
+    def set_positions(self, pos_nd: torch.Tensor):
+        self.pos.zero_()
+        idx = torch.from_numpy(self.L.pad_of).to(self.pos.device)
+        self.pos[idx, : self.d] = pos_nd.to(device=self.pos.device, dtype=torch.float32)
+
+    def get_positions(self) -> torch.Tensor:
+        idx = torch.from_numpy(self.L.pad_of).to(self.pos.device)
+        return self.pos[idx][:, : self.d]
+
+    # The iteration is three local phases separated by the three exchanges; `step` runs them with
+    # torch.distributed, the single-GPU tests drive several engines ("virtual ranks") phase by phase.
+    def phase_a(self, sampled_indices: Optional[torch.Tensor] = None):
+        """sample -> spring + midpoints of the owned rows -> shard-local KNN (fills self.part)."""
+        st, L = self.st, self.L
+        if L.n_edges == 0 or self.kp1 > L.n_edges:
+            raise RuntimeError("selected index k out of range")       # torch.topk in the reference (:583)
+        if sampled_indices is not None:
+            self.samp.copy_(sampled_indices.to(self.samp.device))
+        else:
+            st.sample(self.iteration, L.n_edges, self.samp)            # same ids on every rank
+        self.iteration += 1
+        # (a) complete spring forces of the owned vertices + midpoints of the owned edges
+        st.spring(self.pos, self.vb, self.ve, self.force, self.mid, self.e_lo)
+        # (b) KNN of the S query midpoints among the owned candidates
+        st.query_mid(self.pos, self.samp, self.qmid)
+        st.hint(self.pos, self.samp, self.kp1, self.tau_hint)
+        st.knn_local(self.mid, self.e_hi - self.e_lo, L.n_edges, self.e_lo, self.qmid, self.tau_hint, self.kp1,
+                     self.part_idx, self.part_dist)
+
+    def phase_b(self):
+        """merge the gathered partial lists -> intersection forces into the owned rows -> update pass 1."""
+        st = self.st
+        st.merge(self.g_idx, self.g_dist, self.knn_idx, self.knn_dist)
+        # (c) every rank evaluates the <= S*k pairs, accumulates only into its own vertex rows
+        st.intersect(self.pos, self.samp, self.knn_idx, self.vb, self.ve, self.force)
+        # (d) update of the owned rows around a global reduction of the column sums
+        st.update_phase1(self.pos[self.vb: self.ve], self.force, self.stats)
+
+    def phase_c(self):
+        """update pass 2 (normalise the owned rows with the reduced column sums)."""
+        self.st.update_phase2(self.pos[self.vb: self.ve], self.L.n, self.stats)
+
+    def own_block(self) -> torch.Tensor:
+        """The rank's block of the position buffer (valid rows + dummies): its all-gather contribution."""
+        return self.pos[self.rank * self.L.slice: (self.rank + 1) * self.L.slice]
+
+    def step(self, sampled_indices: Optional[torch.Tensor] = None):
+        self.phase_a(sampled_indices)
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.gathered.view(-1), self.part, group=self.group)
+        else:
+            self.gathered.view(-1).copy_(self.part)
+        self.phase_b()
+        if self.world > 1:
+            dist.all_reduce(self.stats, group=self.group)
+        self.phase_c()
+        if self.world > 1:
+            block = self.own_block()
+            dist.all_gather_into_tensor(self.pos.view(-1), (block if self.inplace else block.clone()).view(-1),
+                                        group=self.group)
+
+
+class CudaStages:
+    """The compute stages of the engine on the CUDA C ABI (include/graphem_b200.h) for one rank of
+    a GraphLayout.  `arrays` lets the owner share graph tensors it has already uploaded."""
+
+    def __init__(self, layout: GraphLayout, rank: int, device, *, n_components: int, k_attr: float, L_min: float,
+                 k_inter: float, seed: int, arrays: Optional[dict] = None):
+        self.L, self.rank = layout, rank
+        self.device = torch.device(device)
+        self.d = int(n_components)
+        self.k_attr, self.L_min, self.k_inter = float(k_attr), float(L_min), float(k_inter)
+        self.seed = int(seed) & (2 ** 64 - 1)
+        self.lib = _cabi.load()
+        _cabi.init_device(self.device.index if self.device.index is not None else torch.cuda.current_device())
+        self.ld, self.mld = self.lib.gem_row_pitch(self.d), self.lib.gem_mid_pitch(self.d)
+        if not layout.sorted_edges or self.d not in (2, 3):
+            raise NotImplementedError("the multi-GPU path needs an (i,j)-sorted edge list and n_components in {2,3}")
+        up = lambda x: torch.from_numpy(x).to(self.device)           # noqa: E731
+        a = arrays or {}
+        self.edges32 = a["edges32"] if "edges32" in a else up(layout.edges32).contiguous()
+        self.row_ptr = a["row_ptr"] if "row_ptr" in a else up(layout.row_ptr)
+        self.col = a["col"] if "col" in a else up(layout.col)
+        self.up_ptr = a["up_ptr"] if "up_ptr" in a else up(layout.up_ptr)
+        self.hubs = up(layout.hubs[rank])
+        self._iter = torch.zeros((1,), device=self.device, dtype=torch.int64)
+        self._knn_ws = None
+        self._stats_ws = None
+
+    def alloc(self, shape, dtype):
+        return torch.zeros(shape, device=self.device, dtype=dtype)
+
+    def _s(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def sample(self, iteration, n_edges, samp):
+        self._iter.fill_(iteration)
+        _cabi.check(self.lib.gem_sample_edges(self.seed, _ptr(self._iter), 0, n_edges,
+                                              samp.numel(), _ptr(samp), self._s()), "gem_sample_edges")
+
+    def spring(self, pos, vb, ve, force, mid, e_lo):
+        _cabi.check(self.lib.gem_spring_midpoints_csr(
+            _ptr(pos), _ptr(self.row_ptr), _ptr(self.col), _ptr(self.up_ptr), vb, ve,
+            _ptr(self.hubs) if self.hubs.numel() else None, int(self.hubs.numel()), self.d, self.k_attr,
+            self.L_min, _ptr(force), _ptr(mid), e_lo, self._s()), "gem_spring_midpoints_csr")
+
+    def query_mid(self, pos, samp, qmid):
+        _cabi.check(self.lib.gem_query_midpoints(_ptr(pos), _ptr(self.edges32), _ptr(samp), samp.numel(), self.d,
+                                                 _ptr(qmid), self._s()), "gem_query_midpoints")
+
+    def hint(self, pos, samp, kp1, tau_hint):
+        _cabi.check(self.lib.gem_knn_linegraph_hint(_ptr(pos), _ptr(self.row_ptr), _ptr(self.col), _ptr(self.edges32),
+                                                    _ptr(samp), samp.numel(), self.d, kp1, _ptr(tau_hint), self._s()),
+                    "gem_knn_linegraph_hint")
+
+    def knn_local(self, mid, e_loc, e_total, e_lo, qmid, tau_hint, kp1, out_idx, out_dist):
+        S = qmid.shape[0]
+        if self._knn_ws is None:
+            nbytes = ctypes.c_size_t(0)
+            _cabi.check(self.lib.gem_knn_workspace_bytes(max(e_loc, 1), self.d, S, kp1, ctypes.byref(nbytes)))
+            self._knn_ws = torch.zeros((nbytes.value + 256,), device=self.device, dtype=torch.uint8)
+            self._knn_ws_bytes = nbytes.value
+        mm = 1 if (S > 25 or e_total > 25) else 0                     # torch.cdist's rule on the WHOLE problem
+        _cabi.check(self.lib.gem_knn_midpoints_shard(_ptr(mid), e_loc, e_total, e_lo, self.d, _ptr(qmid), S, kp1, mm,
+                                                     _ptr(tau_hint), _ptr(out_idx), _ptr(out_dist), _ptr(self._knn_ws),
+                                                     self._knn_ws_bytes, self._s()), "gem_knn_midpoints_shard")
+
+    def merge(self, g_idx, g_dist, out_idx, out_dist):
+        parts, S, kp1 = g_idx.shape
+        _cabi.check(self.lib.gem_topk_merge_strided(_ptr(g_dist), _ptr(g_idx), g_dist.stride(0), g_idx.stride(0), parts,
+                                                    S, kp1, _ptr(out_idx), _ptr(out_dist), self._s()),
+                    "gem_topk_merge_strided")
+
+    def intersect(self, pos, samp, knn_idx, vb, ve, force):
+        S, kp1 = knn_idx.shape
+        if kp1 > 1 and ve > vb:
+            _cabi.check(self.lib.gem_intersection_forces_range(_ptr(pos), _ptr(self.edges32), pos.shape[0], self.d,
+                                                               _ptr(samp), _ptr(knn_idx), S, kp1, self.k_inter,
+                                                               vb, ve, _ptr(force), self._s()),
+                        "gem_intersection_forces_range")
+
+    def _ws(self, n_rows):
+        if self._stats_ws is None:
+            nbytes = ctypes.c_size_t(0)
+            _cabi.check(self.lib.gem_update_workspace_bytes(max(n_rows, 1), self.d, ctypes.byref(nbytes)))
+            self._stats_ws = torch.zeros((nbytes.value + 256,), device=self.device, dtype=torch.uint8)
+        return self._stats_ws
+
+    def update_phase1(self, own, force, stats):
+        ws = self._ws(own.shape[0])
+        sums = ws[: stats.numel() * 8].view(torch.float64)
+        if own.shape[0] > 0:
+            _cabi.check(self.lib.gem_update_positions(_ptr(own), _ptr(force), None, own.shape[0], own.shape[0], self.d,
+                                                      _ptr(ws), 1, self._s()), "gem_update_positions(phase 1)")
+            stats.copy_(sums)
+        else:
+            stats.zero_()
+
+    def update_phase2(self, own, n_total, stats):
+        ws = self._ws(own.shape[0])
+        ws[: stats.numel() * 8].view(torch.float64).copy_(stats)
+        if own.shape[0] > 0:
+            _cabi.check(self.lib.gem_update_positions(_ptr(own), None, None, own.shape[0], n_total, self.d, _ptr(ws),
+                                                      2, self._s()), "gem_update_positions(phase 2)")
+
+
+class ShardedGraphEmbedder(GraphEmbedderPyTorch):
+    """GraphEmbedderPyTorch across the ranks of a torch.distributed process group (one process
+    per GPU, backend nccl).  Same constructor; every rank passes the same adjacency / seed and ends
+    every iteration with the same replicated positions."""
+
+    def __init__(self, adjacency, n_components=2, *args, process_group=None, **kwargs):
+        if not dist.is_initialized():
+            raise RuntimeError("ShardedGraphEmbedder needs an initialised torch.distributed process group")
+        self._group = process_group
+        super().__init__(adjacency, n_components, *args, **kwargs)
+        if self.sampler != "device":
+            raise NotImplementedError("the multi-GPU path uses the device sampler (identical ids on every rank)")
+        stages = CudaStages(self._layout, self._rank, self.device, n_components=self.n_components, k_attr=self.k_attr,
+                            L_min=self.L_min, k_inter=self.k_inter, seed=self._sampler_seed,
+                            arrays=dict(edges32=self._edges32, row_ptr=self._row_ptr, col=self._col,
+                                        up_ptr=self._up_ptr))
+        self._engine = ShardedLayoutEngine(self._layout, self._rank, stages, n_components=self.n_components,
+                                           n_neighbors=self.n_neighbors, sample_size=self.sample_size,
+                                           group=self._group, pos=self._pos)
+        # rank 0's initial positions are the truth (ARPACK start vectors are not reproducible across processes)
+        dist.broadcast(self._pos, src=dist.get_global_rank(self._group, 0) if self._group is not None else 0,
+                       group=self._group)
+        self._engine.pos = self._pos
+
+    def _world_and_rank(self):
+        return dist.get_world_size(self._group), dist.get_rank(self._group)
+
+    def update_positions(self, sampled_indices=None):
+        with torch.cuda.device(self.device):
+            self._engine.pos = self._pos
+            self._engine.step(sampled_indices)
+        self.last_sampled_indices = self._engine.samp
+        self.last_knn_indices = self._engine.knn_idx[:, 1:]
+
+    def run_layout(self, num_iterations=100):
+        for _ in range(int(num_iterations)):
+            self.update_positions()
+        return self.positions
+
+    def run_layout_device(self, num_iterations=100):
+        for _ in range(int(num_iterations)):
+            self.update_positions()
+
+    def profile_step(self):
+        raise NotImplementedError("per-stage profiling is a single-GPU tool")

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define GEM_ABI_VERSION 1
+#define GEM_ABI_VERSION 2
 
 #define GEM_OK 0
 #define GEM_E_BADARG (-1)      /* null pointer, negative size, unsupported d */
@@ -56,6 +56,21 @@ int gem_mid_pitch(int d);
  * `edges` points at the first edge of the (shard of the) list, `e` edges long. */
 int gem_spring_midpoints(const float *pos, const int32_t *edges, int64_t n, int64_t e, int d,
                          float k_attr, float l_min, float *force, float *mid, void *stream);
+
+/* Same stage in vertex-parallel ("pull") form over the symmetric CSR of the graph -- no atomics,
+ * no zero-fill, deterministic: a group of lanes per vertex v sums the terms of its incident edges
+ * and writes force[v - v_begin]; the row entries w > v are the edges (v,w) with ids
+ * up_ptr[v] .. up_ptr[v+1]-1 (edge list sorted by (i,j)), whose midpoints are written to
+ * mid[(id - mid_base)].  Only d = 2, 3.  The multi-GPU path gives each rank a vertex range
+ * [v_begin, v_end): it produces COMPLETE forces for its vertices and the midpoints of the edges
+ * whose first endpoint it owns, so no force reduction across ranks is needed.
+ *   row_ptr (n+1) int64, col (2e) int32 ascending per row, up_ptr (n+1) int64 (#edges with first
+ *   endpoint < v); hubs: ids (within the range) of the vertices with degree > gem_hub_degree(),
+ *   handled by one CTA each; force -> row v_begin of the accumulator; mid -> row of edge mid_base. */
+int gem_hub_degree(void);
+int gem_spring_midpoints_csr(const float *pos, const int64_t *row_ptr, const int32_t *col, const int64_t *up_ptr,
+                             int64_t v_begin, int64_t v_end, const int32_t *hubs, int64_t n_hubs, int d,
+                             float k_attr, float l_min, float *force, float *mid, int64_t mid_base, void *stream);
 
 /* Sampling of the query edges.  Replaces `torch.randperm(E, device)[:S]` / `arange(E)`
  * (_locate_knn_midpoints, :404-413) by a keyed bijection of [0,e) evaluated at 0..s-1
@@ -81,6 +96,13 @@ int gem_knn_workspace_bytes(int64_t e, int d, int64_t s, int kp1, size_t *bytes)
 int gem_knn_midpoints(const float *mid, int64_t e, int64_t idx_offset, int d, const float *qmid,
                       int64_t s, int kp1, int mm_mode, const float *tau_hint, int64_t *out_idx,
                       float *out_dist, void *ws, size_t ws_bytes, void *stream);
+/* Shard-local form for the multi-GPU path: `mid` holds e of the e_total candidates of the whole
+ * problem (ids idx_offset .. idx_offset+e-1).  The k-range check and torch.cdist's mode choice use
+ * e_total; rows with fewer than kp1 local candidates (or none: e == 0, mid may be NULL) are padded
+ * with (distance +inf, index -1), which gem_topk_merge orders last. */
+int gem_knn_midpoints_shard(const float *mid, int64_t e, int64_t e_total, int64_t idx_offset, int d,
+                            const float *qmid, int64_t s, int kp1, int mm_mode, const float *tau_hint,
+                            int64_t *out_idx, float *out_dist, void *ws, size_t ws_bytes, void *stream);
 /* Optional search radius per query for gem_knn_midpoints (tau_hint, may be NULL): only
  * neighbours with distance <= tau_hint[q] are required.  gem_knn_linegraph_hint computes a valid
  * one: the (k+1)-th smallest exact distance among the edges incident to the endpoints of the query
@@ -106,6 +128,11 @@ int gem_knn_debug_stats(int enable, int64_t e, int d, int64_t s, int kp1, size_t
  * exchange step of the edge-sharded multi-GPU KNN (after an all-gather of the partial lists). */
 int gem_topk_merge(const float *dists, const int64_t *idxs, int parts, int64_t s, int kp1,
                    int64_t *out_idx, float *out_dist, void *stream);
+
+/* Same, with the partial lists of part p at dists + p*dist_stride / idxs + p*idx_stride (elements):
+ * lets one all-gather of a packed {dist | idx} block per rank feed the merge without repacking. */
+int gem_topk_merge_strided(const float *dists, const int64_t *idxs, int64_t dist_stride, int64_t idx_stride,
+                           int parts, int64_t s, int kp1, int64_t *out_idx, float *out_dist, void *stream);
 
 /* (c) intersection repulsion.  Replaces _compute_intersection_forces (:638-736) and
  * _check_line_intersections (:738-774).  knn_full is the (s, kp1) list INCLUDING column 0,
@@ -142,6 +169,9 @@ typedef struct gem_plan {
     const int32_t *edges;     /* (e, 2) */
     const int64_t *row_ptr;   /* (n+1) symmetric CSR offsets, or NULL (no line-graph bound) */
     const int32_t *col;       /* (2e)  symmetric CSR columns, or NULL */
+    const int64_t *up_ptr;    /* (n+1) #edges with first endpoint < v, or NULL (edge-parallel spring kernel) */
+    const int32_t *hubs;      /* (n_hubs) vertices with degree > gem_hub_degree(), or NULL */
+    int64_t n_hubs;
     float *force;             /* (n, ld)   scratch */
     float *mid;               /* (e, mld)  scratch */
     float *qmid;              /* (s, mld)  scratch */

@@ -119,6 +119,91 @@ __global__ void __launch_bounds__(THREADS, MINB) loop_kernel(const float4 *__res
     if (nh) atomicAdd(hits, nh);
 }
 
+
+// ---- flipped roles: lanes hold candidates, the 256 queries are warp-uniform and come from the constant bank
+// (FFMA2 takes the packed coefficient pair as a UNIFORM-register operand: no register-file read for it)
+__constant__ float2 cq0[128], cq1[128], cq2[128];
+template <int C, bool TH_SMEM, int THREADS, int MINB, int U>
+__global__ void __launch_bounds__(THREADS, MINB) flip_kernel(const float4 *__restrict__ cand, const float *__restrict__ theta,
+                                                             int reps, unsigned *__restrict__ hits) {
+    __shared__ __align__(16) float4 tile[kTile];
+    __shared__ __align__(16) float th[256];
+    for (int i = threadIdx.x; i < kTile; i += THREADS) tile[i] = cand[i];
+    for (int i = threadIdx.x; i < 256; i += THREADS) th[i] = theta[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int W = THREADS / 32;
+    unsigned nh = 0;
+    for (int r = 0; r < reps; ++r) {
+        // warp w takes candidate blocks of 32*C: block b -> candidates b*32*C + j*32 + lane
+        for (int b = warp; b * 32 * C < kTile; b += W) {
+            float x[C], y[C], z[C], np[C];
+#pragma unroll
+            for (int j = 0; j < C; ++j) {
+                const float4 t = tile[b * 32 * C + j * 32 + lane];
+                x[j] = t.x; y[j] = t.y; z[j] = t.z; np[j] = __fmul_rn(t.w, 0.99999618530273437f);
+            }
+            bool any = false;
+#pragma unroll U
+            for (int m = 0; m < 128; ++m) {
+                const unsigned long long a0 = *reinterpret_cast<const unsigned long long *>(&cq0[m]);
+                const unsigned long long a1 = *reinterpret_cast<const unsigned long long *>(&cq1[m]);
+                const unsigned long long a2 = *reinterpret_cast<const unsigned long long *>(&cq2[m]);
+                float lo[C], hi[C];
+#pragma unroll
+                for (int j = 0; j < C; ++j) {
+                    unsigned long long f = fma2f(a2, pack2f(z[j], z[j]), pack2f(np[j], np[j]));
+                    f = fma2f(a1, pack2f(y[j], y[j]), f);
+                    f = fma2f(a0, pack2f(x[j], x[j]), f);
+                    unpack2f(f, lo[j], hi[j]);
+                }
+                float ml, mh;
+                if (C == 3) { ml = min3f(lo[0], lo[1], lo[2]); mh = min3f(hi[0], hi[1], hi[2]); }
+                else if (C == 6) { ml = fminf(min3f(lo[0], lo[1], lo[2]), min3f(lo[3 % C], lo[4 % C], lo[5 % C]));
+                                   mh = fminf(min3f(hi[0], hi[1], hi[2]), min3f(hi[3 % C], hi[4 % C], hi[5 % C])); }
+                else { ml = lo[0]; mh = hi[0];
+#pragma unroll
+                    for (int j = 1; j < C; ++j) { ml = fminf(ml, lo[j]); mh = fminf(mh, hi[j]); } }
+                if (TH_SMEM) {
+                    const float2 t2 = *reinterpret_cast<const float2 *>(&th[2 * m]);
+                    any |= (ml <= t2.x); any |= (mh <= t2.y);
+                } else {
+                    any |= (ml <= -100.f); any |= (mh <= -100.f);
+                }
+            }
+            if (any) ++nh;
+        }
+    }
+    if (nh) atomicAdd(hits, nh);
+}
+
+template <int C, bool TH_SMEM, int THREADS, int MINB, int U>
+void run_flip(const char *name, const float4 *cand, const float *theta, unsigned *hits, int sms) {
+    const int blocks = sms * MINB;
+    const int reps = 64;
+    auto k = flip_kernel<C, TH_SMEM, THREADS, MINB, U>;
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, THREADS, 0);
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, k);
+    k<<<blocks, THREADS>>>(cand, theta, 2, hits);
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    float best = 1e30f;
+    for (int it = 0; it < 5; ++it) {
+        cudaEventRecord(a);
+        k<<<blocks, THREADS>>>(cand, theta, reps, hits);
+        cudaEventRecord(b);
+        cudaEventSynchronize(b);
+        float ms; cudaEventElapsedTime(&ms, a, b);
+        if (ms < best) best = ms;
+    }
+    const double pairs = (double)blocks * reps * kTile * 256.0;
+    printf("%-44s regs %3d occ %d/SM(%2d warps)  %.3f ms  %.3e pairs/s  %.1f TFLOP/s(FMA)  c3-scan-equiv %.1f us  err=%s\n", name,
+           fa.numRegs, occ, occ * THREADS / 32, best, pairs / (best * 1e-3), pairs * 6.0 / (best * 1e-3) / 1e12,
+           1.024e9 * 0.99996 / (pairs / (best * 1e-3)) * 1e6, cudaGetErrorString(cudaGetLastError()));
+}
+
 template <int KQ, int G, bool PACKED, bool MASK, bool PF, int THREADS, int MINB>
 void run(const char *name, const float4 *q, const float4 *cand, unsigned *hits, int sms) {
     const int blocks = sms * MINB;
@@ -165,6 +250,32 @@ int main() {
     cudaMemcpy(q, hq, sizeof(hq), cudaMemcpyHostToDevice);
     cudaMemcpy(cand, hc, kTile * sizeof(float4), cudaMemcpyHostToDevice);
 
+    {
+        float2 h0[128], h1[128], h2[128]; float hth[256];
+        for (int m = 0; m < 128; ++m) {
+            h0[m] = make_float2(hq[2 * m].x, hq[2 * m + 1].x); h1[m] = make_float2(hq[2 * m].y, hq[2 * m + 1].y);
+            h2[m] = make_float2(hq[2 * m].z, hq[2 * m + 1].z);
+        }
+        for (int i = 0; i < 256; ++i) hth[i] = -100.f;
+        cudaMemcpyToSymbol(cq0, h0, sizeof(h0)); cudaMemcpyToSymbol(cq1, h1, sizeof(h1)); cudaMemcpyToSymbol(cq2, h2, sizeof(h2));
+        float *theta; cudaMalloc(&theta, 1024); cudaMemcpy(theta, hth, 1024, cudaMemcpyHostToDevice);
+        run_flip<3, true, 256, 2, 128>("flip C3 th-smem 256x2 U128", cand, theta, hits, sms);
+        run_flip<3, true, 256, 2, 16>("flip C3 th-smem 256x2 U16", cand, theta, hits, sms);
+        run_flip<3, true, 256, 4, 16>("flip C3 th-smem 256x4 U16", cand, theta, hits, sms);
+        run_flip<3, true, 256, 4, 8>("flip C3 th-smem 256x4 U8", cand, theta, hits, sms);
+        run_flip<3, false, 256, 4, 8>("flip C3 th-imm 256x4 U8", cand, theta, hits, sms);
+        run_flip<6, true, 256, 2, 128>("flip C6 th-smem 256x2 U128", cand, theta, hits, sms);
+        run_flip<6, true, 256, 2, 16>("flip C6 th-smem 256x2 U16", cand, theta, hits, sms);
+        run_flip<6, true, 256, 2, 8>("flip C6 th-smem 256x2 U8", cand, theta, hits, sms);
+        run_flip<6, true, 256, 3, 8>("flip C6 th-smem 256x3 U8", cand, theta, hits, sms);
+        run_flip<6, true, 256, 4, 8>("flip C6 th-smem 256x4 U8", cand, theta, hits, sms);
+        run_flip<6, true, 256, 4, 4>("flip C6 th-smem 256x4 U4", cand, theta, hits, sms);
+        run_flip<6, false, 256, 4, 8>("flip C6 th-imm 256x4 U8", cand, theta, hits, sms);
+        run_flip<4, true, 256, 4, 8>("flip C4 th-smem 256x4 U8", cand, theta, hits, sms);
+        run_flip<2, true, 256, 4, 8>("flip C2 th-smem 256x4 U8", cand, theta, hits, sms);
+        run_flip<12, true, 128, 4, 4>("flip C12 th-smem 128x4 U4", cand, theta, hits, sms);
+        run_flip<12, true, 128, 4, 8>("flip C12 th-smem 128x4 U8", cand, theta, hits, sms);
+    }
     //   KQ G  PACKED MASK  PF    THREADS MINB
     run<8, 3, true, true, false, 256, 2>("kq8 g3 ffma2 mask (current) 256x2", q, cand, hits, sms);
     run<8, 3, false, true, false, 256, 2>("kq8 g3 ffma  mask 256x2", q, cand, hits, sms);

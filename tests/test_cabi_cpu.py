@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), f"{n} declared in include/graphem_b200.h but not exported"
     assert sorted(_cabi.SIGNATURES) == names, "ctypes SIGNATURES out of sync with the header"
     loaded = _cabi.load()
-    assert loaded.gem_abi_version() == 1
+    assert loaded.gem_abi_version() == _cabi.ABI_VERSION == int(re.search(r"#define GEM_ABI_VERSION (\d+)", open(HEADER).read()).group(1))
     assert loaded.gem_row_pitch(2) == 2 and loaded.gem_row_pitch(3) == 4 and loaded.gem_row_pitch(7) == 7
     assert loaded.gem_mid_pitch(2) == 2 and loaded.gem_mid_pitch(3) == 4 and loaded.gem_mid_pitch(7) == 8
     assert b"out of range" in loaded.gem_error_string(-3)

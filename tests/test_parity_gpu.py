@@ -303,3 +303,65 @@ def test_private_api_shapes_like_reference_tests():
     x = emb._check_line_intersections(torch.tensor([[0., 0.]]), torch.tensor([[1., 1.]]),
                                       torch.tensor([[0., 1.]]), torch.tensor([[1., 0.]]))
     assert x.tolist() == [True]
+
+
+# ----------------------------------------------------------------------------- spring stage: both kernels
+def test_spring_edge_parallel_kernel_matches_golden(golden):
+    """A foreign edge tensor routes to the edge-parallel (atomic) kernel; the object's own sorted
+    list routes to the vertex-parallel CSR kernel (test_spring_forces_and_midpoints)."""
+    emb = make_embedder(golden)
+    edges = emb.edges.clone()
+    F = emb._compute_spring_forces(emb._positions, edges).cpu().numpy()
+    assert rel_inf(F, golden["F_spring"]) <= TOL
+    assert np.array_equal(emb._compute_midpoints(emb._positions, edges).cpu().numpy(), golden["mid"])
+
+
+def test_spring_csr_kernel_hubs_and_determinism():
+    """Preferential-attachment graph with rows far above the hub threshold: CSR kernel == oracle,
+    bitwise reproducible run to run (no atomics), midpoints exact."""
+    import graphem_rapids_b200 as gr
+    n = 60000
+    adj = gr.generate_ba(n, 4, seed=3)
+    pos0 = np.random.default_rng(5).standard_normal((n, 3)).astype(np.float32)
+    emb = gr.GraphEmbedderPyTorch(adj, n_components=3, device="cuda:0", verbose=False, seed=0, initial_positions=pos0)
+    deg = np.asarray(adj.sum(1)).ravel()
+    assert deg.max() > 4 * emb._lib.gem_hub_degree() and emb._hubs.numel() > 0
+    F1 = emb._compute_spring_forces(emb._positions, emb.edges)
+    F2 = emb._compute_spring_forces(emb._positions, emb.edges)
+    assert torch.equal(F1, F2)
+    pos = torch.from_numpy(pos0)
+    ref = oracle.spring_forces(pos, emb.edges.cpu(), 0.2, 1.0).numpy()
+    assert rel_inf(F1.cpu().numpy(), ref) <= TOL
+    mid = emb._compute_midpoints(emb._positions, emb.edges).cpu()
+    assert torch.equal(mid, oracle.midpoints(pos, emb.edges.cpu()))
+    # d = 2 and an isolated vertex (row of length 0 must still be written: no memset precedes the kernel)
+    import scipy.sparse as sp
+    a2 = sp.lil_matrix((500, 500), dtype=np.int64)
+    rr = gr.generate_random_regular(499, 4, seed=1).tocoo()
+    a2[rr.row, rr.col] = 1
+    p2 = np.random.default_rng(6).standard_normal((500, 2)).astype(np.float32)
+    e2 = gr.GraphEmbedderPyTorch(a2.tocsr(), n_components=2, device="cuda:0", verbose=False, seed=0, initial_positions=p2)
+    F = e2._compute_spring_forces(e2._positions, e2.edges).cpu().numpy()
+    assert np.all(F[499] == 0)
+    assert rel_inf(F, oracle.spring_forces(torch.from_numpy(p2), e2.edges.cpu(), 0.2, 1.0).numpy()) <= TOL
+
+
+def test_unsorted_edge_list_falls_back_to_edge_kernel():
+    """A CSR with unsorted column indices gives a nonzero() order that is not (i,j)-sorted: the
+    embedder must keep the reference's edge order and use the edge-parallel kernel."""
+    import scipy.sparse as sp
+    import graphem_rapids_b200 as gr
+    base = gr.generate_random_regular(300, 6, seed=4).tocsr()
+    base.sort_indices()
+    idx = base.indices.copy()
+    for r in range(300):                                   # reverse the column order inside every row
+        idx[base.indptr[r]:base.indptr[r + 1]] = idx[base.indptr[r]:base.indptr[r + 1]][::-1]
+    adj = sp.csr_matrix((base.data, idx, base.indptr), shape=base.shape)
+    pos0 = np.random.default_rng(7).standard_normal((300, 3)).astype(np.float32)
+    emb = gr.GraphEmbedderPyTorch(adj, n_components=3, device="cuda:0", verbose=False, seed=1, initial_positions=pos0)
+    assert not emb._layout.sorted_edges
+    emb.update_positions()
+    samp = emb.last_sampled_indices.cpu()
+    ref = oracle.layout_step(torch.from_numpy(pos0), emb.edges.cpu(), samp, n_neighbors=10, strict=True)
+    assert torch.equal(emb._bufs["knn_idx"].cpu(), ref["knn_full"])
+    assert rel_inf(emb.positions, ref["new_pos"].numpy()) <= TOL

@@ -1,0 +1,134 @@
+"""GPU tests of the multi-GPU path.
+
+1. "Virtual ranks" on ONE GPU: R ShardedLayoutEngine objects bound to the CUDA stages are driven
+   phase by phase in one process, the three exchanges done by local copies.  This exercises every
+   range-restricted kernel entry (CSR spring over a vertex range, shard-local KNN with global ids and
+   short lists, strided merge, vertex-sliced intersection, two-phase update) against the oracle.
+2. Real ranks: 2 processes x 2 GPUs over NCCL (skipped when the box has one GPU).
+"""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import oracle                                              # noqa: E402
+from gem_testutil import rel_inf                                       # noqa: E402
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _graph(kind, n):
+    import graphem_rapids_b200 as gr
+    return {"ba": lambda: gr.generate_ba(n, 4, seed=1), "rr": lambda: gr.generate_random_regular(n, 8, seed=1),
+            "sbm": lambda: gr.generate_sbm(n // 4, 4, 8.0 / (n // 4), 2.0 / n, seed=1)}[kind]()
+
+
+@pytest.mark.parametrize("kind,n,d,k,R", [("ba", 30000, 3, 10, 2), ("rr", 20000, 2, 10, 4), ("sbm", 20000, 3, 32, 3),
+                                          ("rr", 64, 3, 20, 8)])       # last: shards shorter than k+1
+def test_virtual_ranks_one_gpu(kind, n, d, k, R):
+    from graphem_rapids_b200.partition import build_layout
+    from graphem_rapids_b200.sharded import CudaStages, ShardedLayoutEngine
+    from graphem_rapids_b200 import _cabi
+    adj = _graph(kind, n)
+    e = oracle.extract_edges(adj).astype(np.int64)
+    L = build_layout(e, n, R, hub_degree=_cabi.load().gem_hub_degree())
+    dev = torch.device("cuda:0")
+    engines = []
+    for r in range(R):
+        st = CudaStages(L, r, dev, n_components=d, k_attr=0.2, L_min=1.0, k_inter=0.5, seed=9)
+        engines.append(ShardedLayoutEngine(L, r, st, n_components=d, n_neighbors=k, sample_size=128))
+    pos0 = torch.from_numpy(np.random.default_rng(2).standard_normal((n, d)).astype(np.float32))
+    for g in engines:
+        g.set_positions(pos0)
+    ref = pos0.clone()
+    edges = torch.from_numpy(e)
+    for it in range(3):
+        for g in engines:
+            g.phase_a()
+        for g in engines:                                  # exchange 1: all-gather of the packed partial lists
+            for r, src in enumerate(engines):
+                g.gathered[r].copy_(src.part)
+        for g in engines:
+            g.phase_b()
+        total = sum(g.stats for g in engines)              # exchange 2: all-reduce of the column sums
+        for g in engines:
+            g.stats.copy_(total)
+            g.phase_c()
+        for g in engines:                                  # exchange 3: all-gather of the position blocks
+            for src in engines:
+                if src is not g:
+                    g.pos[src.rank * L.slice:(src.rank + 1) * L.slice].copy_(src.own_block())
+        samp = engines[0].samp.cpu()
+        assert all(torch.equal(g.samp.cpu(), samp) for g in engines)
+        o = oracle.layout_step(ref, edges, samp, n_neighbors=k, strict=True)
+        for g in engines:
+            assert torch.equal(g.knn_idx.cpu(), o["knn_full"]) and torch.equal(g.knn_dist.cpu(), o["knn_dist"])
+        got = engines[0].get_positions().cpu()
+        assert all(torch.equal(g.pos, engines[0].pos) for g in engines)
+        assert rel_inf(got.numpy(), o["new_pos"].numpy()) <= TOL
+        ref = got.clone()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _nccl_worker(rank, world, port, out):
+    import torch.distributed as dist
+    import graphem_rapids_b200 as gr
+    from graphem_rapids_b200.sharded import ShardedGraphEmbedder
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        n, d, k = 40000, 3, 10
+        adj = gr.generate_ba(n, 4, seed=1)
+        pos0 = np.random.default_rng(2).standard_normal((n, d)).astype(np.float32)
+        emb = ShardedGraphEmbedder(adj, n_components=d, device=dev, n_neighbors=k, sample_size=256, verbose=False,
+                                   seed=4, initial_positions=pos0)
+        ref = torch.from_numpy(pos0)
+        ok, worst = True, 0.0
+        for it in range(3):
+            emb.update_positions()
+            samp = emb.last_sampled_indices.cpu()
+            o = oracle.layout_step(ref, emb.edges.cpu(), samp, n_neighbors=k, strict=True)
+            ok &= bool(torch.equal(emb._engine.knn_idx.cpu(), o["knn_full"]))
+            got = emb.positions
+            worst = max(worst, rel_inf(got, o["new_pos"].numpy()))
+            ref = torch.from_numpy(got)
+        mine = emb._pos.clone()
+        dist.broadcast(mine, src=0)
+        same = bool(torch.equal(mine, emb._pos))
+        flag = torch.tensor([int(ok and same and worst <= TOL)], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            out.put((int(flag.item()), worst))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_real_ranks_nccl():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=600)
+        assert p.exitcode == 0
+    flag, worst = out.get()
+    assert flag == 1, worst
