@@ -1,5 +1,7 @@
 """CPU: pin oracle/ (the restatement) against golden vectors recorded from the REAL reference
 (tests/golden/make_golden.py).  Bit-exact wherever the reference is deterministic."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -121,3 +123,24 @@ def test_kp1_larger_than_E_raises():
         oracle.knn_strict(mid, torch.arange(5), 7)
     with pytest.raises(RuntimeError):
         oracle.knn_reference(mid, mid, 7, 100)
+
+
+# ----------------------------------------------------------------------------- 50-iteration runs of the real reference
+LONG_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "long")
+LONG_CASES = sorted(f[:-4] for f in os.listdir(LONG_DIR) if f.endswith(".npz"))
+
+
+@pytest.mark.parametrize("name", LONG_CASES)
+def test_oracle_replays_reference_50_iterations(name):
+    """tests/golden/make_golden_long.py: with the samples the reference drew, the oracle lands on the
+    reference's final positions (and therefore on its Spearman(radius, degree/betweenness))."""
+    from scipy.stats import spearmanr
+    z = np.load(os.path.join(LONG_DIR, name + ".npz"))
+    samples = [torch.from_numpy(s.astype(np.int64)) for s in z["samples"]]
+    out = oracle.run_layout(torch.from_numpy(z["pos0"]), torch.from_numpy(z["edges"].astype(np.int64)), len(samples),
+                            sample_size=int(z["sample_size"]), n_neighbors=int(z["n_neighbors"]), strict=True,
+                            samples=samples).numpy()
+    assert np.abs(out - z["final_pos"]).max() <= 1e-5 * np.abs(z["final_pos"]).max()
+    r = np.linalg.norm(out, axis=1)
+    assert abs(spearmanr(r, z["degree"]).correlation - float(z["rho_degree"])) <= 1e-6
+    assert abs(spearmanr(r, z["betweenness"]).correlation - float(z["rho_betweenness"])) <= 1e-6

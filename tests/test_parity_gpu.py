@@ -365,3 +365,37 @@ def test_unsorted_edge_list_falls_back_to_edge_kernel():
     ref = oracle.layout_step(torch.from_numpy(pos0), emb.edges.cpu(), samp, n_neighbors=10, strict=True)
     assert torch.equal(emb._bufs["knn_idx"].cpu(), ref["knn_full"])
     assert rel_inf(emb.positions, ref["new_pos"].numpy()) <= TOL
+
+
+# ----------------------------------------------------------------------------- north star: 50 iterations, Spearman within 0.01
+import os as _os
+_LONG_DIR = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden", "long")
+
+
+@pytest.mark.parametrize("name", sorted(f[:-4] for f in _os.listdir(_LONG_DIR) if f.endswith(".npz")))
+def test_50_iterations_spearman_within_0p01_of_reference(name):
+    """C1 (README quick start, BASELINE.json configs[0]) and a scaled-down C3: 50 iterations with the
+    samples the REAL reference drew; Spearman(radius, degree) and Spearman(radius, betweenness) of the
+    CUDA layout must be within 0.01 of the reference's (tests/golden/make_golden_long.py)."""
+    import graphem_rapids_b200 as gr
+    from scipy.stats import spearmanr
+    z = np.load(_os.path.join(_LONG_DIR, name + ".npz"))
+    n, d = int(z["n"]), int(z["d"])
+    adj = adjacency_from_edges(z["edges"], n)
+    emb = gr.GraphEmbedderPyTorch(adj, n_components=d, device="cuda:0", n_neighbors=int(z["n_neighbors"]),
+                                  sample_size=int(z["sample_size"]), verbose=False, seed=0, initial_positions=z["pos0"])
+    for s in z["samples"]:
+        emb.update_positions(sampled_indices=torch.from_numpy(s.astype(np.int64)))
+    pos = emb.positions
+    r = np.linalg.norm(pos, axis=1)
+    rho_d = spearmanr(r, z["degree"]).correlation
+    rho_b = spearmanr(r, z["betweenness"]).correlation
+    assert abs(rho_d - float(z["rho_degree"])) <= 0.01, (rho_d, float(z["rho_degree"]))
+    assert abs(rho_b - float(z["rho_betweenness"])) <= 0.01, (rho_b, float(z["rho_betweenness"]))
+    # the trajectories themselves stay close (fp32 summation order is the only difference)
+    print(name, "max |pos - ref| / max |ref| after 50 iterations:", rel_inf(pos, z["final_pos"]))
+    # and the product's own device sampler gives a statistically equivalent layout (different samples)
+    emb2 = gr.GraphEmbedderPyTorch(adj, n_components=d, device="cuda:0", n_neighbors=int(z["n_neighbors"]),
+                                   sample_size=int(z["sample_size"]), verbose=False, seed=0, initial_positions=z["pos0"])
+    r2 = np.linalg.norm(emb2.run_layout(50), axis=1)
+    assert abs(spearmanr(r2, z["degree"]).correlation - float(z["rho_degree"])) <= 0.05
