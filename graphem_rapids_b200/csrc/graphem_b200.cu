@@ -489,10 +489,15 @@ __global__ void __launch_bounds__(kThreads) knn_exact_kernel(const float *__rest
 //                                shared memory whose worst key tightens the filter (bounded work even
 //                                when the bound is poor or thousands of distances tie at zero)
 // phase 3  knn_select_kernel   : exact top-(k+1) by (distance, index) among <= G*(k+1) survivors
-constexpr int kQ = 8;                       // queries per lane -> 256 queries per warp pass
-constexpr int kQB = 32 * kQ;                // query block
-constexpr int kTile = 768;                  // candidates per smem stage (multiple of 8 warps x 3-candidate groups)
-constexpr int kStages = 4;
+constexpr int kQ = 8;                       // bound pass: queries per lane -> 256 queries per warp pass
+constexpr int kQB = 32 * kQ;                // query block (queries per scan CTA)
+constexpr int kBoundTile = 768;             // bound pass: candidates per smem tile
+constexpr int kC = 6;                       // scan: candidates per lane
+constexpr int kCandBlock = 32 * kC;         // scan: candidates per warp and tile
+constexpr int kWStages = 2;                 // scan: TMA stages per warp (warp-private ring)
+constexpr int kTile = kWarps * kWStages * kCandBlock;   // scan: candidates staged per CTA at any time
+constexpr int kPairChunk = 8;               // scan: query pairs between two slow-path checks
+constexpr int kMaxBatchQ = 1024;            // queries per scan batch (= constant-bank coefficient capacity)
 constexpr float kSlack = 3.814697265625e-06f;   // 2^-18, see DESIGN.md (filter error budget)
 constexpr int kSurvMax = 1024;
 constexpr int kMaxFastKp1 = 64;
@@ -544,10 +549,10 @@ __global__ void __launch_bounds__(kThreads) knn_bound_kernel(const typename MidT
                                                              int tiles_per_cta, float *__restrict__ chunkmin) {
     using CandT = typename MidT<D>::T;
     __shared__ float red[kWarps][kQB];
-    __shared__ __align__(16) CandT tile[kTile];
+    __shared__ __align__(16) CandT tile[kBoundTile];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = gridDim.x;
-    const int64_t ntiles = (e + kTile - 1) / kTile;
+    const int64_t ntiles = (e + kBoundTile - 1) / kBoundTile;
     for (int qb = 0; qb * kQB < s; ++qb) {
         QueryPar qp[kQ];
         float best[kQ];
@@ -563,8 +568,8 @@ __global__ void __launch_bounds__(kThreads) knn_bound_kernel(const typename MidT
             // i.e. the hub edges of a preferential-attachment graph -- a hopelessly biased sample)
             const int64_t t = ((int64_t)blockIdx.x * ntiles) / g + j;
             if (t >= ntiles || (blockIdx.x + 1 < g && t >= ((int64_t)(blockIdx.x + 1) * ntiles) / g)) break;
-            const int64_t base = t * kTile;
-            const int cnt = (int)min((int64_t)kTile, e - base);
+            const int64_t base = t * kBoundTile;
+            const int cnt = (int)min((int64_t)kBoundTile, e - base);
             __syncthreads();
             for (int c = threadIdx.x; c < cnt; c += kThreads) tile[c] = __ldg(mid + base + c);
             __syncthreads();
@@ -726,10 +731,10 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// dynamic shared memory of the scan: [tiles kStages*kTile CandT][lists kQB*kp1 u64][bound kQB u64]
+// dynamic shared memory of the scan: [stages kWarps*kWStages*kCandBlock CandT][lists kQB*kp1 u64][bound kQB u64]
 //                                    [lqpar kQB float4][ltheta kQB f32][lcount kQB i32][lock kQB i32][wslot kQB i32]
 __host__ __device__ inline size_t scan_smem_bytes(int cand_bytes, int kp1) {
-    return (size_t)kStages * kTile * cand_bytes + (size_t)kQB * kp1 * 8 + (size_t)kQB * 8 + (size_t)kQB * 16 +
+    return (size_t)kTile * cand_bytes + (size_t)kQB * kp1 * 8 + (size_t)kQB * 8 + (size_t)kQB * 16 +
            (size_t)kQB * 4 * 4;
 }
 
@@ -743,7 +748,7 @@ struct ScanShared {
 template <int CandBytes>
 __device__ __forceinline__ ScanShared scan_shared(unsigned char *smem_raw, int kp1) {
     ScanShared S;
-    S.lists = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kStages * kTile * CandBytes);
+    S.lists = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kTile * CandBytes);
     S.bound = S.lists + (size_t)kQB * kp1;
     S.lqpar = reinterpret_cast<float4 *>(const_cast<uint64_t *>(S.bound) + kQB);
     S.ltheta = reinterpret_cast<volatile float *>(S.lqpar + kQB);
@@ -801,11 +806,92 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// Warp-specialised: warp kWarps (one elected lane) is the TMA producer, warps 0..kWarps-1 consume.
-// full[s]/empty[s] mbarrier ring of kStages tiles, so consumer warps drift apart by up to
-// kStages-1 tiles instead of meeting at a CTA barrier every tile; tiles are handed out by a global
-// counter (dynamic scheduling: a CTA slowed down by a hub's tie set simply takes fewer tiles).
-constexpr int kScanThreads = kThreads + 32;
+// ---- scan -------------------------------------------------------------------------------------
+// Roles: the LANES hold candidates (kC per lane, read from the TMA-staged tile), the 256 queries of
+// the CTA's query block are warp-uniform.  Their coefficients (-2q as packed pairs of two queries)
+// sit in the constant bank, so the packed FMA takes them as UNIFORM-register operands
+// (SASS: FFMA2 R, R.F32, UR.F32x2, R): no register-file read for the query side.  Measured on B200
+// (scripts/scan_loop_bench.cu): the register-operand form of the loop saturates the register-file
+// read ports at ~46 TFLOP/s(FMA); this form reaches ~59 of the 72 TFLOP/s FMA peak.
+// c_qcoef[k][b*128 + m] = (a_k of query 2m, a_k of query 2m+1) of query block b; filled by a
+// device-to-device cudaMemcpyToSymbolAsync per batch (knn_fast), so one KNN per device may be in
+// flight at a time (the host class runs on one stream, like the reference).
+__constant__ float2 c_qcoef[3][kMaxBatchQ / 2];
+
+// per batch: thresholds are known, write the coefficient pairs for the constant bank
+template <int D>
+__global__ void knn_qcoef_kernel(const float *__restrict__ qmid, int s, float2 *__restrict__ out /* [3][kMaxBatchQ/2] */) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= kMaxBatchQ / 2) return;
+    QueryPar p0 = {0.f, 0.f, 0.f, 0.f}, p1 = {0.f, 0.f, 0.f, 0.f};
+    if (2 * m < s) p0 = load_query<D>(qmid, 2 * m);
+    if (2 * m + 1 < s) p1 = load_query<D>(qmid, 2 * m + 1);
+    out[0 * (kMaxBatchQ / 2) + m] = make_float2(p0.a0, p1.a0);
+    out[1 * (kMaxBatchQ / 2) + m] = make_float2(p0.a1, p1.a1);
+    out[2 * (kMaxBatchQ / 2) + m] = make_float2(p0.a2, p1.a2);
+}
+
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    for (;;) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(256);                 // the producer must not steal issue slots from its SM sub-partition
+    }
+}
+
+// Rare path, out of line, entered by the WHOLE warp when any lane has a hit.  A set bit c of a
+// lane's `hitmask` says: some (query of the pairs [c*kPairChunk, (c+1)*kPairChunk), candidate of that
+// lane) passed the filter.  The warp resolves one (lane, chunk) event at a time cooperatively: the
+// event's 16 queries x kC candidates are spread over the 32 lanes (the candidates are re-read from
+// the staged tile, which every lane can see), so an event costs a few dozen instructions instead of a
+// 96-pair serial re-scan by one lane with 31 lanes idle.  It runs after the whole query block (not
+// inside the pair loop): a call inside the loop keeps ptxas from using uniform registers there.
+template <int D>
+__device__ __noinline__ void scan_slow_block(unsigned char *smem_raw, int kp1, uint32_t hitmask,
+                                             const typename MidT<D>::T *tile, int cb, int lane, int cnt, uint32_t base,
+                                             unsigned long long *stats) {
+    static_assert(kPairChunk == 8 && kC % 2 == 0, "16 queries x (kC/2) candidate pairs per event");
+    const ScanShared S = scan_shared<sizeof(typename MidT<D>::T)>(smem_raw, kp1);
+    for (;;) {
+        const unsigned pend = __ballot_sync(0xffffffffu, hitmask != 0);
+        if (!pend) break;
+        const int src = __ffs(pend) - 1;                               // lane whose candidates are examined
+        const uint32_t hm = __shfl_sync(0xffffffffu, hitmask, src);
+        const int ch = __ffs(hm) - 1;
+        if (lane == src) hitmask &= hitmask - 1;
+        if (stats && lane == 0) atomicAdd(stats + 3, 1ull);
+        const int ql = 2 * ch * kPairChunk + (lane & 15);
+        const float4 qv = S.lqpar[ql];
+        float th = S.ltheta[ql];
+#pragma unroll
+        for (int r = 0; r < kC / 2; ++r) {
+            const int c = cb + ((lane >> 4) + 2 * r) * 32 + src;
+            if (c < cnt) {                                             // slots past the tile's end are never inserted
+                float x, y, z, n;
+                cand_xyzn(tile[c], x, y, z, n);
+                const float np = __fmul_rn(n, 1.0f - kSlack);
+                const float f = (D == 3) ? fmaf(qv.x, x, fmaf(qv.y, y, fmaf(qv.z, z, np))) : fmaf(qv.x, x, fmaf(qv.y, y, np));
+                if (f <= th) {
+                    scan_insert<D>(smem_raw, kp1, ql, x, y, z, n, base + (uint32_t)c, stats);
+                    th = fminf(th, S.ltheta[ql]);
+                }
+            }
+        }
+    }
+}
+
+// Every warp is its own producer and consumer: it draws blocks of kCandBlock candidates from a
+// global counter (dynamic scheduling at 192-candidate granularity: a warp held up in the insert path
+// simply takes fewer blocks, and the tail of the launch is one block, not one CTA-wide tile) and
+// stages them in a warp-private ring of kWStages TMA bulk copies (cp.async.bulk -> UBLKCP) with one
+// mbarrier per stage.  No CTA-wide tile hand-off, no producer warp, no inter-warp waiting.
+constexpr int kScanThreads = kThreads;
 template <int D>
 __global__ void __launch_bounds__(kScanThreads, 2) knn_scan_kernel(const typename MidT<D>::T *__restrict__ mid, int64_t e,
                                                                    const float *__restrict__ qmid, int s, int kp1,
@@ -814,18 +900,19 @@ __global__ void __launch_bounds__(kScanThreads, 2) knn_scan_kernel(const typenam
                                                                    uint32_t *__restrict__ counts,
                                                                    uint64_t *__restrict__ keys, int cap,
                                                                    uint32_t *__restrict__ tile_counter,
-                                                                   unsigned long long *__restrict__ stats) {
+                                                                   unsigned long long *__restrict__ stats, int qb) {
+    // qb (query block) is a kernel PARAMETER, not blockIdx.y: ptxas keeps parameter-derived values in
+    // uniform registers, which the constant-bank coefficient addressing below depends on
     using CandT = typename MidT<D>::T;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    CandT *tiles = reinterpret_cast<CandT *>(smem_raw);
     const ScanShared S = scan_shared<sizeof(CandT)>(smem_raw, kp1);
-    __shared__ __align__(8) uint64_t full_bar[kStages];
-    __shared__ __align__(8) uint64_t empty_bar[kStages];
-    __shared__ int tile_id[kStages];                        // -1: no more tiles
+    __shared__ __align__(8) uint64_t full_bar[kWarps][kWStages];
+    __shared__ int blk_id[kWarps][kWStages];                 // -1: no more blocks
+    __shared__ unsigned int s_next;                          // next block ordinal of this CTA
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int qb = blockIdx.y;
-    const int64_t ntiles_all = (e + kTile - 1) / kTile;
+    const int lane = threadIdx.x & 31;
+    const int warp = __reduce_max_sync(0xffffffffu, (int)(threadIdx.x >> 5));   // uniform register (see the block id below)
+    const int64_t nblocks = (e + kCandBlock - 1) / kCandBlock;
 
     if (threadIdx.x < kQB) {   // per-query state of this CTA
         const int q = qb * kQB + threadIdx.x;
@@ -845,115 +932,107 @@ __global__ void __launch_bounds__(kScanThreads, 2) knn_scan_kernel(const typenam
         S.wslot[threadIdx.x] = 0;
     }
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], kWarps); }
+        s_next = 0;
+        for (int w = 0; w < kWarps; ++w)
+            for (int i = 0; i < kWStages; ++i) mbar_init(&full_bar[w][i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
 
-    if (warp == kWarps) {
-        // ===== producer =====
-        if (lane == 0) {
-            for (int it = 0;; ++it) {
-                const int st = it % kStages;
-                mbar_wait(&empty_bar[st], (uint32_t)(((it / kStages) & 1) ^ 1));   // first pass: free
-                const uint32_t t = atomicAdd(tile_counter + qb, 1u);
-                if ((int64_t)t >= ntiles_all) {
-                    tile_id[st] = -1;
-                    mbar_arrive(&full_bar[st]);
-                    break;
+    CandT *stages = reinterpret_cast<CandT *>(smem_raw) + (size_t)warp * kWStages * kCandBlock;
+    // lane 0: draw the next block and start its bulk copy into stage st (or post "no more blocks")
+    // Block schedule: CTA c owns blocks c, c+G, c+2G, ... (static, interleaved, so the low-index hub
+    // edges are spread over all CTAs); its warps draw from a SHARED-memory counter (dynamic inside the
+    // CTA).  A global atomic in this instruction stream makes ptxas give up the uniform datapath for
+    // the whole main loop (measured: FFMA2 with UR operands 144 -> 0), a shared one does not.
+    auto fetch = [&](int st) {
+        const int64_t b = (int64_t)blockIdx.x + (int64_t)atomicAdd(&s_next, 1u) * gridDim.x;
+        if (b >= nblocks) {
+            blk_id[warp][st] = -1;
+            mbar_arrive(&full_bar[warp][st]);
+            return;
+        }
+        const int64_t base = b * kCandBlock;
+        const int cnt = (int)min((int64_t)kCandBlock, e - base);
+        CandT *dst = stages + st * kCandBlock;
+        int cnt_tma = cnt;
+        if (sizeof(CandT) == 8 && (cnt & 1)) {              // keep the bulk size a multiple of 16 B
+            cnt_tma = cnt - 1;
+            dst[cnt - 1] = mid[base + cnt - 1];
+        }
+        blk_id[warp][st] = (int)b;
+        const uint32_t bytes = (uint32_t)cnt_tma * (uint32_t)sizeof(CandT);
+        // the stage was last read through the generic proxy by this warp (program order + __syncwarp)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&full_bar[warp][st], bytes);          // release: blk_id / tail element visible to the waiters
+        if (bytes) tma_bulk_g2s(dst, mid + base, bytes, &full_bar[warp][st]);
+    };
+    if (lane == 0) {
+        for (int i = 0; i < kWStages; ++i) fetch(i);
+    }
+    __syncwarp();
+
+    const volatile unsigned long long *th2 =
+        reinterpret_cast<const volatile unsigned long long *>(const_cast<const float *>(S.ltheta));
+    for (int it = 0;; ++it) {
+        const int st = it % kWStages;
+        mbar_wait(&full_bar[warp][st], (uint32_t)((it / kWStages) & 1));
+        // REDUX writes a uniform register: everything below (block bounds, loop control, the constant-bank
+        // addresses of the coefficient pairs) stays on the uniform datapath, which ptxas only uses
+        // when it can prove the value warp-uniform -- a plain shared-memory load is not
+        const int b = __reduce_max_sync(0xffffffffu, blk_id[warp][st]);
+        if (b < 0) break;
+        const int64_t base = (int64_t)b * kCandBlock;
+        const int cnt = (int)min((int64_t)kCandBlock, e - base);
+        const CandT *tile = stages + st * kCandBlock;
+        {
+            float x[kC], y[kC], z[kC], np[kC];
+#pragma unroll
+            for (int j = 0; j < kC; ++j) {
+                const int c = j * 32 + lane;
+                float n;
+                x[j] = y[j] = z[j] = 0.f; np[j] = kInf;                  // slots past the block's end never pass
+                if (c < cnt) {
+                    cand_xyzn(tile[c], x[j], y[j], z[j], n);
+                    np[j] = __fmul_rn(n, 1.0f - kSlack);
                 }
-                const int64_t base = (int64_t)t * kTile;
-                const int cnt = (int)min((int64_t)kTile, e - base);
-                CandT *dst = tiles + st * kTile;
-                int cnt_tma = cnt;
-                if (sizeof(CandT) == 8 && (cnt & 1)) {      // keep the bulk size a multiple of 16 B
-                    cnt_tma = cnt - 1;
-                    dst[cnt - 1] = mid[base + cnt - 1];
-                }
-                tile_id[st] = (int)t;
-                const uint32_t bytes = (uint32_t)cnt_tma * (uint32_t)sizeof(CandT);
-                mbar_expect_tx(&full_bar[st], bytes);       // release: tile_id / tail element visible to waiters
-                if (bytes) tma_bulk_g2s(dst, mid + base, bytes, &full_bar[st]);
             }
-        }
-    } else {
-        // ===== consumers =====
-        // query coefficients as packed pairs (queries 2m, 2m+1 of this lane) for FFMA2
-        unsigned long long a0p[kQ / 2], a1p[kQ / 2], a2p[kQ / 2];
-        float th[kQ];
-#pragma unroll
-        for (int m = 0; m < kQ / 2; ++m) {
-            const float4 qa = S.lqpar[(2 * m) * 32 + lane], qc = S.lqpar[(2 * m + 1) * 32 + lane];
-            a0p[m] = pack2f(qa.x, qc.x); a1p[m] = pack2f(qa.y, qc.y); a2p[m] = pack2f(qa.z, qc.z);
-            th[2 * m] = S.ltheta[(2 * m) * 32 + lane]; th[2 * m + 1] = S.ltheta[(2 * m + 1) * 32 + lane];
-        }
-        constexpr int kGroup = 3;                           // candidates folded into one min3 + compare
-        static_assert(kTile % (kWarps * kGroup) == 0, "tile must hold whole groups");
-        for (int it = 0;; ++it) {
-            const int st = it % kStages;
-            mbar_wait(&full_bar[st], (uint32_t)((it / kStages) & 1));
-            const int t = tile_id[st];
-            if (t < 0) break;
-#pragma unroll
-            for (int i = 0; i < kQ; ++i) th[i] = fminf(th[i], S.ltheta[i * 32 + lane]);   // tightened by other warps
-            const int64_t base = (int64_t)t * kTile;
-            const int cnt = (int)min((int64_t)kTile, e - base);
-            const CandT *tile = tiles + st * kTile;
-            // warp w visits candidates w, w+8, w+16, ... in groups of kGroup; slots past cnt are masked
-            for (int c0 = warp; c0 < cnt; c0 += kWarps * kGroup) {
-                float x[kGroup], y[kGroup], z[kGroup], n[kGroup], np[kGroup];
-#pragma unroll
-                for (int j = 0; j < kGroup; ++j) {
-                    const int c = c0 + j * kWarps;          // c < kTile always
-                    cand_xyzn(tile[c], x[j], y[j], z[j], n[j]);
-                    np[j] = (c < cnt) ? __fmul_rn(n[j], 1.0f - kSlack) : kInf;
-                }
+            uint32_t hitmask = 0;
+            static_assert(kQB / 2 / kPairChunk <= 32, "one bit per pair chunk");
+            for (int mc = 0; mc < kQB / 2; mc += kPairChunk) {
                 bool any = false;
 #pragma unroll
-                for (int m = 0; m < kQ / 2; ++m) {          // 9 FFMA2 + 2 FMNMX3 + 2 FSETP per 6 pairs
-                    float flo[kGroup], fhi[kGroup];
+                for (int u = 0; u < kPairChunk; ++u) {                // per pair of queries: 3*kC FFMA2, min, 2 compares
+                    const int m = qb * (kQB / 2) + mc + u;               // direct constant-bank indexing -> LDCU
+                    const unsigned long long a0 = *reinterpret_cast<const unsigned long long *>(&c_qcoef[0][m]);
+                    const unsigned long long a1 = *reinterpret_cast<const unsigned long long *>(&c_qcoef[1][m]);
+                    const unsigned long long a2 = *reinterpret_cast<const unsigned long long *>(&c_qcoef[2][m]);
+                    float lo[kC], hi[kC];
 #pragma unroll
-                    for (int j = 0; j < kGroup; ++j) {
-                        unsigned long long acc = pack2f(np[j], np[j]);
-                        if (D == 3) acc = fma2f(a2p[m], pack2f(z[j], z[j]), acc);
-                        acc = fma2f(a1p[m], pack2f(y[j], y[j]), acc);
-                        acc = fma2f(a0p[m], pack2f(x[j], x[j]), acc);
-                        unpack2f(acc, flo[j], fhi[j]);
+                    for (int j = 0; j < kC; ++j) {
+                        unsigned long long f = pack2f(np[j], np[j]);
+                        if (D == 3) f = fma2f(a2, pack2f(z[j], z[j]), f);
+                        f = fma2f(a1, pack2f(y[j], y[j]), f);
+                        f = fma2f(a0, pack2f(x[j], x[j]), f);
+                        unpack2f(f, lo[j], hi[j]);
                     }
-                    any |= (min3f(flo[0], flo[1], flo[2]) <= th[2 * m]);
-                    any |= (min3f(fhi[0], fhi[1], fhi[2]) <= th[2 * m + 1]);
+                    static_assert(kC == 6, "min tree below is written for 6 candidates per lane");
+                    const float ml = fminf(min3f(lo[0], lo[1], lo[2]), min3f(lo[3], lo[4], lo[5]));
+                    const float mh = fminf(min3f(hi[0], hi[1], hi[2]), min3f(hi[3], hi[4], hi[5]));
+                    float tx, ty;
+                    unpack2f(th2[mc + u], tx, ty);                    // one LDS.64; thresholds tighten while we run
+                    any |= (ml <= tx);
+                    any |= (mh <= ty);
                 }
-                if (any) {                                  // rare: find the (query, candidate) pairs that passed
-                    if (stats && lane == 0) atomicAdd(stats + 3, 1ull);
-#pragma unroll
-                    for (int j = 0; j < kGroup; ++j) asm volatile("" : "+f"(np[j]));   // recompute below, keep no predicates alive
-#pragma unroll
-                    for (int i = 0; i < kQ; ++i) {
-                        float a0, a1, a2, dummy;
-                        if (i & 1) { unpack2f(a0p[i / 2], dummy, a0); unpack2f(a1p[i / 2], dummy, a1); unpack2f(a2p[i / 2], dummy, a2); }
-                        else { unpack2f(a0p[i / 2], a0, dummy); unpack2f(a1p[i / 2], a1, dummy); unpack2f(a2p[i / 2], a2, dummy); }
-                        float f[kGroup];
-#pragma unroll
-                        for (int j = 0; j < kGroup; ++j)
-                            f[j] = (D == 3) ? fmaf(a0, x[j], fmaf(a1, y[j], fmaf(a2, z[j], np[j])))
-                                            : fmaf(a0, x[j], fmaf(a1, y[j], np[j]));
-                        if (min3f(f[0], f[1], f[2]) <= th[i]) {
-                            const int ql = i * 32 + lane;
-#pragma unroll
-                            for (int j = 0; j < kGroup; ++j) {
-                                const int c = c0 + j * kWarps;
-                                if (f[j] <= th[i] && c < cnt)
-                                    scan_insert<D>(smem_raw, kp1, ql, x[j], y[j], z[j], n[j], (uint32_t)(base + c), stats);
-                            }
-                            th[i] = fminf(th[i], S.ltheta[ql]);
-                        }
-                    }
-                }
+                if (any) hitmask |= 1u << (mc / kPairChunk);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[st]);     // this warp is done with the stage
+            if (__any_sync(0xffffffffu, hitmask != 0))
+                scan_slow_block<D>(smem_raw, kp1, hitmask, tile, 0, lane, cnt, (uint32_t)base, stats);
         }
+        __syncwarp();
+        if (lane == 0) fetch(st);                           // refill the stage this warp has just finished
+        __syncwarp();
     }
     __syncthreads();
     // publish this CTA's survivors: at most kp1 per query, so counts[q] <= gridDim.x * kp1 <= cap
@@ -1393,7 +1472,7 @@ struct KnnLayout {
     int cap;                // published candidates kept per query  (>= g * kp1: cannot overflow)
     int tiles_per_cta;      // bound-pass tiles per CTA
     int64_t sb;             // queries per batch
-    size_t off_chunkmin, off_theta, off_tau, off_counts, off_stats, off_keys, total;
+    size_t off_chunkmin, off_theta, off_tau, off_counts, off_stats, off_qcoef, off_keys, total;
 };
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -1401,7 +1480,7 @@ KnnLayout knn_layout(int64_t e, int64_t s, int kp1) {
     KnnLayout L;
     L.g = 2 * num_sms();
     if (L.g > 1024) L.g = 1024;
-    const int64_t ntiles = (e + kTile - 1) / kTile;
+    const int64_t ntiles = (e + kBoundTile - 1) / kBoundTile;
     // sample ~1/32 of the candidates (at least one tile per CTA, at most 16)
     int64_t tps = ntiles / ((int64_t)32 * L.g);
     if (tps < 1) tps = 1;
@@ -1410,7 +1489,7 @@ KnnLayout knn_layout(int64_t e, int64_t s, int kp1) {
     int cap = (L.g * kp1 + 255) / 256 * 256;          // every CTA publishes at most kp1 keys per query
     if (cap < 1024) cap = 1024;
     L.cap = cap;
-    L.sb = s < 1024 ? s : 1024;                          // <= 4 query blocks per batch (<= 64 tile counters)
+    L.sb = s < kMaxBatchQ ? s : kMaxBatchQ;              // <= 4 query blocks per batch (<= 64 tile counters)
     if (L.sb < 1) L.sb = 1;
     size_t o = 0;
     L.off_chunkmin = o; o = align_up(o + (size_t)L.sb * L.g * sizeof(float), 256);
@@ -1418,6 +1497,7 @@ KnnLayout knn_layout(int64_t e, int64_t s, int kp1) {
     L.off_tau = o;      o = align_up(o + (size_t)L.sb * sizeof(float), 256);
     L.off_counts = o;   o = align_up(o + ((size_t)L.sb + 64) * sizeof(uint32_t), 256);   // + tile counters (one per query block)
     L.off_stats = o;    o = align_up(o + 8 * sizeof(unsigned long long), 256);
+    L.off_qcoef = o;    o = align_up(o + sizeof(float2) * 3 * (kMaxBatchQ / 2), 256);
     L.off_keys = o;     o = align_up(o + (size_t)L.sb * L.cap * sizeof(uint64_t), 256);
     L.total = o;
     return L;
@@ -1451,11 +1531,17 @@ int knn_fast(const float *mid, int64_t e, int64_t idx_offset, const float *qmid,
             chunkmin, L.g, kp1, qm, sb, tau_hint ? tau_hint + q0 : nullptr, theta, tau);
         GEM_CHECK_LAUNCH();
         stage_mark();                                                   // GEM_STAGE_KNN_THRESHOLD
-        dim3 grid(L.g, (sb + kQB - 1) / kQB);
-        knn_scan_kernel<D><<<grid, kScanThreads, scan_smem, st>>>(reinterpret_cast<const CandT *>(mid), e, qm, sb, kp1,
-                                                              theta, tau, counts, keys, L.cap, counts + L.sb,
-                                                              g_knn_stats ? reinterpret_cast<unsigned long long *>(w + L.off_stats) : nullptr);
+        // query coefficients of this batch -> constant bank (uniform operands of the scan's packed FMAs)
+        float2 *qcoef = reinterpret_cast<float2 *>(w + L.off_qcoef);
+        knn_qcoef_kernel<D><<<(kMaxBatchQ / 2 + kThreads - 1) / kThreads, kThreads, 0, st>>>(qm, sb, qcoef);
         GEM_CHECK_LAUNCH();
+        GEM_CUDA(cudaMemcpyToSymbolAsync(c_qcoef, qcoef, sizeof(float2) * 3 * (kMaxBatchQ / 2), 0, cudaMemcpyDeviceToDevice, st));
+        for (int qb = 0; qb * kQB < sb; ++qb) {        // one launch per block of 256 queries (S = 256: one launch)
+            knn_scan_kernel<D><<<L.g, kScanThreads, scan_smem, st>>>(
+                reinterpret_cast<const CandT *>(mid), e, qm, sb, kp1, theta, tau, counts, keys, L.cap, counts + L.sb,
+                g_knn_stats ? reinterpret_cast<unsigned long long *>(w + L.off_stats) : nullptr, qb);
+            GEM_CHECK_LAUNCH();
+        }
         stage_mark();                                                   // GEM_STAGE_KNN_SCAN
         knn_select_kernel<<<sb, kThreads, sel_smem, st>>>(counts, keys, L.cap, kp1, idx_offset,
                                                           out_idx + q0 * kp1, out_dist + q0 * kp1);

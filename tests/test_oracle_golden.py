@@ -130,17 +130,34 @@ LONG_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "l
 LONG_CASES = sorted(f[:-4] for f in os.listdir(LONG_DIR) if f.endswith(".npz"))
 
 
+def long_case_inputs(z):
+    """(edges int64 (E,2), pos0 (n,d)) of a long golden case; the 100 K case stores neither: graph and
+    initial positions are the repo's deterministic ones (tests/golden/make_golden_long.py)."""
+    if "pos0" in z.files:
+        return z["edges"].astype(np.int64), z["pos0"]
+    import graphem_rapids_b200.generators as gen
+    n, d = int(z["n"]), int(z["d"])
+    edges = oracle.extract_edges(gen.generate_ba(n, 4, seed=0)).astype(np.int64)
+    pos0 = (np.random.default_rng(0).standard_normal((n, d)) * 0.1).astype(np.float32)
+    return edges, pos0
+
+
 @pytest.mark.parametrize("name", LONG_CASES)
 def test_oracle_replays_reference_50_iterations(name):
     """tests/golden/make_golden_long.py: with the samples the reference drew, the oracle lands on the
     reference's final positions (and therefore on its Spearman(radius, degree/betweenness))."""
     from scipy.stats import spearmanr
     z = np.load(os.path.join(LONG_DIR, name + ".npz"))
+    edges, pos0 = long_case_inputs(z)
     samples = [torch.from_numpy(s.astype(np.int64)) for s in z["samples"]]
-    out = oracle.run_layout(torch.from_numpy(z["pos0"]), torch.from_numpy(z["edges"].astype(np.int64)), len(samples),
+    out = oracle.run_layout(torch.from_numpy(pos0), torch.from_numpy(edges), len(samples),
                             sample_size=int(z["sample_size"]), n_neighbors=int(z["n_neighbors"]), strict=True,
                             samples=samples).numpy()
-    assert np.abs(out - z["final_pos"]).max() <= 1e-5 * np.abs(z["final_pos"]).max()
+    if "final_pos" in z.files:
+        assert np.abs(out - z["final_pos"]).max() <= 1e-5 * np.abs(z["final_pos"]).max()
     r = np.linalg.norm(out, axis=1)
-    assert abs(spearmanr(r, z["degree"]).correlation - float(z["rho_degree"])) <= 1e-6
-    assert abs(spearmanr(r, z["betweenness"]).correlation - float(z["rho_betweenness"])) <= 1e-6
+    # small cases replay bit for bit; at 100 K vertices torch.topk's tie order / threaded index_add_ make the
+    # reference's own trajectory differ from the strict (distance, index) replay -- within the north star's 0.01
+    tol = 1e-6 if "final_pos" in z.files else 0.01
+    assert abs(spearmanr(r, z["degree"]).correlation - float(z["rho_degree"])) <= tol
+    assert abs(spearmanr(r, z["betweenness"]).correlation - float(z["rho_betweenness"])) <= tol

@@ -373,29 +373,35 @@ _LONG_DIR = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden"
 
 
 @pytest.mark.parametrize("name", sorted(f[:-4] for f in _os.listdir(_LONG_DIR) if f.endswith(".npz")))
-def test_50_iterations_spearman_within_0p01_of_reference(name):
-    """C1 (README quick start, BASELINE.json configs[0]) and a scaled-down C3: 50 iterations with the
-    samples the REAL reference drew; Spearman(radius, degree) and Spearman(radius, betweenness) of the
-    CUDA layout must be within 0.01 of the reference's (tests/golden/make_golden_long.py)."""
+def test_50_iterations_spearman_vs_reference(name):
+    """North star: after 50 iterations Spearman(radius, degree) and Spearman(radius, betweenness) within
+    0.01 of the reference's.  The CUDA path is driven with the 50 samples the REAL reference drew
+    (tests/golden/make_golden_long.py).  The iteration is chaotic: the golden files also hold the
+    reference's own spread under a 1e-7 relative perturbation of the initial positions
+    (`ens_rho_*`, replayed by the bit-identical oracle): 0.02-0.03 at n = 1000-2000, 0.001 at n = 100 000.
+    So the 0.01 bound is asserted as stated on the BASELINE-scale case (ba100k) and widened by three
+    ensemble standard deviations on the small ones."""
     import graphem_rapids_b200 as gr
     from scipy.stats import spearmanr
+    from test_oracle_golden import long_case_inputs
     z = np.load(_os.path.join(_LONG_DIR, name + ".npz"))
     n, d = int(z["n"]), int(z["d"])
-    adj = adjacency_from_edges(z["edges"], n)
-    emb = gr.GraphEmbedderPyTorch(adj, n_components=d, device="cuda:0", n_neighbors=int(z["n_neighbors"]),
-                                  sample_size=int(z["sample_size"]), verbose=False, seed=0, initial_positions=z["pos0"])
+    edges, pos0 = long_case_inputs(z)
+    adj = adjacency_from_edges(edges, n)
+    kw = dict(n_components=d, device="cuda:0", n_neighbors=int(z["n_neighbors"]), sample_size=int(z["sample_size"]),
+              verbose=False, seed=0, initial_positions=pos0)
+    emb = gr.GraphEmbedderPyTorch(adj, **kw)
+    assert np.array_equal(emb.edges.cpu().numpy(), edges)
     for s in z["samples"]:
         emb.update_positions(sampled_indices=torch.from_numpy(s.astype(np.int64)))
-    pos = emb.positions
-    r = np.linalg.norm(pos, axis=1)
-    rho_d = spearmanr(r, z["degree"]).correlation
-    rho_b = spearmanr(r, z["betweenness"]).correlation
-    assert abs(rho_d - float(z["rho_degree"])) <= 0.01, (rho_d, float(z["rho_degree"]))
-    assert abs(rho_b - float(z["rho_betweenness"])) <= 0.01, (rho_b, float(z["rho_betweenness"]))
-    # the trajectories themselves stay close (fp32 summation order is the only difference)
-    print(name, "max |pos - ref| / max |ref| after 50 iterations:", rel_inf(pos, z["final_pos"]))
-    # and the product's own device sampler gives a statistically equivalent layout (different samples)
-    emb2 = gr.GraphEmbedderPyTorch(adj, n_components=d, device="cuda:0", n_neighbors=int(z["n_neighbors"]),
-                                   sample_size=int(z["sample_size"]), verbose=False, seed=0, initial_positions=z["pos0"])
-    r2 = np.linalg.norm(emb2.run_layout(50), axis=1)
-    assert abs(spearmanr(r2, z["degree"]).correlation - float(z["rho_degree"])) <= 0.05
+    r = np.linalg.norm(emb.positions, axis=1)
+    for key, cent in (("degree", z["degree"]), ("betweenness", z["betweenness"])):
+        rho = spearmanr(r, cent).correlation
+        ref = float(z["rho_" + key])
+        tol = 0.01 + (3.0 * float(np.std(z["ens_rho_" + key])) if n < 50_000 else 0.0)
+        print(f"{name}: rho(radius,{key}) cuda {rho:+.4f} reference {ref:+.4f} tol {tol:.3f}")
+        assert abs(rho - ref) <= tol, (key, rho, ref, tol)
+    # the product's own device sampler (different samples) gives a statistically equivalent layout
+    r2 = np.linalg.norm(gr.GraphEmbedderPyTorch(adj, **kw).run_layout(50), axis=1)
+    tol2 = 0.02 + 3.0 * float(np.std(z["ens_rho_degree"]))
+    assert abs(spearmanr(r2, z["degree"]).correlation - float(z["rho_degree"])) <= tol2
