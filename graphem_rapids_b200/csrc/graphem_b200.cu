@@ -543,8 +543,14 @@ __device__ __forceinline__ float filter_threshold(float ta, float qn) {
     return __fadd_ru(th, 1e-37f);
 }
 
+// Candidates come either from the midpoint array or -- `mid == nullptr` -- are recomputed from
+// (pos, edges) with the spring kernel's own expression (identical bits).  The second form depends on
+// the positions only, so gem_layout_step runs the whole bound/threshold preparation on a second
+// stream concurrently with the spring kernel that produces `mid`.
 template <int D>
-__global__ void __launch_bounds__(kThreads) knn_bound_kernel(const typename MidT<D>::T *__restrict__ mid, int64_t e,
+__global__ void __launch_bounds__(kThreads) knn_bound_kernel(const typename MidT<D>::T *__restrict__ mid,
+                                                             const float *__restrict__ pos,
+                                                             const int2 *__restrict__ edges, int64_t e,
                                                              const float *__restrict__ qmid, int s,
                                                              int tiles_per_cta, float *__restrict__ chunkmin) {
     using CandT = typename MidT<D>::T;
@@ -571,7 +577,14 @@ __global__ void __launch_bounds__(kThreads) knn_bound_kernel(const typename MidT
             const int64_t base = t * kBoundTile;
             const int cnt = (int)min((int64_t)kBoundTile, e - base);
             __syncthreads();
-            for (int c = threadIdx.x; c < cnt; c += kThreads) tile[c] = __ldg(mid + base + c);
+            if (mid != nullptr) {
+                for (int c = threadIdx.x; c < cnt; c += kThreads) tile[c] = __ldg(mid + base + c);
+            } else {
+                for (int c = threadIdx.x; c < cnt; c += kThreads) {
+                    const int2 ed = __ldg(edges + base + c);
+                    tile[c] = make_mid(half_sum(Vec<D>::load(pos, ed.x), Vec<D>::load(pos, ed.y)));
+                }
+            }
             __syncthreads();
             for (int c = warp; c < cnt; c += kWarps) {
                 float x, y, z, n;
@@ -665,7 +678,8 @@ template <int D>
 __global__ void __launch_bounds__(kThreads) knn_threshold_kernel(const float *__restrict__ chunkmin, int g, int kp1,
                                                                  const float *__restrict__ qmid, int s,
                                                                  const float *__restrict__ hint,
-                                                                 float *__restrict__ theta, float *__restrict__ tau) {
+                                                                 float *__restrict__ theta, float *__restrict__ tau,
+                                                                 float *__restrict__ qcoef /* [3][kMaxBatchQ/2][2] */) {
     const int lane = threadIdx.x & 31;
     const int q = blockIdx.x * kWarps + (threadIdx.x >> 5);
     if (q >= s) return;
@@ -704,6 +718,10 @@ __global__ void __launch_bounds__(kThreads) knn_threshold_kernel(const float *__
         const QueryPar qp = load_query<D>(qmid, q);
         theta[q] = filter_threshold(ta, qp.qn);
         tau[q] = ta;
+        // staging copy of c_qcoef: pair m = q/2, component q&1
+        qcoef[(0 * (kMaxBatchQ / 2) + q / 2) * 2 + (q & 1)] = qp.a0;
+        qcoef[(1 * (kMaxBatchQ / 2) + q / 2) * 2 + (q & 1)] = qp.a1;
+        qcoef[(2 * (kMaxBatchQ / 2) + q / 2) * 2 + (q & 1)] = qp.a2;
     }
 }
 
@@ -760,6 +778,12 @@ __device__ __forceinline__ ScanShared scan_shared(unsigned char *smem_raw, int k
 
 // Rare path, out of line: candidate (x,y,z,n) with global id `idx` passed the fp32 filter for query
 // slot ql of this CTA; re-evaluate it in the exact cdist chain and insert into the CTA's list.
+//   * list not yet full (the normal regime: a CTA sees ~1/300 of the candidates, so a query's list
+//     rarely fills): lock-free append -- one shared-memory atomicAdd claims a slot, one store fills it;
+//   * list full: under the per-query lock, replace the worst key; the new worst becomes the bound
+//     and tightens the filter threshold (bounded work under poor bounds / thousands of exact ties).
+// Slots hold the sentinel ~0 until written, so the first locked visitor can wait for appends in flight.
+constexpr uint64_t kEmptyKey = ~0ull;
 template <int D>
 __device__ __noinline__ void scan_insert(unsigned char *smem_raw, int kp1, int ql, float x, float y, float z, float n,
                                          uint32_t idx, unsigned long long *stats) {
@@ -770,29 +794,39 @@ __device__ __noinline__ void scan_insert(unsigned char *smem_raw, int kp1, int q
     const uint64_t key = make_key(chain_mm(p, x, y, z, n, D), idx);
     bool pending = key < S.bound[ql];
     if (stats) atomicAdd(stats + (pending ? 1 : 0), 1ull);
+    if (!pending) return;
+    volatile uint64_t *lst = S.lists + (size_t)ql * kp1;
+    const int slot = atomicAdd(&S.lcount[ql], 1);
+    if (slot < kp1) {                                       // lock-free append
+        lst[slot] = key;
+        if (stats) atomicAdd(stats + 2, 1ull);
+        return;
+    }
     while (pending) {                                       // canonical SIMT-safe lock: work inside the loop
         if (atomicCAS(&S.lock[ql], 0, 1) == 0) {
             __threadfence_block();
+            int ws = S.wslot[ql];
+            if (ws < 0) {                                   // first visitor of a full list: find its worst key
+                uint64_t worst = 0;
+                for (int u = 0; u < kp1; ++u) {
+                    uint64_t ku;
+                    while ((ku = lst[u]) == kEmptyKey) {}   // an append that claimed the slot is still in flight
+                    if (ku >= worst) { worst = ku; ws = u; }
+                }
+                S.wslot[ql] = ws;
+                S.bound[ql] = worst;
+                S.ltheta[ql] = fminf(S.ltheta[ql], filter_threshold(key_dist(worst), p.qn));
+            }
             if (key < S.bound[ql]) {
-                uint64_t *lst = S.lists + (size_t)ql * kp1;
-                const int nl = S.lcount[ql];
-                if (nl < kp1) {
-                    lst[nl] = key;
-                    S.lcount[ql] = nl + 1;
-                } else {
-                    lst[S.wslot[ql]] = key;                 // replace the current worst
+                lst[ws] = key;                              // replace the current worst, then find the new one
+                uint64_t worst = 0;
+                for (int u = 0; u < kp1; ++u) {
+                    const uint64_t ku = lst[u];
+                    if (ku >= worst) { worst = ku; ws = u; }
                 }
-                if (nl + 1 >= kp1) {                        // list full: its worst key becomes the bound
-                    uint64_t worst = lst[0];
-                    int ws = 0;
-                    for (int u = 1; u < kp1; ++u) {
-                        const uint64_t ku = lst[u];
-                        if (ku > worst) { worst = ku; ws = u; }
-                    }
-                    S.wslot[ql] = ws;
-                    S.bound[ql] = worst;
-                    S.ltheta[ql] = fminf(S.ltheta[ql], filter_threshold(key_dist(worst), p.qn));
-                }
+                S.wslot[ql] = ws;
+                S.bound[ql] = worst;
+                S.ltheta[ql] = fminf(S.ltheta[ql], filter_threshold(key_dist(worst), p.qn));
                 if (stats) atomicAdd(stats + 2, 1ull);
             }
             __threadfence_block();
@@ -817,19 +851,6 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 // device-to-device cudaMemcpyToSymbolAsync per batch (knn_fast), so one KNN per device may be in
 // flight at a time (the host class runs on one stream, like the reference).
 __constant__ float2 c_qcoef[3][kMaxBatchQ / 2];
-
-// per batch: thresholds are known, write the coefficient pairs for the constant bank
-template <int D>
-__global__ void knn_qcoef_kernel(const float *__restrict__ qmid, int s, float2 *__restrict__ out /* [3][kMaxBatchQ/2] */) {
-    const int m = blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= kMaxBatchQ / 2) return;
-    QueryPar p0 = {0.f, 0.f, 0.f, 0.f}, p1 = {0.f, 0.f, 0.f, 0.f};
-    if (2 * m < s) p0 = load_query<D>(qmid, 2 * m);
-    if (2 * m + 1 < s) p1 = load_query<D>(qmid, 2 * m + 1);
-    out[0 * (kMaxBatchQ / 2) + m] = make_float2(p0.a0, p1.a0);
-    out[1 * (kMaxBatchQ / 2) + m] = make_float2(p0.a1, p1.a1);
-    out[2 * (kMaxBatchQ / 2) + m] = make_float2(p0.a2, p1.a2);
-}
 
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity) {
     uint32_t done;
@@ -929,7 +950,8 @@ __global__ void __launch_bounds__(kScanThreads, 2) knn_scan_kernel(const typenam
         S.ltheta[threadIdx.x] = th;
         S.lcount[threadIdx.x] = 0;
         S.lock[threadIdx.x] = 0;
-        S.wslot[threadIdx.x] = 0;
+        S.wslot[threadIdx.x] = -1;                          // worst slot unknown until the list is full
+        for (int u = 0; u < kp1; ++u) S.lists[(size_t)threadIdx.x * kp1 + u] = kEmptyKey;
     }
     if (threadIdx.x == 0) {
         s_next = 0;
@@ -1038,7 +1060,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) knn_scan_kernel(const typenam
     // publish this CTA's survivors: at most kp1 per query, so counts[q] <= gridDim.x * kp1 <= cap
     if (threadIdx.x < kQB) {
         const int q = qb * kQB + threadIdx.x;
-        const int nl = S.lcount[threadIdx.x];
+        const int nl = min(S.lcount[threadIdx.x], kp1);     // the counter keeps running past a full list
         if (q < s && nl > 0) {
             const uint32_t slot = atomicAdd(counts + q, (uint32_t)nl);
             const uint64_t *lst = S.lists + (size_t)threadIdx.x * kp1;
@@ -1048,11 +1070,141 @@ __global__ void __launch_bounds__(kScanThreads, 2) knn_scan_kernel(const typenam
     }
 }
 
+// merge `parts` sorted partial lists per query by (distance, index); total <= kMaxKp1 * 8
+__global__ void __launch_bounds__(kThreads) topk_merge_kernel(const float *__restrict__ dists,
+                                                              const int64_t *__restrict__ idxs, int64_t dist_stride,
+                                                              int64_t idx_stride, int parts, int64_t s,
+                                                              int kp1, int64_t *__restrict__ out_idx,
+                                                              float *__restrict__ out_dist) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int total = parts * kp1;
+    float *sd = reinterpret_cast<float *>(smem_raw);                        // total
+    int64_t *si = reinterpret_cast<int64_t *>(smem_raw + (((size_t)total * 4 + 15) / 16) * 16);   // total
+    const int64_t q = blockIdx.x;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int p = i / kp1, r = i % kp1;
+        sd[i] = dists[(int64_t)p * dist_stride + q * kp1 + r] + 0.f;
+        si[i] = idxs[(int64_t)p * idx_stride + q * kp1 + r];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const float dv = sd[i];
+        const int64_t iv = si[i];
+        int r = 0;
+        for (int u = 0; u < total; ++u) {
+            const float du = sd[u];
+            r += (du < dv) || (du == dv && si[u] < iv);
+        }
+        if (r < kp1) { out_idx[q * kp1 + r] = iv; out_dist[q * kp1 + r] = dv; }
+    }
+}
+
+// ==========================================================================================
+// (c) intersection repulsion (embedder_pytorch.py:638-736, :738-774)
+// ==========================================================================================
+__device__ __forceinline__ float orient2d(float ax, float ay, float bx, float by, float cx, float cy) {
+    // (b0-a0)*(c1-a1) - (b1-a1)*(c0-a0), every op rounded (:762-763)
+    return __fsub_rn(__fmul_rn(__fsub_rn(bx, ax), __fsub_rn(cy, ay)), __fmul_rn(__fsub_rn(by, ay), __fsub_rn(cx, ax)));
+}
+
+// one candidate pair (edge i = sampled query edge, edge j = one of its neighbours)
+template <int D>
+__device__ __forceinline__ void intersect_pair(const float *__restrict__ pos, const int2 *__restrict__ edges, int64_t i,
+                                               int64_t j, float k_inter, int v_begin, int v_end,
+                                               float *__restrict__ force) {
+    if (!(i < j)) return;                                        // :672  (also drops the -1 padding of a short list)
+    const int2 ei = edges[i], ej = edges[j];                     // :681-682
+    if (ei.x == ej.x || ei.x == ej.y || ei.y == ej.x || ei.y == ej.y) return;   // :685-692
+    const Vec<D> p1 = Vec<D>::load(pos, ei.x), p2 = Vec<D>::load(pos, ei.y);    // :702-705
+    const Vec<D> q1 = Vec<D>::load(pos, ej.x), q2 = Vec<D>::load(pos, ej.y);
+    const float o1 = orient2d(p1.x, p1.y, p2.x, p2.y, q1.x, q1.y);              // :766-769
+    const float o2 = orient2d(p1.x, p1.y, p2.x, p2.y, q2.x, q2.y);
+    const float o3 = orient2d(q1.x, q1.y, q2.x, q2.y, p1.x, p1.y);
+    const float o4 = orient2d(q1.x, q1.y, q2.x, q2.y, p2.x, p2.y);
+    if (!((__fmul_rn(o1, o2) < 0.f) && (__fmul_rn(o3, o4) < 0.f))) return;      // :772
+    const Vec<D> cen = (((p1 + p2) + q1) + q2) / 4.0f;                          // :722
+    const Vec<D> v[4] = {p1, p2, q1, q2};
+    const int vid[4] = {ei.x, ei.y, ej.x, ej.y};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {                                               // :727-734
+        const Vec<D> diff = v[u] - cen;
+        const float dist = norm2(diff) + 1e-6f;
+        const Vec<D> rep = (k_inter * diff) / (dist * dist);
+        // vertex-sliced accumulation (multi-GPU: a rank adds only into the vertex range it owns)
+        if (vid[u] >= v_begin && vid[u] < v_end) rep.red_add(force, vid[u] - v_begin);
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(kThreads) intersection_kernel(const float *__restrict__ pos,
+                                                                const int2 *__restrict__ edges,
+                                                                const int64_t *__restrict__ samp,
+                                                                const int64_t *__restrict__ knn_full, int64_t s, int kp1,
+                                                                float k_inter, int v_begin, int v_end,
+                                                                float *__restrict__ force) {
+    const int k = kp1 - 1;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= s * k) return;
+    const int64_t r = t / k;
+    const int c = (int)(t % k);
+    // :668 sampled edge, :421 column 0 dropped, :669 neighbour
+    intersect_pair<D>(pos, edges, samp[r], knn_full[r * kp1 + 1 + c], k_inter, v_begin, v_end, force);
+}
+
+__global__ void __launch_bounds__(kThreads) intersection_generic_kernel(const float *__restrict__ pos,
+                                                                        const int2 *__restrict__ edges,
+                                                                        const int64_t *__restrict__ samp,
+                                                                        const int64_t *__restrict__ knn_full, int64_t s,
+                                                                        int kp1, int d, float k_inter, int v_begin,
+                                                                        int v_end, float *__restrict__ force) {
+    const int k = kp1 - 1;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= s * k) return;
+    const int64_t r = t / k;
+    const int c = (int)(t % k);
+    const int64_t i = samp[r];
+    const int64_t j = knn_full[r * kp1 + 1 + c];
+    if (!(i < j)) return;
+    const int2 ei = edges[i], ej = edges[j];
+    if (ei.x == ej.x || ei.x == ej.y || ei.y == ej.x || ei.y == ej.y) return;
+    const float *p1 = pos + (int64_t)ei.x * d, *p2 = pos + (int64_t)ei.y * d;
+    const float *q1 = pos + (int64_t)ej.x * d, *q2 = pos + (int64_t)ej.y * d;
+    const float o1 = orient2d(p1[0], p1[1], p2[0], p2[1], q1[0], q1[1]);
+    const float o2 = orient2d(p1[0], p1[1], p2[0], p2[1], q2[0], q2[1]);
+    const float o3 = orient2d(q1[0], q1[1], q2[0], q2[1], p1[0], p1[1]);
+    const float o4 = orient2d(q1[0], q1[1], q2[0], q2[1], p2[0], p2[1]);
+    if (!((__fmul_rn(o1, o2) < 0.f) && (__fmul_rn(o3, o4) < 0.f))) return;
+    const float *v[4] = {p1, p2, q1, q2};
+    const int vid[4] = {ei.x, ei.y, ej.x, ej.y};
+    for (int u = 0; u < 4; ++u) {
+        if (vid[u] < v_begin || vid[u] >= v_end) continue;
+        float nsq = 0.f;
+        for (int a = 0; a < d; ++a) {
+            const float cen = __fdiv_rn(((p1[a] + p2[a]) + q1[a]) + q2[a], 4.0f);
+            const float df = v[u][a] - cen;
+            nsq = (a == 0) ? df * df : fmaf(df, df, nsq);
+        }
+        const float dist = __fsqrt_rn(nsq) + 1e-6f;
+        const float dd = dist * dist;
+        for (int a = 0; a < d; ++a) {
+            const float cen = __fdiv_rn(((p1[a] + p2[a]) + q1[a]) + q2[a], 4.0f);
+            atomicAdd(force + (int64_t)(vid[u] - v_begin) * d + a, __fdiv_rn(k_inter * (v[u][a] - cen), dd));
+        }
+    }
+}
+
 // per query: exact top-kp1 among n = counts[q] <= cap published keys (unique)
+// Optional fused tail (fx.force != nullptr): the CTA of query q then evaluates the k candidate
+// pairs (samp[q], neighbour c) of _compute_intersection_forces -- the separate intersection launch
+// and its dependency on this kernel disappear from the iteration's critical path.
+struct FusedIntersect {
+    const float *pos; const int2 *edges; const int64_t *samp; float *force;
+    float k_inter; int d, v_begin, v_end;
+};
 __global__ void __launch_bounds__(kThreads) knn_select_kernel(const uint32_t *__restrict__ counts,
                                                               const uint64_t *__restrict__ keys, int cap, int kp1,
                                                               int64_t idx_offset, int64_t *__restrict__ out_idx,
-                                                              float *__restrict__ out_dist) {
+                                                              float *__restrict__ out_dist, FusedIntersect fx) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *all = reinterpret_cast<uint64_t *>(smem_raw);        // cap
     __shared__ uint64_t sub[kThreads];
@@ -1103,123 +1255,16 @@ __global__ void __launch_bounds__(kThreads) knn_select_kernel(const uint32_t *__
             out_dist[(int64_t)q * kp1 + r] = key_dist(k);
         }
     }
-}
-
-// merge `parts` sorted partial lists per query by (distance, index); total <= kMaxKp1 * 8
-__global__ void __launch_bounds__(kThreads) topk_merge_kernel(const float *__restrict__ dists,
-                                                              const int64_t *__restrict__ idxs, int64_t dist_stride,
-                                                              int64_t idx_stride, int parts, int64_t s,
-                                                              int kp1, int64_t *__restrict__ out_idx,
-                                                              float *__restrict__ out_dist) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int total = parts * kp1;
-    float *sd = reinterpret_cast<float *>(smem_raw);                        // total
-    int64_t *si = reinterpret_cast<int64_t *>(smem_raw + (((size_t)total * 4 + 15) / 16) * 16);   // total
-    const int64_t q = blockIdx.x;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const int p = i / kp1, r = i % kp1;
-        sd[i] = dists[(int64_t)p * dist_stride + q * kp1 + r] + 0.f;
-        si[i] = idxs[(int64_t)p * idx_stride + q * kp1 + r];
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const float dv = sd[i];
-        const int64_t iv = si[i];
-        int r = 0;
-        for (int u = 0; u < total; ++u) {
-            const float du = sd[u];
-            r += (du < dv) || (du == dv && si[u] < iv);
-        }
-        if (r < kp1) { out_idx[q * kp1 + r] = iv; out_dist[q * kp1 + r] = dv; }
-    }
-}
-
-// ==========================================================================================
-// (c) intersection repulsion (embedder_pytorch.py:638-736, :738-774)
-// ==========================================================================================
-__device__ __forceinline__ float orient2d(float ax, float ay, float bx, float by, float cx, float cy) {
-    // (b0-a0)*(c1-a1) - (b1-a1)*(c0-a0), every op rounded (:762-763)
-    return __fsub_rn(__fmul_rn(__fsub_rn(bx, ax), __fsub_rn(cy, ay)), __fmul_rn(__fsub_rn(by, ay), __fsub_rn(cx, ax)));
-}
-
-template <int D>
-__global__ void __launch_bounds__(kThreads) intersection_kernel(const float *__restrict__ pos,
-                                                                const int2 *__restrict__ edges,
-                                                                const int64_t *__restrict__ samp,
-                                                                const int64_t *__restrict__ knn_full, int64_t s, int kp1,
-                                                                float k_inter, int v_begin, int v_end,
-                                                                float *__restrict__ force) {
-    const int k = kp1 - 1;
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= s * k) return;
-    const int64_t r = t / k;
-    const int c = (int)(t % k);
-    const int64_t i = samp[r];                                   // :668
-    const int64_t j = knn_full[r * kp1 + 1 + c];                 // :421 column 0 dropped, :669
-    if (!(i < j)) return;                                        // :672  (also drops the -1 padding of a short list)
-    const int2 ei = edges[i], ej = edges[j];                     // :681-682
-    if (ei.x == ej.x || ei.x == ej.y || ei.y == ej.x || ei.y == ej.y) return;   // :685-692
-    const Vec<D> p1 = Vec<D>::load(pos, ei.x), p2 = Vec<D>::load(pos, ei.y);    // :702-705
-    const Vec<D> q1 = Vec<D>::load(pos, ej.x), q2 = Vec<D>::load(pos, ej.y);
-    const float o1 = orient2d(p1.x, p1.y, p2.x, p2.y, q1.x, q1.y);              // :766-769
-    const float o2 = orient2d(p1.x, p1.y, p2.x, p2.y, q2.x, q2.y);
-    const float o3 = orient2d(q1.x, q1.y, q2.x, q2.y, p1.x, p1.y);
-    const float o4 = orient2d(q1.x, q1.y, q2.x, q2.y, p2.x, p2.y);
-    if (!((__fmul_rn(o1, o2) < 0.f) && (__fmul_rn(o3, o4) < 0.f))) return;      // :772
-    const Vec<D> cen = (((p1 + p2) + q1) + q2) / 4.0f;                          // :722
-    const Vec<D> v[4] = {p1, p2, q1, q2};
-    const int vid[4] = {ei.x, ei.y, ej.x, ej.y};
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {                                               // :727-734
-        const Vec<D> diff = v[u] - cen;
-        const float dist = norm2(diff) + 1e-6f;
-        const Vec<D> rep = (k_inter * diff) / (dist * dist);
-        // vertex-sliced accumulation (multi-GPU: a rank adds only into the vertex range it owns)
-        if (vid[u] >= v_begin && vid[u] < v_end) rep.red_add(force, vid[u] - v_begin);
-    }
-}
-
-__global__ void __launch_bounds__(kThreads) intersection_generic_kernel(const float *__restrict__ pos,
-                                                                        const int2 *__restrict__ edges,
-                                                                        const int64_t *__restrict__ samp,
-                                                                        const int64_t *__restrict__ knn_full, int64_t s,
-                                                                        int kp1, int d, float k_inter, int v_begin,
-                                                                        int v_end, float *__restrict__ force) {
-    const int k = kp1 - 1;
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= s * k) return;
-    const int64_t r = t / k;
-    const int c = (int)(t % k);
-    const int64_t i = samp[r];
-    const int64_t j = knn_full[r * kp1 + 1 + c];
-    if (!(i < j)) return;
-    const int2 ei = edges[i], ej = edges[j];
-    if (ei.x == ej.x || ei.x == ej.y || ei.y == ej.x || ei.y == ej.y) return;
-    const float *p1 = pos + (int64_t)ei.x * d, *p2 = pos + (int64_t)ei.y * d;
-    const float *q1 = pos + (int64_t)ej.x * d, *q2 = pos + (int64_t)ej.y * d;
-    const float o1 = orient2d(p1[0], p1[1], p2[0], p2[1], q1[0], q1[1]);
-    const float o2 = orient2d(p1[0], p1[1], p2[0], p2[1], q2[0], q2[1]);
-    const float o3 = orient2d(q1[0], q1[1], q2[0], q2[1], p1[0], p1[1]);
-    const float o4 = orient2d(q1[0], q1[1], q2[0], q2[1], p2[0], p2[1]);
-    if (!((__fmul_rn(o1, o2) < 0.f) && (__fmul_rn(o3, o4) < 0.f))) return;
-    const float *v[4] = {p1, p2, q1, q2};
-    const int vid[4] = {ei.x, ei.y, ej.x, ej.y};
-    for (int u = 0; u < 4; ++u) {
-        if (vid[u] < v_begin || vid[u] >= v_end) continue;
-        float nsq = 0.f;
-        for (int a = 0; a < d; ++a) {
-            const float cen = __fdiv_rn(((p1[a] + p2[a]) + q1[a]) + q2[a], 4.0f);
-            const float df = v[u][a] - cen;
-            nsq = (a == 0) ? df * df : fmaf(df, df, nsq);
-        }
-        const float dist = __fsqrt_rn(nsq) + 1e-6f;
-        const float dd = dist * dist;
-        for (int a = 0; a < d; ++a) {
-            const float cen = __fdiv_rn(((p1[a] + p2[a]) + q1[a]) + q2[a], 4.0f);
-            atomicAdd(force + (int64_t)(vid[u] - v_begin) * d + a, __fdiv_rn(k_inter * (v[u][a] - cen), dd));
+    if (fx.force != nullptr) {
+        __syncthreads();                                     // the list of this query is complete (same CTA wrote it)
+        for (int c = t; c < kp1 - 1; c += kThreads) {
+            const int64_t i = fx.samp[q], j = out_idx[(int64_t)q * kp1 + 1 + c];
+            if (fx.d == 2) intersect_pair<2>(fx.pos, fx.edges, i, j, fx.k_inter, fx.v_begin, fx.v_end, fx.force);
+            else intersect_pair<3>(fx.pos, fx.edges, i, j, fx.k_inter, fx.v_begin, fx.v_end, fx.force);
         }
     }
 }
+
 
 // ==========================================================================================
 // (d) update (embedder_pytorch.py:796-804): two passes around one global reduction
@@ -1503,54 +1548,85 @@ KnnLayout knn_layout(int64_t e, int64_t s, int kp1) {
     return L;
 }
 
+// Phase A of the fast path (one query batch): bound -> threshold (+ coefficient pairs) -> constant
+// bank.  Reads the candidates from `mid`, or recomputes the sampled ones from (pos, edges) when
+// mid == nullptr, in which case nothing here depends on the spring kernel's output.
 template <int D>
-int knn_fast(const float *mid, int64_t e, int64_t idx_offset, const float *qmid, int64_t s, int kp1,
-             const float *tau_hint, int64_t *out_idx, float *out_dist, void *ws, size_t ws_bytes, cudaStream_t st) {
+int knn_prepare(const KnnLayout &L, char *w, const float *mid, const float *pos, const int2 *edges, int64_t e,
+                const float *qm, int sb, int kp1, const float *tau_hint, cudaStream_t st) {
     using CandT = typename MidT<D>::T;
-    const KnnLayout L = knn_layout(e, s, kp1);
-    if (ws == nullptr || ws_bytes < L.total || ((uintptr_t)ws & 255)) return GEM_E_WORKSPACE;
-    if (((uintptr_t)mid & 15) || ((uintptr_t)qmid & 15)) return GEM_E_BADARG;
-    char *w = reinterpret_cast<char *>(ws);
     float *chunkmin = reinterpret_cast<float *>(w + L.off_chunkmin);
+    float *theta = reinterpret_cast<float *>(w + L.off_theta);
+    float *tau = reinterpret_cast<float *>(w + L.off_tau);
+    uint32_t *counts = reinterpret_cast<uint32_t *>(w + L.off_counts);
+    float *qcoef = reinterpret_cast<float *>(w + L.off_qcoef);
+    GEM_CUDA(cudaMemsetAsync(counts, 0, ((size_t)L.sb + 64) * sizeof(uint32_t), st));
+    knn_bound_kernel<D><<<L.g, kThreads, 0, st>>>(reinterpret_cast<const CandT *>(mid), pos, edges, e, qm, sb,
+                                                  L.tiles_per_cta, chunkmin);
+    GEM_CHECK_LAUNCH();
+    stage_mark();                                                   // GEM_STAGE_KNN_BOUND
+    knn_threshold_kernel<D><<<(sb + kWarps - 1) / kWarps, kThreads, 0, st>>>(chunkmin, L.g, kp1, qm, sb, tau_hint, theta,
+                                                                             tau, qcoef);
+    GEM_CHECK_LAUNCH();
+    // query coefficients of this batch -> constant bank (uniform operands of the scan's packed FMAs)
+    GEM_CUDA(cudaMemcpyToSymbolAsync(c_qcoef, qcoef, sizeof(float2) * 3 * (kMaxBatchQ / 2), 0, cudaMemcpyDeviceToDevice, st));
+    stage_mark();                                                   // GEM_STAGE_KNN_THRESHOLD
+    return GEM_OK;
+}
+
+// Phase B: scan (one launch per block of 256 queries) -> select (+ optional fused intersection forces)
+template <int D>
+int knn_scan_select(const KnnLayout &L, char *w, const float *mid, int64_t e, int64_t idx_offset, const float *qm, int sb,
+                    int kp1, int64_t *out_idx, float *out_dist, const FusedIntersect &fx, cudaStream_t st) {
+    using CandT = typename MidT<D>::T;
     float *theta = reinterpret_cast<float *>(w + L.off_theta);
     float *tau = reinterpret_cast<float *>(w + L.off_tau);
     uint32_t *counts = reinterpret_cast<uint32_t *>(w + L.off_counts);
     uint64_t *keys = reinterpret_cast<uint64_t *>(w + L.off_keys);
     const size_t scan_smem = scan_smem_bytes((int)sizeof(CandT), kp1);
     const size_t sel_smem = (size_t)L.cap * sizeof(uint64_t);
+    for (int qb = 0; qb * kQB < sb; ++qb) {        // S = 256: one launch
+        knn_scan_kernel<D><<<L.g, kScanThreads, scan_smem, st>>>(
+            reinterpret_cast<const CandT *>(mid), e, qm, sb, kp1, theta, tau, counts, keys, L.cap, counts + L.sb,
+            g_knn_stats ? reinterpret_cast<unsigned long long *>(w + L.off_stats) : nullptr, qb);
+        GEM_CHECK_LAUNCH();
+    }
+    stage_mark();                                                   // GEM_STAGE_KNN_SCAN
+    knn_select_kernel<<<sb, kThreads, sel_smem, st>>>(counts, keys, L.cap, kp1, idx_offset, out_idx, out_dist, fx);
+    GEM_CHECK_LAUNCH();
+    stage_mark();                                                   // GEM_STAGE_KNN_SELECT
+    stage_mark();                                                   // GEM_STAGE_KNN_FALLBACK (none needed)
+    return GEM_OK;
+}
+
+bool knn_fast_applicable(int mm, int d, int64_t e, int kp1) {
+    return mm && (d == 2 || d == 3) && e >= 2048 && kp1 <= kMaxFastKp1 && kp1 <= e && e < ((int64_t)1 << 32);
+}
+
+template <int D>
+int knn_fast(const float *mid, int64_t e, int64_t idx_offset, const float *qmid, int64_t s, int kp1,
+             const float *tau_hint, int64_t *out_idx, float *out_dist, void *ws, size_t ws_bytes, cudaStream_t st) {
+    const KnnLayout L = knn_layout(e, s, kp1);
+    if (ws == nullptr || ws_bytes < L.total || ((uintptr_t)ws & 255)) return GEM_E_WORKSPACE;
+    if (((uintptr_t)mid & 15) || ((uintptr_t)qmid & 15)) return GEM_E_BADARG;
+    char *w = reinterpret_cast<char *>(ws);
     const int mld = mid_pitch(D);
+    FusedIntersect none = {};
     for (int64_t q0 = 0; q0 < s; q0 += L.sb) {
         const int sb = (int)((s - q0) < L.sb ? (s - q0) : L.sb);
         const float *qm = qmid + q0 * mld;
-        GEM_CUDA(cudaMemsetAsync(counts, 0, ((size_t)L.sb + 64) * sizeof(uint32_t), st));   // counts + tile counters
-        knn_bound_kernel<D><<<L.g, kThreads, 0, st>>>(reinterpret_cast<const CandT *>(mid), e, qm, sb,
-                                                      L.tiles_per_cta, chunkmin);
-        GEM_CHECK_LAUNCH();
-        stage_mark();                                                   // GEM_STAGE_KNN_BOUND
-        knn_threshold_kernel<D><<<(sb + kWarps - 1) / kWarps, kThreads, 0, st>>>(
-            chunkmin, L.g, kp1, qm, sb, tau_hint ? tau_hint + q0 : nullptr, theta, tau);
-        GEM_CHECK_LAUNCH();
-        stage_mark();                                                   // GEM_STAGE_KNN_THRESHOLD
-        // query coefficients of this batch -> constant bank (uniform operands of the scan's packed FMAs)
-        float2 *qcoef = reinterpret_cast<float2 *>(w + L.off_qcoef);
-        knn_qcoef_kernel<D><<<(kMaxBatchQ / 2 + kThreads - 1) / kThreads, kThreads, 0, st>>>(qm, sb, qcoef);
-        GEM_CHECK_LAUNCH();
-        GEM_CUDA(cudaMemcpyToSymbolAsync(c_qcoef, qcoef, sizeof(float2) * 3 * (kMaxBatchQ / 2), 0, cudaMemcpyDeviceToDevice, st));
-        for (int qb = 0; qb * kQB < sb; ++qb) {        // one launch per block of 256 queries (S = 256: one launch)
-            knn_scan_kernel<D><<<L.g, kScanThreads, scan_smem, st>>>(
-                reinterpret_cast<const CandT *>(mid), e, qm, sb, kp1, theta, tau, counts, keys, L.cap, counts + L.sb,
-                g_knn_stats ? reinterpret_cast<unsigned long long *>(w + L.off_stats) : nullptr, qb);
-            GEM_CHECK_LAUNCH();
-        }
-        stage_mark();                                                   // GEM_STAGE_KNN_SCAN
-        knn_select_kernel<<<sb, kThreads, sel_smem, st>>>(counts, keys, L.cap, kp1, idx_offset,
-                                                          out_idx + q0 * kp1, out_dist + q0 * kp1);
-        GEM_CHECK_LAUNCH();
-        stage_mark();                                                   // GEM_STAGE_KNN_SELECT
-        stage_mark();                                                   // GEM_STAGE_KNN_FALLBACK (none needed)
+        int rc = knn_prepare<D>(L, w, mid, nullptr, nullptr, e, qm, sb, kp1, tau_hint ? tau_hint + q0 : nullptr, st);
+        if (rc) return rc;
+        rc = knn_scan_select<D>(L, w, mid, e, idx_offset, qm, sb, kp1, out_idx + q0 * kp1, out_dist + q0 * kp1, none, st);
+        if (rc) return rc;
     }
     return GEM_OK;
 }
+
+// second stream + fork/join events of gem_layout_step, per device (created by gem_init)
+constexpr int kMaxDevices = 64;
+struct AuxStream { cudaStream_t st = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+AuxStream g_aux[kMaxDevices];
 
 int resolve_mm_mode(int mm_mode, int64_t s, int64_t e) {
     if (mm_mode < 0) return (s > 25 || e > 25) ? 1 : 0;      // torch.cdist default compute_mode
@@ -1578,6 +1654,13 @@ int gem_init(void) {
     GEM_CUDA(cudaFuncSetAttribute(knn_scan_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)scan_smem_bytes(16, kMaxFastKp1)));
     GEM_CUDA(cudaFuncSetAttribute(knn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    if (dev >= 0 && dev < kMaxDevices && g_aux[dev].st == nullptr) {
+        // the one exception to "the library owns nothing": a non-blocking side stream and two events, so
+        // that gem_layout_step can run the KNN preparation concurrently with the spring kernel
+        GEM_CUDA(cudaStreamCreateWithFlags(&g_aux[dev].st, cudaStreamNonBlocking));
+        GEM_CUDA(cudaEventCreateWithFlags(&g_aux[dev].fork, cudaEventDisableTiming));
+        GEM_CUDA(cudaEventCreateWithFlags(&g_aux[dev].join, cudaEventDisableTiming));
+    }
     return GEM_OK;
 }
 
@@ -1834,30 +1917,98 @@ int gem_update_positions(float *pos, const float *f_spring, const float *f_inter
     return GEM_OK;
 }
 
+// spring stage of gem_layout_step on `st`
+static int layout_spring(const gem_plan *p, void *st) {
+    if (p->row_ptr && p->col && p->up_ptr && (p->d == 2 || p->d == 3))
+        return gem_spring_midpoints_csr(p->pos, p->row_ptr, p->col, p->up_ptr, 0, p->n, p->hubs, p->n_hubs, p->d, p->k_attr,
+                                        p->l_min, p->force, p->mid, 0, st);
+    return gem_spring_midpoints(p->pos, p->edges, p->n, p->e, p->d, p->k_attr, p->l_min, p->force, p->mid, st);
+}
+
 int gem_layout_step(const gem_plan *p, void *stream) {
     if (!p || !p->pos || !p->edges || !p->force || !p->mid || !p->qmid || !p->samp || !p->knn_idx || !p->knn_dist ||
         !p->stats_ws)
         return GEM_E_BADARG;
     if (p->kp1 > p->e) return GEM_E_KRANGE;
     int rc;
+    cudaStream_t main_st = (cudaStream_t)stream;
+    const bool have_hint = p->row_ptr && p->col && p->tau_hint && (p->d == 2 || p->d == 3);
+    const int mm = resolve_mm_mode(p->mm_mode, p->s, p->e);
+    const bool fast = knn_fast_applicable(mm, p->d, p->e, p->kp1) && p->s <= kMaxBatchQ;
+    if (fast) {
+        // ---- fast path: [sample -> query midpoints -> line-graph hint -> bound -> threshold -> constant bank]
+        // depends on the positions only, so it runs on the side stream while the spring kernel streams the
+        // graph on the main one; the scan joins both.  The profiling variant runs the same launches in
+        // series on one stream so that the per-stage events mean something.
+        const KnnLayout L = knn_layout(p->e, p->s, p->kp1);
+        if (p->knn_ws == nullptr || p->knn_ws_bytes < L.total || ((uintptr_t)p->knn_ws & 255)) return GEM_E_WORKSPACE;
+        char *w = reinterpret_cast<char *>(p->knn_ws);
+        int dev = 0;
+        GEM_CUDA(cudaGetDevice(&dev));
+        const bool overlap = g_timer == nullptr && dev >= 0 && dev < kMaxDevices && g_aux[dev].st != nullptr;
+        cudaStream_t side = overlap ? g_aux[dev].st : main_st;
+        const int2 *ed = reinterpret_cast<const int2 *>(p->edges);
+        stage_mark();                                                   // start
+        if (overlap) {
+            GEM_CUDA(cudaEventRecord(g_aux[dev].fork, main_st));
+            GEM_CUDA(cudaStreamWaitEvent(side, g_aux[dev].fork, 0));
+        }
+        if (!p->external_sample) {
+            rc = gem_sample_edges(p->seed, p->iter_counter, 1, p->e, p->s, p->samp, side);
+            if (rc) return rc;
+        }
+        stage_mark();                                                   // GEM_STAGE_SAMPLE
+        if (!overlap) {
+            rc = layout_spring(p, main_st);
+            if (rc) return rc;
+        }
+        stage_mark();                                                   // GEM_STAGE_SPRING
+        rc = gem_query_midpoints(p->pos, p->edges, p->samp, p->s, p->d, p->qmid, side);
+        if (rc) return rc;
+        stage_mark();                                                   // GEM_STAGE_QUERY_MID
+        if (have_hint) {
+            rc = gem_knn_linegraph_hint(p->pos, p->row_ptr, p->col, p->edges, p->samp, p->s, p->d, p->kp1, p->tau_hint, side);
+            if (rc) return rc;
+        }
+        const float *hint = have_hint ? p->tau_hint : nullptr;
+        rc = p->d == 2 ? knn_prepare<2>(L, w, nullptr, p->pos, ed, p->e, p->qmid, (int)p->s, p->kp1, hint, side)
+                       : knn_prepare<3>(L, w, nullptr, p->pos, ed, p->e, p->qmid, (int)p->s, p->kp1, hint, side);
+        if (rc) return rc;
+        if (overlap) {
+            GEM_CUDA(cudaEventRecord(g_aux[dev].join, side));
+            rc = layout_spring(p, main_st);
+            if (rc) return rc;
+            GEM_CUDA(cudaStreamWaitEvent(main_st, g_aux[dev].join, 0));
+        }
+        FusedIntersect fx = {};
+        if (p->kp1 > 1) {
+            // total = spring + inter (:796): the repulsion goes straight into the spring accumulator
+            fx.pos = p->pos; fx.edges = ed; fx.samp = p->samp; fx.force = p->force;
+            fx.k_inter = p->k_inter; fx.d = p->d; fx.v_begin = 0; fx.v_end = (int)p->n;
+        }
+        rc = p->d == 2 ? knn_scan_select<2>(L, w, p->mid, p->e, 0, p->qmid, (int)p->s, p->kp1, p->knn_idx, p->knn_dist, fx, main_st)
+                       : knn_scan_select<3>(L, w, p->mid, p->e, 0, p->qmid, (int)p->s, p->kp1, p->knn_idx, p->knn_dist, fx, main_st);
+        if (rc) return rc;
+        stage_mark();                                                   // GEM_STAGE_INTERSECT (fused into the select kernel)
+        rc = gem_update_positions(p->pos, p->force, nullptr, p->n, p->n, p->d, p->stats_ws, 0, stream);
+        stage_mark();                                                   // GEM_STAGE_UPDATE
+        return rc;
+    }
+    // ---- general path (tiny graphs, generic n_components, direct-mode cdist, k+1 > 64, S > 1024): in series
     stage_mark();                                                       // start
     if (!p->external_sample) {
         rc = gem_sample_edges(p->seed, p->iter_counter, 1, p->e, p->s, p->samp, stream);
         if (rc) return rc;
     }
     stage_mark();                                                       // GEM_STAGE_SAMPLE
-    if (p->row_ptr && p->col && p->up_ptr && (p->d == 2 || p->d == 3))
-        rc = gem_spring_midpoints_csr(p->pos, p->row_ptr, p->col, p->up_ptr, 0, p->n, p->hubs, p->n_hubs, p->d, p->k_attr,
-                                      p->l_min, p->force, p->mid, 0, stream);
-    else
-        rc = gem_spring_midpoints(p->pos, p->edges, p->n, p->e, p->d, p->k_attr, p->l_min, p->force, p->mid, stream);
+    rc = layout_spring(p, stream);
     if (rc) return rc;
     stage_mark();                                                       // GEM_STAGE_SPRING
     rc = gem_query_midpoints(p->pos, p->edges, p->samp, p->s, p->d, p->qmid, stream);
     if (rc) return rc;
     stage_mark();                                                       // GEM_STAGE_QUERY_MID
     const float *hint = nullptr;
-    if (p->row_ptr && p->col && p->tau_hint && (p->d == 2 || p->d == 3)) {
+    if (have_hint) {
         rc = gem_knn_linegraph_hint(p->pos, p->row_ptr, p->col, p->edges, p->samp, p->s, p->d, p->kp1, p->tau_hint, stream);
         if (rc) return rc;
         hint = p->tau_hint;
