@@ -1834,6 +1834,38 @@ int gem_knn_midpoints_shard(const float *mid, int64_t e, int64_t e_total, int64_
                   : knn_fast<3>(mid, e, idx_offset, qmid, s, kp1, tau_hint, out_idx, out_dist, ws, ws_bytes, st);
 }
 
+int gem_knn_fast_path(int64_t e, int64_t e_total, int d, int64_t s, int kp1) {
+    const int mm = resolve_mm_mode(-1, s, e_total);
+    return (knn_fast_applicable(mm, d, e, kp1) && s <= kMaxBatchQ && kp1 <= e_total) ? 1 : 0;
+}
+
+int gem_knn_prepare(const float *mid, const float *pos, const int32_t *edges, int64_t e, int d, const float *qmid,
+                    int64_t s, int kp1, const float *tau_hint, void *ws, size_t ws_bytes, void *stream) {
+    if (!qmid || e <= 0 || s <= 0 || kp1 <= 0 || (!mid && (!pos || !edges))) return GEM_E_BADARG;
+    if (!gem_knn_fast_path(e, e, d, s, kp1)) return GEM_E_BADARG;
+    const KnnLayout L = knn_layout(e, s, kp1);
+    if (ws == nullptr || ws_bytes < L.total || ((uintptr_t)ws & 255)) return GEM_E_WORKSPACE;
+    char *w = reinterpret_cast<char *>(ws);
+    const int2 *ed = reinterpret_cast<const int2 *>(edges);
+    cudaStream_t st = (cudaStream_t)stream;
+    return d == 2 ? knn_prepare<2>(L, w, mid, pos, ed, e, qmid, (int)s, kp1, tau_hint, st)
+                  : knn_prepare<3>(L, w, mid, pos, ed, e, qmid, (int)s, kp1, tau_hint, st);
+}
+
+int gem_knn_scan(const float *mid, int64_t e, int64_t idx_offset, int d, const float *qmid, int64_t s, int kp1,
+                 int64_t *out_idx, float *out_dist, void *ws, size_t ws_bytes, void *stream) {
+    if (!mid || !qmid || !out_idx || !out_dist || e <= 0 || s <= 0 || kp1 <= 0) return GEM_E_BADARG;
+    if (!gem_knn_fast_path(e, e, d, s, kp1)) return GEM_E_BADARG;
+    const KnnLayout L = knn_layout(e, s, kp1);
+    if (ws == nullptr || ws_bytes < L.total || ((uintptr_t)ws & 255)) return GEM_E_WORKSPACE;
+    if (((uintptr_t)mid & 15) || ((uintptr_t)qmid & 15)) return GEM_E_BADARG;
+    char *w = reinterpret_cast<char *>(ws);
+    FusedIntersect none = {};
+    cudaStream_t st = (cudaStream_t)stream;
+    return d == 2 ? knn_scan_select<2>(L, w, mid, e, idx_offset, qmid, (int)s, kp1, out_idx, out_dist, none, st)
+                  : knn_scan_select<3>(L, w, mid, e, idx_offset, qmid, (int)s, kp1, out_idx, out_dist, none, st);
+}
+
 int gem_topk_merge(const float *dists, const int64_t *idxs, int parts, int64_t s, int kp1, int64_t *out_idx,
                    float *out_dist, void *stream) {
     return gem_topk_merge_strided(dists, idxs, s * kp1, s * kp1, parts, s, kp1, out_idx, out_dist, stream);

@@ -84,7 +84,10 @@ class ShardedLayoutEngine:
             raise RuntimeError("selected index k out of range")       # torch.topk in the reference (:583)
         if sampled_indices is not None:
             self.samp.copy_(sampled_indices.to(self.samp.device))
-        else:
+        begin = getattr(st, "begin_step", None)
+        if begin is not None:
+            begin()                                                    # CUDA stages: fork the side stream here
+        if sampled_indices is None:
             st.sample(self.iteration, L.n_edges, self.samp)            # same ids on every rank
         self.iteration += 1
         # (a) complete spring forces of the owned vertices + midpoints of the owned edges
@@ -151,9 +154,22 @@ class CudaStages:
         self.col = a["col"] if "col" in a else up(layout.col)
         self.up_ptr = a["up_ptr"] if "up_ptr" in a else up(layout.up_ptr)
         self.hubs = up(layout.hubs[rank])
-        self._iter = torch.zeros((1,), device=self.device, dtype=torch.int64)
+        self._iter = torch.zeros((1,), device=self.device, dtype=torch.int64)   # device-side iteration counter
         self._knn_ws = None
         self._stats_ws = None
+        # The KNN preparation (sample, query midpoints, line-graph hint, bound, thresholds) needs the
+        # positions only: it runs on a side stream while the spring kernel runs on the current one.
+        self._side = torch.cuda.Stream(device=self.device)
+        self._fork = torch.cuda.Event()
+        self._join = torch.cuda.Event()
+
+    def begin_step(self):
+        main = torch.cuda.current_stream(self.device)
+        self._fork.record(main)
+        self._side.wait_event(self._fork)
+
+    def _side_ptr(self):
+        return ctypes.c_void_p(self._side.cuda_stream)
 
     def alloc(self, shape, dtype):
         return torch.zeros(shape, device=self.device, dtype=dtype)
@@ -162,11 +178,13 @@ class CudaStages:
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def sample(self, iteration, n_edges, samp):
-        self._iter.fill_(iteration)
-        _cabi.check(self.lib.gem_sample_edges(self.seed, _ptr(self._iter), 0, n_edges,
-                                              samp.numel(), _ptr(samp), self._s()), "gem_sample_edges")
+        # the device counter advances by itself (bump = 1), so a captured CUDA graph replays correctly;
+        # every rank starts from 0 and therefore draws the same ids
+        _cabi.check(self.lib.gem_sample_edges(self.seed, _ptr(self._iter), 1, n_edges,
+                                              samp.numel(), _ptr(samp), self._side_ptr()), "gem_sample_edges")
 
     def spring(self, pos, vb, ve, force, mid, e_lo):
+        self._pos_ref = pos
         _cabi.check(self.lib.gem_spring_midpoints_csr(
             _ptr(pos), _ptr(self.row_ptr), _ptr(self.col), _ptr(self.up_ptr), vb, ve,
             _ptr(self.hubs) if self.hubs.numel() else None, int(self.hubs.numel()), self.d, self.k_attr,
@@ -174,11 +192,12 @@ class CudaStages:
 
     def query_mid(self, pos, samp, qmid):
         _cabi.check(self.lib.gem_query_midpoints(_ptr(pos), _ptr(self.edges32), _ptr(samp), samp.numel(), self.d,
-                                                 _ptr(qmid), self._s()), "gem_query_midpoints")
+                                                 _ptr(qmid), self._side_ptr()), "gem_query_midpoints")
 
     def hint(self, pos, samp, kp1, tau_hint):
         _cabi.check(self.lib.gem_knn_linegraph_hint(_ptr(pos), _ptr(self.row_ptr), _ptr(self.col), _ptr(self.edges32),
-                                                    _ptr(samp), samp.numel(), self.d, kp1, _ptr(tau_hint), self._s()),
+                                                    _ptr(samp), samp.numel(), self.d, kp1, _ptr(tau_hint),
+                                                    self._side_ptr()),
                     "gem_knn_linegraph_hint")
 
     def knn_local(self, mid, e_loc, e_total, e_lo, qmid, tau_hint, kp1, out_idx, out_dist):
@@ -188,6 +207,21 @@ class CudaStages:
             _cabi.check(self.lib.gem_knn_workspace_bytes(max(e_loc, 1), self.d, S, kp1, ctypes.byref(nbytes)))
             self._knn_ws = torch.zeros((nbytes.value + 256,), device=self.device, dtype=torch.uint8)
             self._knn_ws_bytes = nbytes.value
+        main = torch.cuda.current_stream(self.device)
+        if self.lib.gem_knn_fast_path(e_loc, e_total, self.d, S, kp1):
+            # bound / thresholds from (pos, local edges) on the side stream, scan on the main one after the join
+            e32 = self.edges32[e_lo: e_lo + e_loc]
+            _cabi.check(self.lib.gem_knn_prepare(None, _ptr(self._pos_ref), _ptr(e32), e_loc, self.d, _ptr(qmid), S, kp1,
+                                                 _ptr(tau_hint), _ptr(self._knn_ws), self._knn_ws_bytes,
+                                                 self._side_ptr()), "gem_knn_prepare")
+            self._join.record(self._side)
+            main.wait_event(self._join)
+            _cabi.check(self.lib.gem_knn_scan(_ptr(mid), e_loc, e_lo, self.d, _ptr(qmid), S, kp1, _ptr(out_idx),
+                                              _ptr(out_dist), _ptr(self._knn_ws), self._knn_ws_bytes, self._s()),
+                        "gem_knn_scan")
+            return
+        self._join.record(self._side)
+        main.wait_event(self._join)
         mm = 1 if (S > 25 or e_total > 25) else 0                     # torch.cdist's rule on the WHOLE problem
         _cabi.check(self.lib.gem_knn_midpoints_shard(_ptr(mid), e_loc, e_total, e_lo, self.d, _ptr(qmid), S, kp1, mm,
                                                      _ptr(tau_hint), _ptr(out_idx), _ptr(out_dist), _ptr(self._knn_ws),
@@ -255,6 +289,8 @@ class ShardedGraphEmbedder(GraphEmbedderPyTorch):
         dist.broadcast(self._pos, src=dist.get_global_rank(self._group, 0) if self._group is not None else 0,
                        group=self._group)
         self._engine.pos = self._pos
+        self._sgraph = None
+        self._sgraph_pos = None
 
     def _world_and_rank(self):
         return dist.get_world_size(self._group), dist.get_rank(self._group)
@@ -266,14 +302,38 @@ class ShardedGraphEmbedder(GraphEmbedderPyTorch):
         self.last_sampled_indices = self._engine.samp
         self.last_knn_indices = self._engine.knn_idx[:, 1:]
 
-    def run_layout(self, num_iterations=100):
-        for _ in range(int(num_iterations)):
-            self.update_positions()
-        return self.positions
+    def _replay(self, num_iterations: int):
+        """Capture one whole sharded iteration -- kernels on both streams AND the three NCCL
+        collectives -- in a CUDA graph and replay it: no Python / launch overhead per iteration."""
+        if self._sgraph is None or self._sgraph_pos != self._pos.data_ptr():
+            self._engine.pos = self._pos
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):                    # warm-up outside capture (NCCL communicators, lazy buffers)
+                self._engine.step()
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._engine.step()
+            self._sgraph, self._sgraph_pos = graph, self._pos.data_ptr()
+            num_iterations -= 1                              # the warm-up step was a real iteration
+        for _ in range(num_iterations):
+            self._sgraph.replay()
+        self.last_sampled_indices = self._engine.samp
+        self.last_knn_indices = self._engine.knn_idx[:, 1:]
 
     def run_layout_device(self, num_iterations=100):
-        for _ in range(int(num_iterations)):
-            self.update_positions()
+        with torch.cuda.device(self.device):
+            if self.use_cuda_graph and num_iterations > 1:
+                self._replay(int(num_iterations))
+            else:
+                for _ in range(int(num_iterations)):
+                    self.update_positions()
+
+    def run_layout(self, num_iterations=100):
+        self.run_layout_device(num_iterations)
+        return self.positions
 
     def profile_step(self):
         raise NotImplementedError("per-stage profiling is a single-GPU tool")

@@ -43,7 +43,8 @@ extern "C" {
 #define GEM_E_NODEVICE (-4)    /* no sm_100 device / kernel image not loadable */
 
 int gem_abi_version(void);
-/* Once per process and device, before the first launch (sets kernel attributes; not capturable). */
+/* Once per process and device, before the first launch (sets kernel attributes, creates the side
+ * stream of gem_layout_step; not capturable). */
 int gem_init(void);
 const char *gem_error_string(int code);
 /* row pitch (floats) of positions/forces and of midpoints for n_components = d */
@@ -103,6 +104,23 @@ int gem_knn_midpoints(const float *mid, int64_t e, int64_t idx_offset, int d, co
 int gem_knn_midpoints_shard(const float *mid, int64_t e, int64_t e_total, int64_t idx_offset, int d,
                             const float *qmid, int64_t s, int kp1, int mm_mode, const float *tau_hint,
                             int64_t *out_idx, float *out_dist, void *ws, size_t ws_bytes, void *stream);
+/* The two phases of the fast path of gem_knn_midpoints[_shard] as separate calls, for callers that
+ * overlap them with other work (gem_layout_step does so internally; the multi-GPU host does it with
+ * its own side stream):
+ *   gem_knn_prepare  bound pass -> thresholds -> query coefficients into the constant bank.  With
+ *                    mid == NULL the sampled candidates are recomputed from (pos, edges) -- `edges`
+ *                    points at the first of the e local edges -- so the call depends on the positions
+ *                    only and can run while the spring kernel is still producing `mid`;
+ *   gem_knn_scan     all-pairs scan + select -> (s, kp1) lists (short rows padded with +inf / -1).
+ * Valid only when gem_knn_fast_path(e, e_total, d, s, kp1) returns 1 (matmul-mode cdist, d in {2,3},
+ * e >= 2048, k+1 <= 64 and <= e, s <= 1024); otherwise use gem_knn_midpoints_shard.  The coefficient
+ * table lives in one __constant__ array per device: at most one prepare/scan pair may be in flight
+ * per device at a time. */
+int gem_knn_fast_path(int64_t e, int64_t e_total, int d, int64_t s, int kp1);
+int gem_knn_prepare(const float *mid, const float *pos, const int32_t *edges, int64_t e, int d, const float *qmid,
+                    int64_t s, int kp1, const float *tau_hint, void *ws, size_t ws_bytes, void *stream);
+int gem_knn_scan(const float *mid, int64_t e, int64_t idx_offset, int d, const float *qmid, int64_t s, int kp1,
+                 int64_t *out_idx, float *out_dist, void *ws, size_t ws_bytes, void *stream);
 /* Optional search radius per query for gem_knn_midpoints (tau_hint, may be NULL): only
  * neighbours with distance <= tau_hint[q] are required.  gem_knn_linegraph_hint computes a valid
  * one: the (k+1)-th smallest exact distance among the edges incident to the endpoints of the query
@@ -158,8 +176,12 @@ int gem_update_workspace_bytes(int64_t n, int d, size_t *bytes);
 int gem_update_positions(float *pos, const float *f_spring, const float *f_inter, int64_t n,
                          int64_t n_total, int d, void *stats_ws, int phase, void *stream);
 
-/* One whole iteration (update_positions, :776-806) on one GPU, launched back to back on
- * `stream`: sample -> spring+midpoints -> query midpoints -> KNN -> intersection -> update. */
+/* One whole iteration (update_positions, :776-806) on one GPU:
+ *   side stream : sample -> query midpoints -> line-graph hint -> KNN bound/threshold   (needs pos only)
+ *   `stream`    : spring forces + midpoints  ==join==>  KNN scan -> select + intersection forces -> update
+ * The side stream and its two events belong to the library (created by gem_init, one set per
+ * device); the fork/join is expressed with events, so the call stays CUDA-graph capturable.
+ * Problems outside the KNN fast path run all stages in series on `stream`. */
 typedef struct gem_plan {
     int64_t n, e, s;          /* vertices, edges, sample size (already min(sample_size, e)) */
     int32_t d, kp1;           /* n_components, n_neighbors + 1 */

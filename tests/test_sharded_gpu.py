@@ -107,6 +107,16 @@ def _nccl_worker(rank, world, port, out):
             got = emb.positions
             worst = max(worst, rel_inf(got, o["new_pos"].numpy()))
             ref = torch.from_numpy(got)
+        # CUDA-graph replay of the whole sharded step (kernels on both streams + the NCCL collectives)
+        # against eager launches of a second embedder with the same seed: same sample stream, same layout
+        emb2 = ShardedGraphEmbedder(adj, n_components=d, device=dev, n_neighbors=k, sample_size=256, verbose=False,
+                                    seed=4, initial_positions=pos0, use_cuda_graph=False)
+        for it in range(3 + 4):
+            emb2.update_positions()
+        emb.run_layout_device(4)
+        torch.cuda.synchronize()
+        ok &= bool(torch.equal(emb.last_sampled_indices, emb2.last_sampled_indices))
+        worst = max(worst, rel_inf(emb.positions, emb2.positions) * 1e-2)      # atomics reorder sums: 1e-3 allowed
         mine = emb._pos.clone()
         dist.broadcast(mine, src=0)
         same = bool(torch.equal(mine, emb._pos))
