@@ -31,6 +31,8 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 METRIC = "layout iters/sec & edge-updates/s, 1M-vertex BA graph, 1/2/4/8 B200 vs host CPU"
+# DRAM traffic of one knn_scan_kernel launch from the committed ncu capture (profiles/), bytes
+SCAN_DRAM_BYTES_NCU = {"c3": 64042752 + 419584}
 
 WORKLOADS = {
     # BASELINE.json configs[2] -- the headline
@@ -214,11 +216,16 @@ def run_b200(args, w):
         torch.cuda.synchronize(dev)
 
     K, W = args.steps, max(args.warmup, 3)
-    for _ in range(W):
-        emb.update_positions()
+    # warm-up: W iterations through the production path (run_layout's CUDA-graph replay; the graph of one
+    # iteration -- both streams and, for N > 1, the NCCL collectives -- is captured here, untimed)
+    emb.run_layout_device(W)
     barrier()
 
-    # ---- device-resident timing: per-step events, L2 flushed (untimed) before every step
+    def one_step():
+        emb.run_layout_device(1)               # one replay of the captured iteration
+
+    # ---- device-resident timing: EXACTLY K steps, each bracketed by its own CUDA events on the launching
+    # stream and preceded by an (untimed) L2 flush; barrier + synchronize on both sides of the region
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
@@ -229,7 +236,7 @@ def run_b200(args, w):
     for i in range(K):
         flush_buf.fill_(i & 0xFF)
         starts[i].record()
-        emb.update_positions()
+        one_step()
         ends[i].record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
@@ -237,17 +244,11 @@ def run_b200(args, w):
     total_ms = float(np.sum(step_ms))
     clk = clocks.stop() if rank == 0 else None
 
-    # ---- back-to-back (warm L2, no flush; CUDA-graph replay when single GPU) for context
-    if world == 1 and hasattr(emb, "run_layout_device"):
-        emb.run_layout_device(2)               # graph capture happens here, untimed
+    # ---- back-to-back (no flush between iterations), for context
     barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    if world == 1:
-        emb.run_layout_device(K) if hasattr(emb, "run_layout_device") else [emb.update_positions() for _ in range(K)]
-    else:
-        for _ in range(K):
-            emb.update_positions()
+    emb.run_layout_device(K)
     b.record()
     barrier()
     b2b_ms = a.elapsed_time(b) / K
@@ -262,7 +263,7 @@ def run_b200(args, w):
     ea.record()
     for _ in range(Ke):
         emb.load_positions(host_in)            # H2D from pinned memory (positions setter semantics)
-        emb.update_positions()
+        one_step()
         emb.read_positions(host_out)           # D2H of the step's result + stream sync
         host_in, host_out = host_out, host_in
     eb.record()
@@ -275,14 +276,16 @@ def run_b200(args, w):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, b2b_ms, e2e_ms = [float(x) for x in t.tolist()]
 
-    # ---- per-kernel roofline (rank 0, single-GPU plan), measured live with CUDA events
+    # ---- per-kernel roofline (rank 0, single GPU), measured live with CUDA events: gem_profile_step runs the
+    # same launches in series on one stream with an event after every stage (in the timed steps above the
+    # KNN preparation overlaps the spring kernel on a side stream, so stage times do not add up to the step)
     stage = None
     roof = None
     extra_roof = {}
     peaks, peak_src = measured_peaks()
     if rank == 0 and world == 1:
         runs = []
-        for i in range(5):
+        for i in range(7):
             flush_buf.fill_(i)
             runs.append(emb.profile_step())
         stage = {k: float(np.median([r[k] for r in runs])) for k in runs[0]}
@@ -291,20 +294,31 @@ def run_b200(args, w):
         N = n
         flops = 2.0 * (d + 2) * S * E                        # 2(d+2) flop per query-candidate pair
         scan_s = stage["knn_scan"] * 1e-3
+        executed = 2.0 * d * S * E                           # what the filter executes: d FMA per pair
         roof = {"kernel": "knn_scan_kernel", "bound": "fp32", "achieved": flops / scan_s / 1e12,
-                "peak": fp32_peak / 1e12, "unit": "TFLOP/s", "frac": flops / scan_s / fp32_peak, "traffic": None,
-                "peak_source": "gem_fp32_peak_probe measured in this run (MEASURED_PEAKS.json has no FP32 figure)",
+                "peak": fp32_peak / 1e12, "unit": "TFLOP/s", "frac": flops / scan_s / fp32_peak,
+                "traffic": SCAN_DRAM_BYTES_NCU.get(args.workload),
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
+                                  "(profiles/r01_knn_scan_v3_ncu.md); algorithmic bytes per launch = 16*E = "
+                                  f"{16.0 * E:.0f}",
+                "peak_source": "gem_fp32_peak_probe: dependent-chain-free FFMA loop measured in this run "
+                               "(MEASURED_PEAKS.json has no FP32 figure); nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.5",
                 "algorithmic_flops_per_launch": flops, "ms": stage["knn_scan"],
-                "note": "2(d+2)*S*E flop per launch; the kernel executes d FFMA + 1 FSETP per pair (conservative "
-                        "filter) and re-checks the rare passes in the exact 5-op cdist chain"}
+                "executed_fma_tflops": executed / scan_s / 1e12,
+                "note": "algorithmic = SURVEY 8(d): 2(d+2)*S*E flop (the 5-term cdist chain per pair). The kernel "
+                        "executes d FMA + a min/compare per pair as a conservative filter and re-checks the rare "
+                        "passes with the exact chain, so `achieved` counts work it does not have to do: "
+                        "executed_fma_tflops is the hardware rate"}
         hbm = peaks["hbm_gbs"]
         ka_bytes = 8.0 * E + 4.0 * d * N + 4.0 * d * N + 4.0 * d * E
         kd_bytes = 20.0 * d * N
         extra_roof = {
-            "spring_mid_kernel": {"bound": "hbm", "achieved": ka_bytes / (stage["spring_mid"] * 1e-3) / 1e9,
+            "spring_csr_kernel": {"bound": "hbm", "achieved": ka_bytes / (stage["spring_mid"] * 1e-3) / 1e9,
                                   "peak": hbm, "unit": "GB/s",
                                   "frac": ka_bytes / (stage["spring_mid"] * 1e-3) / 1e9 / hbm,
-                                  "algorithmic_bytes": ka_bytes, "ms": stage["spring_mid"]},
+                                  "algorithmic_bytes": ka_bytes, "ms": stage["spring_mid"],
+                                  "note": "bound in practice by the L1 wavefront rate of 2E scattered 16-byte position "
+                                          "gathers (DESIGN.md section 4a), not by DRAM"},
             "update_pass1+2": {"bound": "hbm", "achieved": kd_bytes / (stage["update"] * 1e-3) / 1e9, "peak": hbm,
                                "unit": "GB/s", "frac": kd_bytes / (stage["update"] * 1e-3) / 1e9 / hbm,
                                "algorithmic_bytes": kd_bytes, "ms": stage["update"]},
@@ -316,6 +330,8 @@ def run_b200(args, w):
         extra_roof["iteration"] = {"t_roof_ms": t_roof * 1e3, "achieved_ms": total_ms / K,
                                    "frac": t_roof * 1e3 / (total_ms / K)}
 
+    if world > 1:
+        emb.close()            # captured graphs hold NCCL kernels: release them before the communicator
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -331,15 +347,19 @@ def run_b200(args, w):
 
     ms_per_step = total_ms / K
     value = E / (ms_per_step * 1e-3)
-    launches_per_step = 11 if world == 1 else 12        # kernels of libgraphem_b200.so per iteration (torch/NCCL kernels not counted)
+    # kernels of libgraphem_b200.so per iteration (memset / memcpy nodes and torch / NCCL kernels not counted):
+    # sample, query_mid, linegraph_hint, knn_bound, knn_threshold, spring_csr, knn_scan, knn_select(+intersection),
+    # update_pass1, update_pass2  [+ topk_merge, intersection on N > 1]
+    launches_per_step = 10 if world == 1 else 12
     line = {
         "metric": METRIC, "value": value, "unit": "edge-updates/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "iters_per_s": 1e3 / ms_per_step,
         "config": {"workload": w["desc"], "N": n, "E": E, "sample_size": min(w["S"], E), "n_neighbors": w["k"],
-                   "parallelism": "single GPU" if world == 1 else f"edge-sharded x{world} (NCCL)",
+                   "parallelism": "single GPU" if world == 1 else f"vertex-range sharded x{world} (NCCL)",
                    "l2": "flushed before every timed step (512 MiB write, untimed)",
+                   "step": "one replay of the CUDA graph of one iteration (run_layout's production path)",
                    "sampler": "device (gem_sample_edges)", "init": "randn*0.1 default_rng(0)"},
         "ms_per_step_back_to_back": b2b_ms,
         "wall_s_timed_region": t_wall,
@@ -347,6 +367,7 @@ def run_b200(args, w):
                 "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
                 "api": "load_positions(pinned) -> update_positions() -> read_positions(pinned)"},
         "gpu_launches": launches_per_step * K,
+        "timed_steps_ms": {"min": float(np.min(step_ms)), "median": float(np.median(step_ms)), "max": float(np.max(step_ms))},
         "clocks": clk,
         "roofline": roof,
         "roofline_other": extra_roof,

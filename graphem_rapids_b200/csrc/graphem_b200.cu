@@ -785,8 +785,8 @@ __device__ __forceinline__ ScanShared scan_shared(unsigned char *smem_raw, int k
 // Slots hold the sentinel ~0 until written, so the first locked visitor can wait for appends in flight.
 constexpr uint64_t kEmptyKey = ~0ull;
 template <int D>
-__device__ __noinline__ void scan_insert(unsigned char *smem_raw, int kp1, int ql, float x, float y, float z, float n,
-                                         uint32_t idx, unsigned long long *stats) {
+__device__ __forceinline__ void scan_insert(unsigned char *smem_raw, int kp1, int ql, float x, float y, float z, float n,
+                                            uint32_t idx, unsigned long long *stats) {
     const ScanShared S = scan_shared<sizeof(typename MidT<D>::T)>(smem_raw, kp1);
     const float4 qv = S.lqpar[ql];
     QueryPar p;

@@ -423,9 +423,12 @@ class GraphEmbedderPyTorch:
         return out
 
     def run_layout_device(self, num_iterations=100):
-        """run_layout without the final device->host copy (positions stay in HBM)."""
+        """run_layout without the final device->host copy (positions stay in HBM).  Replays the captured
+        CUDA graph of one iteration (capturing it on first use with more than one iteration)."""
         with torch.cuda.device(self.device):
-            if self.use_cuda_graph and self.sampler == "device" and num_iterations > 1:
+            if self.n_edges == 0 or self.n_neighbors + 1 > self.n_edges:
+                raise RuntimeError("selected index k out of range")
+            if self.use_cuda_graph and self.sampler == "device" and (num_iterations > 1 or self._graph is not None):
                 self._run_graph(int(num_iterations))
             else:
                 for _ in range(int(num_iterations)):

@@ -63,12 +63,14 @@ class GraphLayout:
         return out
 
 
-def balanced_vertex_ranges(deg: np.ndarray, up: np.ndarray, world: int, w_entry: float = 1.0, w_edge: float = 10.0,
-                           w_vertex: float = 2.0):
+def balanced_vertex_ranges(deg: np.ndarray, up: np.ndarray, world: int, w_entry: float = 1.0, w_edge: float = 4.5,
+                           w_vertex: float = 3.0):
     """Contiguous vertex ranges with (approximately) equal cost
         cost(v) = w_entry*deg(v) + w_edge*up(v) + w_vertex
-    (spring work ~ CSR entries, KNN work ~ owned candidate edges, update work ~ vertices; the KNN
-    scan dominates, so the owned edge count is weighted highest).  Every rank gets >= 1 vertex."""
+    (spring work ~ CSR entries, KNN work ~ owned candidate edges, update + position all-gather ~
+    vertices).  The weights are the measured single-B200 costs on the 1M-vertex BA graph in units of
+    the per-entry spring cost: scan 45 us / M edges, spring 10 us / M entries, update 27 us / M rows.
+    Every rank gets >= 1 vertex."""
     n = len(deg)
     if world > n:
         raise ValueError(f"cannot shard {n} vertices across {world} ranks")

@@ -323,9 +323,17 @@ class ShardedGraphEmbedder(GraphEmbedderPyTorch):
         self.last_sampled_indices = self._engine.samp
         self.last_knn_indices = self._engine.knn_idx[:, 1:]
 
+    def close(self):
+        """Release the captured CUDA graph.  Call before torch.distributed.destroy_process_group(): tearing
+        down an NCCL communicator whose collectives are still referenced by a live graph hangs."""
+        self._sgraph = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize(self.device)
+
     def run_layout_device(self, num_iterations=100):
         with torch.cuda.device(self.device):
-            if self.use_cuda_graph and num_iterations > 1:
+            if self.use_cuda_graph and (num_iterations > 1 or self._sgraph is not None):
                 self._replay(int(num_iterations))
             else:
                 for _ in range(int(num_iterations)):

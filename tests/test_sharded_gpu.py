@@ -124,6 +124,7 @@ def _nccl_worker(rank, world, port, out):
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if rank == 0:
             out.put((int(flag.item()), worst))
+        emb.close()                                  # release the captured graph before the communicator goes away
     finally:
         dist.destroy_process_group()
 
@@ -138,7 +139,10 @@ def test_two_real_ranks_nccl():
     for p in procs:
         p.start()
     for p in procs:
-        p.join(timeout=600)
-        assert p.exitcode == 0
+        p.join(timeout=240)
+    hung = [p for p in procs if p.exitcode is None]
+    for p in hung:
+        p.kill()
+    assert not hung and all(p.exitcode == 0 for p in procs)
     flag, worst = out.get()
     assert flag == 1, worst
