@@ -74,6 +74,10 @@ template <> struct Vec<2> {
     __device__ void red_add(float *base, int64_t row) const {
         atomicAdd(reinterpret_cast<float2 *>(base) + row, make_float2(x, y));   // red.global.add.v2.f32
     }
+    __device__ Vec fetch_add(float *base, int64_t row) const {                  // atom.global.add.v2.f32, old value
+        const float2 o = atomicAdd(reinterpret_cast<float2 *>(base) + row, make_float2(x, y));
+        return {o.x, o.y};
+    }
 };
 template <> struct Vec<3> {
     float x, y, z;
@@ -89,6 +93,10 @@ template <> struct Vec<3> {
     __device__ void store(float *base, int64_t row) const { reinterpret_cast<float4 *>(base)[row] = make_float4(x, y, z, 0.f); }
     __device__ void red_add(float *base, int64_t row) const {
         atomicAdd(reinterpret_cast<float4 *>(base) + row, make_float4(x, y, z, 0.f));   // red.global.add.v4.f32
+    }
+    __device__ Vec fetch_add(float *base, int64_t row) const {                          // atom.global.add.v4.f32, old value
+        const float4 o = atomicAdd(reinterpret_cast<float4 *>(base) + row, make_float4(x, y, z, 0.f));
+        return {o.x, o.y, o.z};
     }
 };
 
@@ -189,7 +197,24 @@ __device__ __forceinline__ Vec<3> shfl_xor_vec(Vec<3> a, int m) {
     return {__shfl_xor_sync(0xffffffffu, a.x, m), __shfl_xor_sync(0xffffffffu, a.y, m), __shfl_xor_sync(0xffffffffu, a.z, m)};
 }
 
-template <int D>
+// stats workspace of the update (shared by update_pass1 and the fused form below):
+//   double sums[2*ld] | pad to 256 | uint32 ticket | pad to 256 | double partials[blocks][2*ld]
+__host__ __device__ inline size_t ws_ticket_off(int ld) { return ((size_t)2 * ld * sizeof(double) + 255) / 256 * 256; }
+constexpr int kUpdBlocksMax = 1184;    // 148 * 8
+
+// FUSE = true: `force` receives the UNNORMALISED NEW POSITION pos + F_spring instead of the force (the
+// add of update pass 1, embedder_pytorch.py:799, without materialising F).  Its fp64 column sums are
+// taken by a read-only pass that gem_layout_step runs on the side stream next to the KNN scan; the
+// intersection forces are added to those rows afterwards with an exact correction of the sums
+// (intersect_pair<D, true>), so only the normalisation pass is left on the critical path behind the
+// KNN.  (Accumulating the sums inside this kernel cost 8 registers = one resident CTA per SM, +16 us.)
+template <int D, bool FUSE>
+__device__ __forceinline__ void spring_emit(const Vec<D> &pv, const Vec<D> &acc, float *__restrict__ out, int64_t row) {
+    if (!FUSE) acc.store(out, row);
+    else (pv + acc).store(out, row);                                 // :799 (total force = spring part here)
+}
+
+template <int D, bool FUSE>
 __global__ void __launch_bounds__(kThreads) spring_csr_kernel(const float *__restrict__ pos,
                                                               const int64_t *__restrict__ row_ptr,
                                                               const int32_t *__restrict__ col,
@@ -221,7 +246,7 @@ __global__ void __launch_bounds__(kThreads) spring_csr_kernel(const float *__res
             float t[3] = {0.f, 0.f, 0.f};
             for (int w = 0; w < kWarps; ++w)
                 for (int j = 0; j < 3; ++j) t[j] += red[w][j];
-            vec_from3<D>(t).store(force, v - v_begin);
+            spring_emit<D, FUSE>(pv, vec_from3<D>(t), force, v - v_begin);
         }
         return;
     }
@@ -268,7 +293,7 @@ __global__ void __launch_bounds__(kThreads) spring_csr_kernel(const float *__res
         }
         acc = acc + shfl_xor_vec(acc, 1);
         acc = acc + shfl_xor_vec(acc, 2);
-        if (valid && !hub && g == 0) acc.store(force, v - v_begin);  // isolated vertices get their zero here
+        if (valid && !hub && g == 0) spring_emit<D, FUSE>(pv, acc, force, v - v_begin);   // isolated vertices too
     }
 }
 
@@ -1108,10 +1133,13 @@ __device__ __forceinline__ float orient2d(float ax, float ay, float bx, float by
 }
 
 // one candidate pair (edge i = sampled query edge, edge j = one of its neighbours)
-template <int D>
+// CORR = true: `force` holds unnormalised new positions whose fp64 column sums are already known
+// (fused spring+update form); the repulsion is added with an atomic that returns the old row, and
+// dsum/dsq receive the exact change of (sum, sum of squares) caused by the value actually stored.
+template <int D, bool CORR = false>
 __device__ __forceinline__ void intersect_pair(const float *__restrict__ pos, const int2 *__restrict__ edges, int64_t i,
                                                int64_t j, float k_inter, int v_begin, int v_end,
-                                               float *__restrict__ force) {
+                                               float *__restrict__ force, double *dsum = nullptr, double *dsq = nullptr) {
     if (!(i < j)) return;                                        // :672  (also drops the -1 padding of a short list)
     const int2 ei = edges[i], ej = edges[j];                     // :681-682
     if (ei.x == ej.x || ei.x == ej.y || ei.y == ej.x || ei.y == ej.y) return;   // :685-692
@@ -1131,7 +1159,22 @@ __device__ __forceinline__ void intersect_pair(const float *__restrict__ pos, co
         const float dist = norm2(diff) + 1e-6f;
         const Vec<D> rep = (k_inter * diff) / (dist * dist);
         // vertex-sliced accumulation (multi-GPU: a rank adds only into the vertex range it owns)
-        if (vid[u] >= v_begin && vid[u] < v_end) rep.red_add(force, vid[u] - v_begin);
+        if (vid[u] >= v_begin && vid[u] < v_end) {
+            if (!CORR) {
+                rep.red_add(force, vid[u] - v_begin);
+            } else {
+                const Vec<D> old = rep.fetch_add(force, vid[u] - v_begin);
+                float o[3], r[3];
+                vec_to3(old, o);
+                vec_to3(rep, r);
+#pragma unroll
+                for (int c = 0; c < D; ++c) {
+                    const float nv = __fadd_rn(o[c], r[c]);               // the value the atomic stored
+                    dsum[c] += (double)nv - (double)o[c];
+                    dsq[c] += (double)nv * (double)nv - (double)o[c] * (double)o[c];
+                }
+            }
+        }
     }
 }
 
@@ -1200,6 +1243,7 @@ __global__ void __launch_bounds__(kThreads) intersection_generic_kernel(const fl
 struct FusedIntersect {
     const float *pos; const int2 *edges; const int64_t *samp; float *force;
     float k_inter; int d, v_begin, v_end;
+    double *sums;          // != nullptr: `force` holds new positions; correct these column sums (2*ld doubles)
 };
 __global__ void __launch_bounds__(kThreads) knn_select_kernel(const uint32_t *__restrict__ counts,
                                                               const uint64_t *__restrict__ keys, int cap, int kp1,
@@ -1257,10 +1301,36 @@ __global__ void __launch_bounds__(kThreads) knn_select_kernel(const uint32_t *__
     }
     if (fx.force != nullptr) {
         __syncthreads();                                     // the list of this query is complete (same CTA wrote it)
+        double ds[3] = {0.0, 0.0, 0.0}, dq[3] = {0.0, 0.0, 0.0};
         for (int c = t; c < kp1 - 1; c += kThreads) {
             const int64_t i = fx.samp[q], j = out_idx[(int64_t)q * kp1 + 1 + c];
-            if (fx.d == 2) intersect_pair<2>(fx.pos, fx.edges, i, j, fx.k_inter, fx.v_begin, fx.v_end, fx.force);
-            else intersect_pair<3>(fx.pos, fx.edges, i, j, fx.k_inter, fx.v_begin, fx.v_end, fx.force);
+            if (fx.sums == nullptr) {
+                if (fx.d == 2) intersect_pair<2>(fx.pos, fx.edges, i, j, fx.k_inter, fx.v_begin, fx.v_end, fx.force);
+                else intersect_pair<3>(fx.pos, fx.edges, i, j, fx.k_inter, fx.v_begin, fx.v_end, fx.force);
+            } else {
+                if (fx.d == 2) intersect_pair<2, true>(fx.pos, fx.edges, i, j, fx.k_inter, fx.v_begin, fx.v_end, fx.force, ds, dq);
+                else intersect_pair<3, true>(fx.pos, fx.edges, i, j, fx.k_inter, fx.v_begin, fx.v_end, fx.force, ds, dq);
+            }
+        }
+        if (fx.sums != nullptr) {                            // CTA-level reduction, then 2*d fp64 atomics per query
+            const int ld = fx.d == 3 ? 4 : fx.d;
+            const bool active = t < ((kp1 - 1 + 31) / 32) * 32;           // whole warps that hold contributions
+            if (active) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        ds[c] += __shfl_down_sync(0xffffffffu, ds[c], o);
+                        dq[c] += __shfl_down_sync(0xffffffffu, dq[c], o);
+                    }
+                }
+                if ((t & 31) == 0) {
+                    for (int c = 0; c < fx.d; ++c) {
+                        if (ds[c] != 0.0) atomicAdd(fx.sums + c, ds[c]);
+                        if (dq[c] != 0.0) atomicAdd(fx.sums + ld + c, dq[c]);
+                    }
+                }
+            }
         }
     }
 }
@@ -1271,8 +1341,6 @@ __global__ void __launch_bounds__(kThreads) knn_select_kernel(const uint32_t *__
 // ==========================================================================================
 // stats_ws layout: double sums[2*ld] | pad to 256 | uint32 ticket | pad to 256 | double partials[blocks][2*ld]
 // (zero-initialised once by the caller; the kernels leave the ticket at zero)
-__host__ __device__ inline size_t ws_ticket_off(int ld) { return ((size_t)2 * ld * sizeof(double) + 255) / 256 * 256; }
-constexpr int kUpdBlocksMax = 1184;    // 148 * 8
 constexpr int kGenericMaxLd = 1024;
 
 template <int LD>
@@ -1287,8 +1355,16 @@ __global__ void __launch_bounds__(kThreads) update_pass1_kernel(float *__restric
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += stride) {
         VT p = reinterpret_cast<VT *>(pos)[v];
-        VT a = reinterpret_cast<const VT *>(fs)[v];
         float *pp = reinterpret_cast<float *>(&p);
+        if (fs == nullptr) {                                 // statistics only: pos already holds pos + F (fused form)
+#pragma unroll
+            for (int j = 0; j < LD; ++j) {
+                sum[j] += (double)pp[j];
+                sq[j] += (double)pp[j] * (double)pp[j];
+            }
+            continue;
+        }
+        VT a = reinterpret_cast<const VT *>(fs)[v];
         float *pa = reinterpret_cast<float *>(&a);
         if (fi != nullptr) {
             VT b = reinterpret_cast<const VT *>(fi)[v];
@@ -1360,8 +1436,8 @@ __device__ __forceinline__ void col_stats(const double *sums, int ld, int j, int
 }
 
 template <int LD>
-__global__ void __launch_bounds__(kThreads) update_pass2_kernel(float *__restrict__ pos, int64_t n, int64_t n_total,
-                                                                int d, const void *__restrict__ ws) {
+__global__ void __launch_bounds__(kThreads) update_pass2_kernel(float *pos, const float *src, int64_t n,
+                                                                int64_t n_total, int d, const void *__restrict__ ws) {
     using VT = typename std::conditional<LD == 2, float2, float4>::type;
     const double *sums = reinterpret_cast<const double *>(ws);
     // the fp64 divide / sqrt of the column statistics once per CTA, not once per thread
@@ -1377,7 +1453,7 @@ __global__ void __launch_bounds__(kThreads) update_pass2_kernel(float *__restric
     for (int j = 0; j < LD; ++j) { mean[j] = s_mean[j]; sd[j] = s_sd[j]; }
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += stride) {
-        VT p = reinterpret_cast<VT *>(pos)[v];
+        VT p = reinterpret_cast<const VT *>(src)[v];             // src == pos (in place) or the fused form's buffer
         float *pp = reinterpret_cast<float *>(&p);
 #pragma unroll
         for (int j = 0; j < LD; ++j) pp[j] = __fdiv_rn(pp[j] - mean[j], sd[j]);   // :802, :804
@@ -1577,7 +1653,8 @@ int knn_prepare(const KnnLayout &L, char *w, const float *mid, const float *pos,
 // Phase B: scan (one launch per block of 256 queries) -> select (+ optional fused intersection forces)
 template <int D>
 int knn_scan_select(const KnnLayout &L, char *w, const float *mid, int64_t e, int64_t idx_offset, const float *qm, int sb,
-                    int kp1, int64_t *out_idx, float *out_dist, const FusedIntersect &fx, cudaStream_t st) {
+                    int kp1, int64_t *out_idx, float *out_dist, const FusedIntersect &fx, cudaStream_t st,
+                    cudaEvent_t before_select = nullptr) {
     using CandT = typename MidT<D>::T;
     float *theta = reinterpret_cast<float *>(w + L.off_theta);
     float *tau = reinterpret_cast<float *>(w + L.off_tau);
@@ -1592,6 +1669,7 @@ int knn_scan_select(const KnnLayout &L, char *w, const float *mid, int64_t e, in
         GEM_CHECK_LAUNCH();
     }
     stage_mark();                                                   // GEM_STAGE_KNN_SCAN
+    if (before_select) GEM_CUDA(cudaStreamWaitEvent(st, before_select, 0));
     knn_select_kernel<<<sb, kThreads, sel_smem, st>>>(counts, keys, L.cap, kp1, idx_offset, out_idx, out_dist, fx);
     GEM_CHECK_LAUNCH();
     stage_mark();                                                   // GEM_STAGE_KNN_SELECT
@@ -1625,7 +1703,7 @@ int knn_fast(const float *mid, int64_t e, int64_t idx_offset, const float *qmid,
 
 // second stream + fork/join events of gem_layout_step, per device (created by gem_init)
 constexpr int kMaxDevices = 64;
-struct AuxStream { cudaStream_t st = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+struct AuxStream { cudaStream_t st = nullptr; cudaEvent_t fork = nullptr, join = nullptr, spring = nullptr, stats = nullptr; };
 AuxStream g_aux[kMaxDevices];
 
 int resolve_mm_mode(int mm_mode, int64_t s, int64_t e) {
@@ -1660,6 +1738,8 @@ int gem_init(void) {
         GEM_CUDA(cudaStreamCreateWithFlags(&g_aux[dev].st, cudaStreamNonBlocking));
         GEM_CUDA(cudaEventCreateWithFlags(&g_aux[dev].fork, cudaEventDisableTiming));
         GEM_CUDA(cudaEventCreateWithFlags(&g_aux[dev].join, cudaEventDisableTiming));
+        GEM_CUDA(cudaEventCreateWithFlags(&g_aux[dev].spring, cudaEventDisableTiming));
+        GEM_CUDA(cudaEventCreateWithFlags(&g_aux[dev].stats, cudaEventDisableTiming));
     }
     return GEM_OK;
 }
@@ -1695,32 +1775,45 @@ int gem_spring_midpoints(const float *pos, const int32_t *edges, int64_t n, int6
 
 int gem_hub_degree(void) { return kHubDeg; }
 
-int gem_spring_midpoints_csr(const float *pos, const int64_t *row_ptr, const int32_t *col, const int64_t *up_ptr,
+static int spring_csr_launch(const float *pos, const int64_t *row_ptr, const int32_t *col, const int64_t *up_ptr,
                              int64_t v_begin, int64_t v_end, const int32_t *hubs, int64_t n_hubs, int d, float k_attr,
-                             float l_min, float *force, float *mid, int64_t mid_base, void *stream) {
+                             float l_min, float *force, float *mid, int64_t mid_base, bool fuse, void *stream) {
     if (!pos || !row_ptr || !col || !up_ptr || !force || v_begin < 0 || v_end < v_begin || n_hubs < 0 ||
         (n_hubs > 0 && !hubs) || (d != 2 && d != 3))
         return GEM_E_BADARG;
     if (v_end == v_begin) return GEM_OK;
     cudaStream_t st = (cudaStream_t)stream;
     // resident CTAs per SM from the occupancy calculator: a grid-stride kernel sized past that runs a ragged second wave
-    static int occ[2] = {0, 0};
-    int &oc = occ[d - 2];
+    static int occ[2][2] = {{0, 0}, {0, 0}};
+    const int f = fuse ? 1 : 0;
+    int &oc = occ[d - 2][f];
     if (oc == 0) {
-        if (d == 2) GEM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oc, spring_csr_kernel<2>, kThreads, 0));
-        else GEM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oc, spring_csr_kernel<3>, kThreads, 0));
+        if (d == 2 && !f) GEM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oc, spring_csr_kernel<2, false>, kThreads, 0));
+        if (d == 3 && !f) GEM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oc, spring_csr_kernel<3, false>, kThreads, 0));
+        if (d == 2 && f) GEM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oc, spring_csr_kernel<2, true>, kThreads, 0));
+        if (d == 3 && f) GEM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oc, spring_csr_kernel<3, true>, kThreads, 0));
         if (oc < 1) oc = 1;
     }
     const int main_blocks = grid_for((v_end - v_begin) * kGrp, oc);
     const int grid = main_blocks + (int)n_hubs;
-    if (d == 2)
-        spring_csr_kernel<2><<<grid, kThreads, 0, st>>>(pos, row_ptr, col, up_ptr, v_begin, v_end, hubs, (int)n_hubs, -k_attr,
-                                                        l_min, force, reinterpret_cast<float2 *>(mid), mid_base);
-    else
-        spring_csr_kernel<3><<<grid, kThreads, 0, st>>>(pos, row_ptr, col, up_ptr, v_begin, v_end, hubs, (int)n_hubs, -k_attr,
-                                                        l_min, force, reinterpret_cast<float4 *>(mid), mid_base);
+#define GEM_SPRING_LAUNCH(DD, FF)                                                                                  \
+    spring_csr_kernel<DD, FF><<<grid, kThreads, 0, st>>>(pos, row_ptr, col, up_ptr, v_begin, v_end, hubs, (int)n_hubs, \
+                                                         -k_attr, l_min, force,                                       \
+                                                         reinterpret_cast<typename MidT<DD>::T *>(mid), mid_base)
+    if (d == 2 && !f) GEM_SPRING_LAUNCH(2, false);
+    if (d == 3 && !f) GEM_SPRING_LAUNCH(3, false);
+    if (d == 2 && f) GEM_SPRING_LAUNCH(2, true);
+    if (d == 3 && f) GEM_SPRING_LAUNCH(3, true);
+#undef GEM_SPRING_LAUNCH
     GEM_CHECK_LAUNCH();
     return GEM_OK;
+}
+
+int gem_spring_midpoints_csr(const float *pos, const int64_t *row_ptr, const int32_t *col, const int64_t *up_ptr,
+                             int64_t v_begin, int64_t v_end, const int32_t *hubs, int64_t n_hubs, int d, float k_attr,
+                             float l_min, float *force, float *mid, int64_t mid_base, void *stream) {
+    return spring_csr_launch(pos, row_ptr, col, up_ptr, v_begin, v_end, hubs, n_hubs, d, k_attr, l_min, force, mid, mid_base,
+                             false, stream);
 }
 
 int gem_sample_edges(uint64_t seed, int64_t *iter_counter, int bump_counter, int64_t e, int64_t s, int64_t *samp,
@@ -1917,21 +2010,28 @@ int gem_update_workspace_bytes(int64_t n, int d, size_t *bytes) {
 
 int gem_update_positions(float *pos, const float *f_spring, const float *f_inter, int64_t n, int64_t n_total, int d,
                          void *stats_ws, int phase, void *stream) {
-    if (!pos || !stats_ws || n <= 0 || d <= 0 || phase < 0 || phase > 2) return GEM_E_BADARG;
-    if (phase != 2 && !f_spring) return GEM_E_BADARG;
+    if (!pos || !stats_ws || n <= 0 || d <= 0 || phase < 0 || phase > 3) return GEM_E_BADARG;
+    if (phase != 2 && phase != 3 && !f_spring) return GEM_E_BADARG;
+    if (phase == 3 && (d != 2 && d != 3)) return GEM_E_BADARG;
     if ((uintptr_t)stats_ws & 255) return GEM_E_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     if (n_total <= 0) n_total = n;
     const int grid = grid_for(n, 8);
     if (d == 2 || d == 3) {
+        if (phase == 3) {                           // column sums of `pos` only (f_spring == NULL: nothing added or written)
+            if (d == 2) update_pass1_kernel<2><<<grid, kThreads, 0, st>>>(pos, nullptr, nullptr, n, stats_ws);
+            else update_pass1_kernel<4><<<grid, kThreads, 0, st>>>(pos, nullptr, nullptr, n, stats_ws);
+            GEM_CHECK_LAUNCH();
+            return GEM_OK;
+        }
         if (phase != 2) {
             if (d == 2) update_pass1_kernel<2><<<grid, kThreads, 0, st>>>(pos, f_spring, f_inter, n, stats_ws);
             else update_pass1_kernel<4><<<grid, kThreads, 0, st>>>(pos, f_spring, f_inter, n, stats_ws);
             GEM_CHECK_LAUNCH();
         }
         if (phase != 1) {
-            if (d == 2) update_pass2_kernel<2><<<grid, kThreads, 0, st>>>(pos, n, n_total, d, stats_ws);
-            else update_pass2_kernel<4><<<grid, kThreads, 0, st>>>(pos, n, n_total, d, stats_ws);
+            if (d == 2) update_pass2_kernel<2><<<grid, kThreads, 0, st>>>(pos, pos, n, n_total, d, stats_ws);
+            else update_pass2_kernel<4><<<grid, kThreads, 0, st>>>(pos, pos, n, n_total, d, stats_ws);
             GEM_CHECK_LAUNCH();
         }
     } else {
@@ -1949,11 +2049,14 @@ int gem_update_positions(float *pos, const float *f_spring, const float *f_inter
     return GEM_OK;
 }
 
-// spring stage of gem_layout_step on `st`
-static int layout_spring(const gem_plan *p, void *st) {
+// spring stage of gem_layout_step on `st`; fuse = true: the CSR kernel writes pos + F_spring and the column sums
+static bool layout_can_fuse(const gem_plan *p) {
+    return p->row_ptr && p->col && p->up_ptr && (p->d == 2 || p->d == 3);
+}
+static int layout_spring(const gem_plan *p, void *st, bool fuse) {
     if (p->row_ptr && p->col && p->up_ptr && (p->d == 2 || p->d == 3))
-        return gem_spring_midpoints_csr(p->pos, p->row_ptr, p->col, p->up_ptr, 0, p->n, p->hubs, p->n_hubs, p->d, p->k_attr,
-                                        p->l_min, p->force, p->mid, 0, st);
+        return spring_csr_launch(p->pos, p->row_ptr, p->col, p->up_ptr, 0, p->n, p->hubs, p->n_hubs, p->d, p->k_attr,
+                                 p->l_min, p->force, p->mid, 0, fuse, st);
     return gem_spring_midpoints(p->pos, p->edges, p->n, p->e, p->d, p->k_attr, p->l_min, p->force, p->mid, st);
 }
 
@@ -1990,9 +2093,17 @@ int gem_layout_step(const gem_plan *p, void *stream) {
             if (rc) return rc;
         }
         stage_mark();                                                   // GEM_STAGE_SAMPLE
+        // with the CSR arrays present the spring kernel also does update pass 1 (p->force := pos + F_spring, fp64
+        // column sums); the intersection forces are then added with a correction of the sums, and only the
+        // normalisation pass is left behind the KNN
+        const bool fuse = layout_can_fuse(p) && (((uintptr_t)p->stats_ws & 255) == 0);
         if (!overlap) {
-            rc = layout_spring(p, main_st);
+            rc = layout_spring(p, main_st, fuse);
             if (rc) return rc;
+            if (fuse) {                                                 // in series: counted in the spring stage
+                rc = gem_update_positions(p->force, nullptr, nullptr, p->n, p->n, p->d, p->stats_ws, 3, main_st);
+                if (rc) return rc;
+            }
         }
         stage_mark();                                                   // GEM_STAGE_SPRING
         rc = gem_query_midpoints(p->pos, p->edges, p->samp, p->s, p->d, p->qmid, side);
@@ -2008,21 +2119,40 @@ int gem_layout_step(const gem_plan *p, void *stream) {
         if (rc) return rc;
         if (overlap) {
             GEM_CUDA(cudaEventRecord(g_aux[dev].join, side));
-            rc = layout_spring(p, main_st);
+            rc = layout_spring(p, main_st, fuse);
             if (rc) return rc;
             GEM_CUDA(cudaStreamWaitEvent(main_st, g_aux[dev].join, 0));
+        }
+        if (fuse && overlap) {
+            // column sums of the new positions: a read-only 4*ld*N-byte pass on the side stream, next to the scan
+            // (which is FP32-bound and leaves the memory system idle); joined before the select kernel corrects them
+            GEM_CUDA(cudaEventRecord(g_aux[dev].spring, main_st));
+            GEM_CUDA(cudaStreamWaitEvent(side, g_aux[dev].spring, 0));
+            rc = gem_update_positions(p->force, nullptr, nullptr, p->n, p->n, p->d, p->stats_ws, 3, side);
+            if (rc) return rc;
+            GEM_CUDA(cudaEventRecord(g_aux[dev].stats, side));
         }
         FusedIntersect fx = {};
         if (p->kp1 > 1) {
             // total = spring + inter (:796): the repulsion goes straight into the spring accumulator
             fx.pos = p->pos; fx.edges = ed; fx.samp = p->samp; fx.force = p->force;
             fx.k_inter = p->k_inter; fx.d = p->d; fx.v_begin = 0; fx.v_end = (int)p->n;
+            fx.sums = fuse ? reinterpret_cast<double *>(p->stats_ws) : nullptr;
         }
-        rc = p->d == 2 ? knn_scan_select<2>(L, w, p->mid, p->e, 0, p->qmid, (int)p->s, p->kp1, p->knn_idx, p->knn_dist, fx, main_st)
-                       : knn_scan_select<3>(L, w, p->mid, p->e, 0, p->qmid, (int)p->s, p->kp1, p->knn_idx, p->knn_dist, fx, main_st);
+        cudaEvent_t before_select = (fuse && overlap) ? g_aux[dev].stats : nullptr;
+        rc = p->d == 2 ? knn_scan_select<2>(L, w, p->mid, p->e, 0, p->qmid, (int)p->s, p->kp1, p->knn_idx, p->knn_dist, fx, main_st, before_select)
+                       : knn_scan_select<3>(L, w, p->mid, p->e, 0, p->qmid, (int)p->s, p->kp1, p->knn_idx, p->knn_dist, fx, main_st, before_select);
         if (rc) return rc;
         stage_mark();                                                   // GEM_STAGE_INTERSECT (fused into the select kernel)
-        rc = gem_update_positions(p->pos, p->force, nullptr, p->n, p->n, p->d, p->stats_ws, 0, stream);
+        if (fuse) {                                                     // normalise p->force (new positions) into p->pos
+            const int grid = grid_for(p->n, 8);
+            if (p->d == 2) update_pass2_kernel<2><<<grid, kThreads, 0, main_st>>>(p->pos, p->force, p->n, p->n, p->d, p->stats_ws);
+            else update_pass2_kernel<4><<<grid, kThreads, 0, main_st>>>(p->pos, p->force, p->n, p->n, p->d, p->stats_ws);
+            GEM_CHECK_LAUNCH();
+            rc = GEM_OK;
+        } else {
+            rc = gem_update_positions(p->pos, p->force, nullptr, p->n, p->n, p->d, p->stats_ws, 0, stream);
+        }
         stage_mark();                                                   // GEM_STAGE_UPDATE
         return rc;
     }
@@ -2033,7 +2163,7 @@ int gem_layout_step(const gem_plan *p, void *stream) {
         if (rc) return rc;
     }
     stage_mark();                                                       // GEM_STAGE_SAMPLE
-    rc = layout_spring(p, stream);
+    rc = layout_spring(p, stream, false);
     if (rc) return rc;
     stage_mark();                                                       // GEM_STAGE_SPRING
     rc = gem_query_midpoints(p->pos, p->edges, p->samp, p->s, p->d, p->qmid, stream);

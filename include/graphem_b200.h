@@ -171,7 +171,9 @@ int gem_intersection_forces_range(const float *pos, const int32_t *edges, int64_
  * zero-initialised once by the caller.
  * phase 0 = both passes; phase 1 = pass 1 only (writes unnormalised positions and the
  * column sums {sum, sum of squares} as 2*ld doubles at the start of stats_ws, for a
- * cross-rank all-reduce); phase 2 = pass 2 only (reads the reduced sums; n_total = global n). */
+ * cross-rank all-reduce); phase 2 = pass 2 only (reads the reduced sums; n_total = global n);
+ * phase 3 = column sums of `pos` only (nothing added or written; f_spring ignored) -- used by
+ * gem_layout_step, whose spring kernel already wrote pos + F_spring. */
 int gem_update_workspace_bytes(int64_t n, int d, size_t *bytes);
 int gem_update_positions(float *pos, const float *f_spring, const float *f_inter, int64_t n,
                          int64_t n_total, int d, void *stats_ws, int phase, void *stream);
