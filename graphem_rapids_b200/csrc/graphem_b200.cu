@@ -61,7 +61,6 @@ inline void stage_mark() { if (g_timer) g_timer->mark(); }
 template <int D> struct Vec;
 template <> struct Vec<2> {
     float x, y;
-    static constexpr int LD = 2;
     __device__ static Vec load(const float *base, int64_t row) {
         float2 t = __ldg(reinterpret_cast<const float2 *>(base) + row);
         return {t.x, t.y};
@@ -81,7 +80,6 @@ template <> struct Vec<2> {
 };
 template <> struct Vec<3> {
     float x, y, z;
-    static constexpr int LD = 4;
     __device__ static Vec load(const float *base, int64_t row) {
         float4 t = __ldg(reinterpret_cast<const float4 *>(base) + row);
         return {t.x, t.y, t.z};
@@ -341,33 +339,40 @@ __host__ __device__ inline uint32_t lowbias32(uint32_t z) {
     z ^= z >> 16; z *= 0x7feb352du; z ^= z >> 15; z *= 0x846ca68bu; z ^= z >> 16;
     return z;
 }
+struct FeistelKey { uint32_t rk[6]; int h; uint64_t mask; };
+__device__ __forceinline__ FeistelKey feistel_key(uint64_t seed, int64_t iter, int64_t e) {
+    FeistelKey k;
+    int b = 2;
+    while (((uint64_t)1 << b) < (uint64_t)e) b += 2;                               // even bit count
+    k.h = b / 2;
+    k.mask = ((uint64_t)1 << k.h) - 1;
+    uint64_t st = seed ^ ((uint64_t)iter * 0xD1342543DE82EF95ull + 0x632BE59BD9B4E019ull);
+    for (int r = 0; r < 6; ++r) k.rk[r] = (uint32_t)splitmix64(st);
+    return k;
+}
+// image of i under the keyed bijection of [0, e)
+__device__ __forceinline__ int64_t feistel_draw(const FeistelKey &k, int64_t e, int64_t i) {
+    uint64_t y = (uint64_t)i;
+    do {
+        uint64_t L = y >> k.h, R = y & k.mask;
+        for (int r = 0; r < 6; ++r) {
+            const uint64_t f = lowbias32((uint32_t)R ^ k.rk[r]);
+            const uint64_t t = R;
+            R = L ^ (f & k.mask);
+            L = t;
+        }
+        y = (L << k.h) | R;
+    } while (y >= (uint64_t)e);
+    return (int64_t)y;
+}
 __global__ void sample_edges_kernel(uint64_t seed, int64_t *iter_counter, int bump, int64_t e, int64_t s,
                                     int64_t *samp) {
     const int64_t iter = iter_counter ? *iter_counter : 0;
     if (s >= e) {
         for (int64_t i = threadIdx.x; i < e; i += blockDim.x) samp[i] = i;          // :412 arange(E)
     } else {
-        int b = 2;
-        while (((uint64_t)1 << b) < (uint64_t)e) b += 2;                           // even bit count
-        const int h = b / 2;
-        const uint64_t mask = ((uint64_t)1 << h) - 1;
-        uint64_t st = seed ^ ((uint64_t)iter * 0xD1342543DE82EF95ull + 0x632BE59BD9B4E019ull);
-        uint32_t rk[6];
-        for (int r = 0; r < 6; ++r) rk[r] = (uint32_t)splitmix64(st);
-        for (int64_t i = threadIdx.x; i < s; i += blockDim.x) {
-            uint64_t y = (uint64_t)i;
-            do {
-                uint64_t L = y >> h, R = y & mask;
-                for (int r = 0; r < 6; ++r) {
-                    const uint64_t f = lowbias32((uint32_t)R ^ rk[r]);
-                    const uint64_t t = R;
-                    R = L ^ (f & mask);
-                    L = t;
-                }
-                y = (L << h) | R;
-            } while (y >= (uint64_t)e);
-            samp[i] = (int64_t)y;
-        }
+        const FeistelKey k = feistel_key(seed, iter, e);
+        for (int64_t i = threadIdx.x; i < s; i += blockDim.x) samp[i] = feistel_draw(k, e, i);
     }
     if (bump && iter_counter) {
         __syncthreads();
@@ -583,7 +588,6 @@ __global__ void __launch_bounds__(kThreads) knn_bound_kernel(const typename MidT
     __shared__ __align__(16) CandT tile[kBoundTile];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = gridDim.x;
-    const int64_t ntiles = (e + kBoundTile - 1) / kBoundTile;
     for (int qb = 0; qb * kQB < s; ++qb) {
         QueryPar qp[kQ];
         float best[kQ];
@@ -593,14 +597,16 @@ __global__ void __launch_bounds__(kThreads) knn_bound_kernel(const typename MidT
             qp[i] = load_query<D>(qmid, q < s ? q : 0);
             best[i] = kInf;
         }
+        // stratified sample: CTA b looks at (up to) tiles_per_cta*kBoundTile consecutive candidates from the
+        // start of ITS share [b*e/g, (b+1)*e/g) of the index range (NOT the scan's interleaving: its first
+        // blocks are the lowest-index edges, i.e. the hub edges of a preferential-attachment graph -- a
+        // hopelessly biased sample).  Every CTA has candidates as soon as e >= g, so small problems get a
+        // finite bound too (with tile-granular shares, e < g*kBoundTile left most chunk minima at +inf).
+        const int64_t lo = ((int64_t)blockIdx.x * e) / g, hi = ((int64_t)(blockIdx.x + 1) * e) / g;
         for (int j = 0; j < tiles_per_cta; ++j) {
-            // stratified sample: CTA b looks at tiles_per_cta consecutive tiles starting at b/g of the
-            // index range (NOT the scan's interleaving: its first g tiles are the lowest-index edges,
-            // i.e. the hub edges of a preferential-attachment graph -- a hopelessly biased sample)
-            const int64_t t = ((int64_t)blockIdx.x * ntiles) / g + j;
-            if (t >= ntiles || (blockIdx.x + 1 < g && t >= ((int64_t)(blockIdx.x + 1) * ntiles) / g)) break;
-            const int64_t base = t * kBoundTile;
-            const int cnt = (int)min((int64_t)kBoundTile, e - base);
+            const int64_t base = lo + (int64_t)j * kBoundTile;
+            if (base >= hi) break;
+            const int cnt = (int)min((int64_t)kBoundTile, hi - base);
             __syncthreads();
             if (mid != nullptr) {
                 for (int c = threadIdx.x; c < cnt; c += kThreads) tile[c] = __ldg(mid + base + c);
@@ -644,13 +650,25 @@ __global__ void __launch_bounds__(kThreads) knn_linegraph_hint_kernel(const floa
                                                                       const int64_t *__restrict__ row_ptr,
                                                                       const int32_t *__restrict__ col,
                                                                       const int2 *__restrict__ edges,
-                                                                      const int64_t *__restrict__ samp, int s, int kp1,
-                                                                      float *__restrict__ hint) {
+                                                                      int64_t *samp, int s, int kp1,
+                                                                      float *__restrict__ hint, int draw, uint64_t seed,
+                                                                      const int64_t *__restrict__ iter_counter,
+                                                                      int64_t e, typename MidT<D>::T *__restrict__ qmid) {
+    // draw != 0: this kernel also draws the sample (gem_sample_edges) and, qmid != nullptr, writes the query
+    // midpoints (gem_query_midpoints): the three per-query preparation launches of the iteration in one
     const int lane = threadIdx.x & 31;
     const int q = blockIdx.x * kWarps + (threadIdx.x >> 5);
     if (q >= s) return;
-    const int2 ed = edges[samp[q]];
+    int64_t id;
+    if (draw) {
+        id = (s >= e) ? (int64_t)q : feistel_draw(feistel_key(seed, iter_counter ? *iter_counter : 0, e), e, q);
+        if (lane == 0) samp[q] = id;
+    } else {
+        id = samp[q];
+    }
+    const int2 ed = edges[id];
     const Vec<D> mq = half_sum(Vec<D>::load(pos, ed.x), Vec<D>::load(pos, ed.y));
+    if (qmid != nullptr && lane == 0) qmid[q] = make_mid(mq);
     QueryPar qp;
     qp.a0 = -2.f * mq.x; qp.a1 = -2.f * mq.y;
     if (D == 3) { const Vec<3> &m3 = reinterpret_cast<const Vec<3> &>(mq); qp.a2 = -2.f * m3.z; } else qp.a2 = 0.f;
@@ -704,7 +722,11 @@ __global__ void __launch_bounds__(kThreads) knn_threshold_kernel(const float *__
                                                                  const float *__restrict__ qmid, int s,
                                                                  const float *__restrict__ hint,
                                                                  float *__restrict__ theta, float *__restrict__ tau,
-                                                                 float *__restrict__ qcoef /* [3][kMaxBatchQ/2][2] */) {
+                                                                 float *__restrict__ qcoef /* [3][kMaxBatchQ/2][2] */,
+                                                                 int64_t *bump_counter) {
+    // (the fused query-preparation kernel reads the iteration counter in every CTA, so the increment
+    //  happens here, one launch later in the same stream)
+    if (bump_counter != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *bump_counter += 1;
     const int lane = threadIdx.x & 31;
     const int q = blockIdx.x * kWarps + (threadIdx.x >> 5);
     if (q >= s) return;
@@ -876,20 +898,6 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 // device-to-device cudaMemcpyToSymbolAsync per batch (knn_fast), so one KNN per device may be in
 // flight at a time (the host class runs on one stream, like the reference).
 __constant__ float2 c_qcoef[3][kMaxBatchQ / 2];
-
-__device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity) {
-    uint32_t done;
-    for (;;) {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-        if (done) break;
-        __nanosleep(256);                 // the producer must not steal issue slots from its SM sub-partition
-    }
-}
 
 // Rare path, out of line, entered by the WHOLE warp when any lane has a hit.  A set bit c of a
 // lane's `hitmask` says: some (query of the pairs [c*kPairChunk, (c+1)*kPairChunk), candidate of that
@@ -1629,7 +1637,8 @@ KnnLayout knn_layout(int64_t e, int64_t s, int kp1) {
 // mid == nullptr, in which case nothing here depends on the spring kernel's output.
 template <int D>
 int knn_prepare(const KnnLayout &L, char *w, const float *mid, const float *pos, const int2 *edges, int64_t e,
-                const float *qm, int sb, int kp1, const float *tau_hint, cudaStream_t st) {
+                const float *qm, int sb, int kp1, const float *tau_hint, cudaStream_t st,
+                int64_t *bump_counter = nullptr) {
     using CandT = typename MidT<D>::T;
     float *chunkmin = reinterpret_cast<float *>(w + L.off_chunkmin);
     float *theta = reinterpret_cast<float *>(w + L.off_theta);
@@ -1642,7 +1651,7 @@ int knn_prepare(const KnnLayout &L, char *w, const float *mid, const float *pos,
     GEM_CHECK_LAUNCH();
     stage_mark();                                                   // GEM_STAGE_KNN_BOUND
     knn_threshold_kernel<D><<<(sb + kWarps - 1) / kWarps, kThreads, 0, st>>>(chunkmin, L.g, kp1, qm, sb, tau_hint, theta,
-                                                                             tau, qcoef);
+                                                                             tau, qcoef, bump_counter);
     GEM_CHECK_LAUNCH();
     // query coefficients of this batch -> constant bank (uniform operands of the scan's packed FMAs)
     GEM_CUDA(cudaMemcpyToSymbolAsync(c_qcoef, qcoef, sizeof(float2) * 3 * (kMaxBatchQ / 2), 0, cudaMemcpyDeviceToDevice, st));
@@ -1878,8 +1887,9 @@ int gem_knn_linegraph_hint(const float *pos, const int64_t *row_ptr, const int32
     cudaStream_t st = (cudaStream_t)stream;
     const int2 *ed = reinterpret_cast<const int2 *>(edges);
     const int grid = (int)((s + kWarps - 1) / kWarps);
-    if (d == 2) knn_linegraph_hint_kernel<2><<<grid, kThreads, 0, st>>>(pos, row_ptr, col, ed, samp, (int)s, kp1, tau_hint);
-    else knn_linegraph_hint_kernel<3><<<grid, kThreads, 0, st>>>(pos, row_ptr, col, ed, samp, (int)s, kp1, tau_hint);
+    int64_t *sm = const_cast<int64_t *>(samp);            // draw == 0: only read
+    if (d == 2) knn_linegraph_hint_kernel<2><<<grid, kThreads, 0, st>>>(pos, row_ptr, col, ed, sm, (int)s, kp1, tau_hint, 0, 0, nullptr, 0, nullptr);
+    else knn_linegraph_hint_kernel<3><<<grid, kThreads, 0, st>>>(pos, row_ptr, col, ed, sm, (int)s, kp1, tau_hint, 0, 0, nullptr, 0, nullptr);
     GEM_CHECK_LAUNCH();
     return GEM_OK;
 }
@@ -2088,7 +2098,11 @@ int gem_layout_step(const gem_plan *p, void *stream) {
             GEM_CUDA(cudaEventRecord(g_aux[dev].fork, main_st));
             GEM_CUDA(cudaStreamWaitEvent(side, g_aux[dev].fork, 0));
         }
-        if (!p->external_sample) {
+        // sample + query midpoints + line-graph hint in ONE launch when the CSR is there (the counter is then
+        // bumped by the threshold kernel); separate launches otherwise
+        const bool fused_prep = have_hint && g_timer == nullptr;
+        int64_t *bump_later = nullptr;
+        if (!fused_prep && !p->external_sample) {
             rc = gem_sample_edges(p->seed, p->iter_counter, 1, p->e, p->s, p->samp, side);
             if (rc) return rc;
         }
@@ -2106,16 +2120,31 @@ int gem_layout_step(const gem_plan *p, void *stream) {
             }
         }
         stage_mark();                                                   // GEM_STAGE_SPRING
-        rc = gem_query_midpoints(p->pos, p->edges, p->samp, p->s, p->d, p->qmid, side);
-        if (rc) return rc;
+        if (fused_prep) {
+            const int grid = (int)((p->s + kWarps - 1) / kWarps);
+            const int draw = p->external_sample ? 0 : 1;
+            if (draw) bump_later = p->iter_counter;
+            if (p->d == 2)
+                knn_linegraph_hint_kernel<2><<<grid, kThreads, 0, side>>>(p->pos, p->row_ptr, p->col, ed, p->samp, (int)p->s, p->kp1,
+                                                                       p->tau_hint, draw, p->seed, p->iter_counter, p->e,
+                                                                       reinterpret_cast<float2 *>(p->qmid));
+            else
+                knn_linegraph_hint_kernel<3><<<grid, kThreads, 0, side>>>(p->pos, p->row_ptr, p->col, ed, p->samp, (int)p->s, p->kp1,
+                                                                       p->tau_hint, draw, p->seed, p->iter_counter, p->e,
+                                                                       reinterpret_cast<float4 *>(p->qmid));
+            GEM_CHECK_LAUNCH();
+        } else {
+            rc = gem_query_midpoints(p->pos, p->edges, p->samp, p->s, p->d, p->qmid, side);
+            if (rc) return rc;
+        }
         stage_mark();                                                   // GEM_STAGE_QUERY_MID
-        if (have_hint) {
+        if (have_hint && !fused_prep) {
             rc = gem_knn_linegraph_hint(p->pos, p->row_ptr, p->col, p->edges, p->samp, p->s, p->d, p->kp1, p->tau_hint, side);
             if (rc) return rc;
         }
         const float *hint = have_hint ? p->tau_hint : nullptr;
-        rc = p->d == 2 ? knn_prepare<2>(L, w, nullptr, p->pos, ed, p->e, p->qmid, (int)p->s, p->kp1, hint, side)
-                       : knn_prepare<3>(L, w, nullptr, p->pos, ed, p->e, p->qmid, (int)p->s, p->kp1, hint, side);
+        rc = p->d == 2 ? knn_prepare<2>(L, w, nullptr, p->pos, ed, p->e, p->qmid, (int)p->s, p->kp1, hint, side, bump_later)
+                       : knn_prepare<3>(L, w, nullptr, p->pos, ed, p->e, p->qmid, (int)p->s, p->kp1, hint, side, bump_later);
         if (rc) return rc;
         if (overlap) {
             GEM_CUDA(cudaEventRecord(g_aux[dev].join, side));
