@@ -1141,6 +1141,11 @@ __device__ __forceinline__ float orient2d(float ax, float ay, float bx, float by
 }
 
 // one candidate pair (edge i = sampled query edge, edge j = one of its neighbours)
+template <int D, bool CORR>
+__device__ __forceinline__ void intersect_pair_core(const float *__restrict__ pos, const int2 *__restrict__ edges, int64_t i,
+                                                    int64_t j, int2 ei, Vec<D> p1, Vec<D> p2, float k_inter, int v_begin,
+                                                    int v_end, float *__restrict__ force, double *dsum, double *dsq);
+
 // CORR = true: `force` holds unnormalised new positions whose fp64 column sums are already known
 // (fused spring+update form); the repulsion is added with an atomic that returns the old row, and
 // dsum/dsq receive the exact change of (sum, sum of squares) caused by the value actually stored.
@@ -1149,10 +1154,21 @@ __device__ __forceinline__ void intersect_pair(const float *__restrict__ pos, co
                                                int64_t j, float k_inter, int v_begin, int v_end,
                                                float *__restrict__ force, double *dsum = nullptr, double *dsq = nullptr) {
     if (!(i < j)) return;                                        // :672  (also drops the -1 padding of a short list)
-    const int2 ei = edges[i], ej = edges[j];                     // :681-682
+    const int2 ei = edges[i];                                    // :681
+    intersect_pair_core<D, CORR>(pos, edges, i, j, ei, Vec<D>::load(pos, ei.x), Vec<D>::load(pos, ei.y), k_inter, v_begin,
+                                 v_end, force, dsum, dsq);
+}
+
+// the same with the query edge's endpoints and positions already in registers (the fused select kernel
+// fetches them while the neighbour list is still being ranked)
+template <int D, bool CORR>
+__device__ __forceinline__ void intersect_pair_core(const float *__restrict__ pos, const int2 *__restrict__ edges, int64_t i,
+                                                    int64_t j, int2 ei, Vec<D> p1, Vec<D> p2, float k_inter, int v_begin,
+                                                    int v_end, float *__restrict__ force, double *dsum, double *dsq) {
+    if (!(i < j)) return;                                        // :672
+    const int2 ej = edges[j];                                    // :682
     if (ei.x == ej.x || ei.x == ej.y || ei.y == ej.x || ei.y == ej.y) return;   // :685-692
-    const Vec<D> p1 = Vec<D>::load(pos, ei.x), p2 = Vec<D>::load(pos, ei.y);    // :702-705
-    const Vec<D> q1 = Vec<D>::load(pos, ej.x), q2 = Vec<D>::load(pos, ej.y);
+    const Vec<D> q1 = Vec<D>::load(pos, ej.x), q2 = Vec<D>::load(pos, ej.y);    // :702-705
     const float o1 = orient2d(p1.x, p1.y, p2.x, p2.y, q1.x, q1.y);              // :766-769
     const float o2 = orient2d(p1.x, p1.y, p2.x, p2.y, q2.x, q2.y);
     const float o3 = orient2d(q1.x, q1.y, q2.x, q2.y, p1.x, p1.y);
@@ -1262,9 +1278,30 @@ __global__ void __launch_bounds__(kThreads) knn_select_kernel(const uint32_t *__
     __shared__ uint64_t sub[kThreads];
     __shared__ uint64_t s_thr;
     __shared__ int s_nsurv;
+    __shared__ int64_t s_nb[kMaxFastKp1];                          // the selected neighbour ids, for the fused tail
     const int q = blockIdx.x, t = threadIdx.x;
+    // the kernel is a chain of dependent global round trips, so everything that can be fetched up front is:
+    // the first kThreads keys (speculatively, before the count is known) and, for the fused tail, the query
+    // edge with its endpoint positions
+    const uint64_t spec = keys[(int64_t)q * cap + t];              // cap >= 1024 > kThreads
+    int64_t qi = 0;
+    int2 qe = make_int2(0, 0);
+    float4 qa = make_float4(0.f, 0.f, 0.f, 0.f), qb4 = qa;
+    if (fx.force != nullptr && t < kp1 - 1) {
+        qi = fx.samp[q];
+        qe = fx.edges[qi];
+        if (fx.d == 3) {
+            qa = __ldg(reinterpret_cast<const float4 *>(fx.pos) + qe.x);
+            qb4 = __ldg(reinterpret_cast<const float4 *>(fx.pos) + qe.y);
+        } else {
+            const float2 a2 = __ldg(reinterpret_cast<const float2 *>(fx.pos) + qe.x);
+            const float2 b2 = __ldg(reinterpret_cast<const float2 *>(fx.pos) + qe.y);
+            qa = make_float4(a2.x, a2.y, 0.f, 0.f); qb4 = make_float4(b2.x, b2.y, 0.f, 0.f);
+        }
+    }
     int n = (int)min(counts[q], (uint32_t)cap);
-    for (int i = t; i < n; i += kThreads) all[i] = keys[(int64_t)q * cap + i];
+    if (t < n) all[t] = spec;
+    for (int i = t + kThreads; i < n; i += kThreads) all[i] = keys[(int64_t)q * cap + i];
     // a hinted (shard-local) search may find fewer than kp1 candidates: pad with (+inf, -1)
     for (int r = n + t; r < kp1; r += kThreads) { out_idx[(int64_t)q * kp1 + r] = -1; out_dist[(int64_t)q * kp1 + r] = kInf; }
     __syncthreads();
@@ -1303,21 +1340,27 @@ __global__ void __launch_bounds__(kThreads) knn_select_kernel(const uint32_t *__
         int r = 0;
         for (int u = 0; u < n; ++u) r += all[u] < k;
         if (r < kp1) {
-            out_idx[(int64_t)q * kp1 + r] = idx_offset + (int64_t)(uint32_t)k;
+            const int64_t id = idx_offset + (int64_t)(uint32_t)k;
+            out_idx[(int64_t)q * kp1 + r] = id;
             out_dist[(int64_t)q * kp1 + r] = key_dist(k);
+            if (r < kMaxFastKp1) s_nb[r] = id;
         }
     }
     if (fx.force != nullptr) {
-        __syncthreads();                                     // the list of this query is complete (same CTA wrote it)
+        const int nfound = n < kp1 ? n : kp1;
+        __syncthreads();                                     // the list of this query is complete
         double ds[3] = {0.0, 0.0, 0.0}, dq[3] = {0.0, 0.0, 0.0};
-        for (int c = t; c < kp1 - 1; c += kThreads) {
-            const int64_t i = fx.samp[q], j = out_idx[(int64_t)q * kp1 + 1 + c];
-            if (fx.sums == nullptr) {
-                if (fx.d == 2) intersect_pair<2>(fx.pos, fx.edges, i, j, fx.k_inter, fx.v_begin, fx.v_end, fx.force);
-                else intersect_pair<3>(fx.pos, fx.edges, i, j, fx.k_inter, fx.v_begin, fx.v_end, fx.force);
+        const int c = t;                                     // kp1 - 1 <= kMaxFastKp1 - 1 < kThreads: one pair per thread
+        if (c < kp1 - 1 && c + 1 < nfound) {
+            const int64_t j = s_nb[1 + c];                   // :421 column 0 dropped
+            if (fx.d == 2) {
+                const Vec<2> p1 = {qa.x, qa.y}, p2 = {qb4.x, qb4.y};
+                if (fx.sums == nullptr) intersect_pair_core<2, false>(fx.pos, fx.edges, qi, j, qe, p1, p2, fx.k_inter, fx.v_begin, fx.v_end, fx.force, ds, dq);
+                else intersect_pair_core<2, true>(fx.pos, fx.edges, qi, j, qe, p1, p2, fx.k_inter, fx.v_begin, fx.v_end, fx.force, ds, dq);
             } else {
-                if (fx.d == 2) intersect_pair<2, true>(fx.pos, fx.edges, i, j, fx.k_inter, fx.v_begin, fx.v_end, fx.force, ds, dq);
-                else intersect_pair<3, true>(fx.pos, fx.edges, i, j, fx.k_inter, fx.v_begin, fx.v_end, fx.force, ds, dq);
+                const Vec<3> p1 = {qa.x, qa.y, qa.z}, p2 = {qb4.x, qb4.y, qb4.z};
+                if (fx.sums == nullptr) intersect_pair_core<3, false>(fx.pos, fx.edges, qi, j, qe, p1, p2, fx.k_inter, fx.v_begin, fx.v_end, fx.force, ds, dq);
+                else intersect_pair_core<3, true>(fx.pos, fx.edges, qi, j, qe, p1, p2, fx.k_inter, fx.v_begin, fx.v_end, fx.force, ds, dq);
             }
         }
         if (fx.sums != nullptr) {                            // CTA-level reduction, then 2*d fp64 atomics per query
