@@ -32,7 +32,7 @@ import torch  # noqa: E402
 
 METRIC = "layout iters/sec & edge-updates/s, 1M-vertex BA graph, 1/2/4/8 B200 vs host CPU"
 # DRAM traffic of one knn_scan_kernel launch from the committed ncu capture (profiles/), bytes
-SCAN_DRAM_BYTES_NCU = {"c3": 64042752 + 419584}
+SCAN_DRAM_BYTES_NCU = {"c3": 64070400 + 451072}
 
 WORKLOADS = {
     # BASELINE.json configs[2] -- the headline
@@ -258,6 +258,9 @@ def run_b200(args, w):
     host_out = torch.empty_like(host_in).pin_memory()
     nbytes = host_in.numel() * 4
     Ke = max(3, min(K, 10))
+    emb.load_positions(host_in)                # untimed: first-use allocations of the staging buffers
+    one_step()
+    emb.read_positions(host_out)
     barrier()
     ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ea.record()
@@ -299,7 +302,7 @@ def run_b200(args, w):
                 "peak": fp32_peak / 1e12, "unit": "TFLOP/s", "frac": flops / scan_s / fp32_peak,
                 "traffic": SCAN_DRAM_BYTES_NCU.get(args.workload),
                 "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
-                                  "(profiles/r01_knn_scan_v3_ncu.md); algorithmic bytes per launch = 16*E = "
+                                  "(profiles/r01_knn_scan_v3_spring_csr_ncu.md); algorithmic bytes per launch = 16*E = "
                                   f"{16.0 * E:.0f}",
                 "peak_source": "gem_fp32_peak_probe: dependent-chain-free FFMA loop measured in this run "
                                "(MEASURED_PEAKS.json has no FP32 figure); nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.5",
@@ -319,9 +322,18 @@ def run_b200(args, w):
                                   "algorithmic_bytes": ka_bytes, "ms": stage["spring_mid"],
                                   "note": "bound in practice by the L1 wavefront rate of 2E scattered 16-byte position "
                                           "gathers (DESIGN.md section 4a), not by DRAM"},
-            "update_pass1+2": {"bound": "hbm", "achieved": kd_bytes / (stage["update"] * 1e-3) / 1e9, "peak": hbm,
-                               "unit": "GB/s", "frac": kd_bytes / (stage["update"] * 1e-3) / 1e9 / hbm,
-                               "algorithmic_bytes": kd_bytes, "ms": stage["update"]},
+            "update (stats pass + normalise)": {
+                "bound": "hbm", "achieved": kd_bytes / (stage["update"] * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                "frac": kd_bytes / (stage["update"] * 1e-3) / 1e9 / hbm, "algorithmic_bytes": kd_bytes,
+                "ms": stage["update"],
+                "note": "the `update` stage is the normalisation pass only: the add of pass 1 is done by the spring kernel "
+                        "(it writes pos+F) and the column-sum pass is timed inside the spring stage; in the timed steps "
+                        "it runs on the side stream next to the scan. frac uses the full 20dN algorithmic bytes of the "
+                        "reference's update and is therefore an upper bound for this stage alone"},
+            "spring+update combined": {
+                "bound": "hbm", "algorithmic_bytes": ka_bytes + kd_bytes, "ms": stage["spring_mid"] + stage["update"],
+                "achieved": (ka_bytes + kd_bytes) / ((stage["spring_mid"] + stage["update"]) * 1e-3) / 1e9, "peak": hbm,
+                "unit": "GB/s", "frac": (ka_bytes + kd_bytes) / ((stage["spring_mid"] + stage["update"]) * 1e-3) / 1e9 / hbm},
             "peak_source": peak_src,
         }
         # whole-iteration roofline: T_roof = B_iter/BW + F_iter/P
