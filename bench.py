@@ -360,9 +360,9 @@ def run_b200(args, w):
     ms_per_step = total_ms / K
     value = E / (ms_per_step * 1e-3)
     # kernels of libgraphem_b200.so per iteration (memset / memcpy nodes and torch / NCCL kernels not counted):
-    # sample, query_mid, linegraph_hint, knn_bound, knn_threshold, spring_csr, knn_scan, knn_select(+intersection),
-    # update_pass1, update_pass2  [+ topk_merge, intersection on N > 1]
-    launches_per_step = 10 if world == 1 else 12
+    # 1 GPU: linegraph_hint (+sample +query midpoints), knn_bound, knn_threshold, spring_csr, column sums, knn_scan,
+    # knn_select (+intersection), normalise; N > 1: the 12 stage kernels of sharded.CudaStages
+    launches_per_step = 8 if world == 1 else 12
     line = {
         "metric": METRIC, "value": value, "unit": "edge-updates/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,

@@ -405,3 +405,41 @@ def test_50_iterations_spearman_vs_reference(name):
     r2 = np.linalg.norm(gr.GraphEmbedderPyTorch(adj, **kw).run_layout(50), axis=1)
     tol2 = 0.02 + 3.0 * float(np.std(z["ens_rho_degree"]))
     assert abs(spearmanr(r2, z["degree"]).correlation - float(z["rho_degree"])) <= tol2
+
+
+# ----------------------------------------------------------------------------- BASELINE.json full sizes: size-independent properties
+@pytest.mark.parametrize("workload", ["c2", "c3"])
+def test_full_size_iteration_properties(workload):
+    """At the bench's full sizes the CPU oracle is too slow to be the checker, so the fused iteration
+    (gem_layout_step: two streams, spring writing pos+F, fused intersection + sum corrections) is checked
+    against in-library cross-checks and invariants:
+      * its neighbour lists == the exact streaming kernel (one CTA per query, no filter) on the same midpoints;
+      * its new positions == the stage-by-stage path (spring forces, intersection forces, two-pass update
+        through the private stage API, each parity-tested against the oracle at small sizes) within 1e-5;
+      * sample: S distinct ids < E; output columns: mean 0, unbiased std 1."""
+    import bench
+    import graphem_rapids_b200 as gr
+    w = bench.WORKLOADS[workload]
+    adj = bench.make_graph(w)
+    n, d, k = adj.shape[0], w["d"], w["k"]
+    pos0 = bench.initial_positions(n, d)
+    emb = gr.GraphEmbedderPyTorch(adj, n_components=d, device="cuda:0", n_neighbors=k, sample_size=w["S"], verbose=False,
+                                  seed=0, initial_positions=pos0)
+    for it in range(2):
+        before = emb._positions.clone()
+        mid = emb._compute_midpoints(before, emb.edges)
+        F = emb._compute_spring_forces(before, emb.edges)
+        emb.update_positions()
+        samp = emb.last_sampled_indices.clone()
+        assert samp.unique().numel() == samp.numel() and int(samp.max()) < emb.n_edges and int(samp.min()) >= 0
+        knn_full = emb._bufs["knn_idx"].clone()
+        ex_idx, ex_dist = emb._knn_points(mid[samp], mid, k + 1, exact=True, return_distances=True)
+        assert torch.equal(knn_full, ex_idx), f"iteration {it}: fast path != exact kernel"
+        assert torch.equal(emb._bufs["knn_dist"], ex_dist)
+        G = emb._compute_intersection_forces(before, emb.edges, knn_full[:, 1:], samp)
+        staged = emb._apply_update(before, F, G).cpu().numpy()
+        got = emb.positions
+        assert rel_inf(got, staged) <= TOL, f"iteration {it}"
+        assert np.all(np.isfinite(got))
+        assert np.abs(got.mean(0, dtype=np.float64)).max() < 1e-4
+        assert np.abs(got.std(0, ddof=1, dtype=np.float64) - 1.0).max() < 1e-3
