@@ -377,7 +377,7 @@ def run_b200(args, w):
         "wall_s_timed_region": t_wall,
         "e2e": {"value": E / (e2e_ms * 1e-3), "unit": "edge-updates/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
-                "api": "load_positions(pinned) -> update_positions() -> read_positions(pinned)"},
+                "api": "load_positions(pinned host) -> run_layout_device(1) [replay of the captured iteration] -> read_positions(pinned host)"},
         "gpu_launches": launches_per_step * K,
         "timed_steps_ms": {"min": float(np.min(step_ms)), "median": float(np.median(step_ms)), "max": float(np.max(step_ms))},
         "clocks": clk,

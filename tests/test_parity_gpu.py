@@ -443,3 +443,23 @@ def test_full_size_iteration_properties(workload):
         assert np.all(np.isfinite(got))
         assert np.abs(got.mean(0, dtype=np.float64)).max() < 1e-4
         assert np.abs(got.std(0, ddof=1, dtype=np.float64) - 1.0).max() < 1e-3
+
+
+@pytest.mark.parametrize("S,k", [(1500, 10), (256, 80)])
+def test_paths_outside_the_fast_path_limits(S, k):
+    """More than 1024 queries (several KNN batches, general in-series iteration) and k+1 > 64 (exact
+    streaming kernel): same contract as the fast path."""
+    import graphem_rapids_b200 as gr
+    n = 12000
+    adj = gr.generate_random_regular(n, 8, seed=6)
+    pos0 = np.random.default_rng(6).standard_normal((n, 3)).astype(np.float32)
+    emb = gr.GraphEmbedderPyTorch(adj, n_components=3, device="cuda:0", n_neighbors=k, sample_size=S, verbose=False,
+                                  seed=2, initial_positions=pos0)
+    emb.update_positions()
+    samp = emb.last_sampled_indices.cpu()
+    ref = oracle.layout_step(torch.from_numpy(pos0), emb.edges.cpu(), samp, n_neighbors=k, strict=True)
+    assert torch.equal(emb._bufs["knn_idx"].cpu(), ref["knn_full"])
+    assert torch.equal(emb._bufs["knn_dist"].cpu(), ref["knn_dist"])
+    assert rel_inf(emb.positions, ref["new_pos"].numpy()) <= TOL
+    p = emb.run_layout(3)                               # graph replay of the general path
+    assert np.all(np.isfinite(p))
