@@ -1512,6 +1512,38 @@ __global__ void __launch_bounds__(kThreads) update_pass2_kernel(float *pos, cons
     }
 }
 
+// Multi-GPU form of pass 2, fused with the position exchange: the rank normalises the rows it owns and
+// stores each result row into EVERY rank's replica of the position buffer -- its own and, through
+// peer-mapped pointers (NVLink / NVSwitch P2P stores), the others' -- so the all-gather of the updated
+// positions is not a separate collective but the store phase of this kernel.
+constexpr int kMaxPeers = 16;
+struct PeerPtrs { float *p[kMaxPeers]; };
+template <int LD>
+__global__ void __launch_bounds__(kThreads) update_pass2_bcast_kernel(PeerPtrs peers, int world, const float *src,
+                                                                      int64_t row_begin, int64_t n, int64_t n_total,
+                                                                      int d, const void *__restrict__ ws) {
+    using VT = typename std::conditional<LD == 2, float2, float4>::type;
+    const double *sums = reinterpret_cast<const double *>(ws);
+    __shared__ float s_mean[LD], s_sd[LD];
+    if (threadIdx.x < LD) {
+        float m = 0.f, sdv = 1.f;
+        if ((int)threadIdx.x < d) col_stats(sums, LD, threadIdx.x, n_total, m, sdv);
+        s_mean[threadIdx.x] = m; s_sd[threadIdx.x] = sdv;
+    }
+    __syncthreads();
+    float mean[LD], sd[LD];
+#pragma unroll
+    for (int j = 0; j < LD; ++j) { mean[j] = s_mean[j]; sd[j] = s_sd[j]; }
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += stride) {
+        VT p = reinterpret_cast<const VT *>(src)[v];             // src: the rank's own (unnormalised) rows
+        float *pp = reinterpret_cast<float *>(&p);
+#pragma unroll
+        for (int j = 0; j < LD; ++j) pp[j] = __fdiv_rn(pp[j] - mean[j], sd[j]);   // :802, :804
+        for (int r = 0; r < world; ++r) reinterpret_cast<VT *>(peers.p[r])[row_begin + v] = p;
+    }
+}
+
 // generic d: one thread per element, column = idx % d; per-block column partials in smem
 __global__ void __launch_bounds__(kThreads) update_pass1_generic_kernel(float *__restrict__ pos,
                                                                         const float *__restrict__ fs,
@@ -2111,6 +2143,25 @@ static int layout_spring(const gem_plan *p, void *st, bool fuse) {
         return spring_csr_launch(p->pos, p->row_ptr, p->col, p->up_ptr, 0, p->n, p->hubs, p->n_hubs, p->d, p->k_attr,
                                  p->l_min, p->force, p->mid, 0, fuse, st);
     return gem_spring_midpoints(p->pos, p->edges, p->n, p->e, p->d, p->k_attr, p->l_min, p->force, p->mid, st);
+}
+
+int gem_update_normalise_push(float *const *peer_pos_host, int world, const float *src, int64_t row_begin, int64_t n,
+                              int64_t n_total, int d, void *stats_ws, void *stream) {
+    if (!peer_pos_host || world < 1 || world > kMaxPeers || !src || !stats_ws || row_begin < 0 || n < 0 || n_total <= 0 ||
+        (d != 2 && d != 3))
+        return GEM_E_BADARG;
+    if ((uintptr_t)stats_ws & 255) return GEM_E_WORKSPACE;
+    if (n == 0) return GEM_OK;
+    PeerPtrs pp;
+    for (int r = 0; r < kMaxPeers; ++r) pp.p[r] = r < world ? peer_pos_host[r] : nullptr;
+    for (int r = 0; r < world; ++r)
+        if (!pp.p[r]) return GEM_E_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = grid_for(n, 8);
+    if (d == 2) update_pass2_bcast_kernel<2><<<grid, kThreads, 0, st>>>(pp, world, src, row_begin, n, n_total, d, stats_ws);
+    else update_pass2_bcast_kernel<4><<<grid, kThreads, 0, st>>>(pp, world, src, row_begin, n, n_total, d, stats_ws);
+    GEM_CHECK_LAUNCH();
+    return GEM_OK;
 }
 
 int gem_layout_step(const gem_plan *p, void *stream) {

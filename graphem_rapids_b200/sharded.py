@@ -124,11 +124,18 @@ class ShardedLayoutEngine:
         self.phase_b()
         if self.world > 1:
             dist.all_reduce(self.stats, group=self.group)
-        self.phase_c()
-        if self.world > 1:
-            block = self.own_block()
-            dist.all_gather_into_tensor(self.pos.view(-1), (block if self.inplace else block.clone()).view(-1),
-                                        group=self.group)
+        push = getattr(self.st, "normalise_and_push", None)
+        if self.world > 1 and push is not None and self.st.peer_ptrs is not None:
+            # CUDA stages with symmetric memory: pass 2 stores the normalised rows straight into every rank's
+            # replica (P2P stores inside the kernel), then one cross-rank barrier -- no all-gather collective.
+            # (The all-reduce above doubles as the "everyone has finished reading the old positions" barrier.)
+            push(self.pos, self.vb, self.ve, self.L.n, self.stats)
+        else:
+            self.phase_c()
+            if self.world > 1:
+                block = self.own_block()
+                dist.all_gather_into_tensor(self.pos.view(-1), (block if self.inplace else block.clone()).view(-1),
+                                            group=self.group)
 
 
 class CudaStages:
@@ -162,6 +169,22 @@ class CudaStages:
         self._side = torch.cuda.Stream(device=self.device)
         self._fork = torch.cuda.Event()
         self._join = torch.cuda.Event()
+
+    peer_ptrs = None            # set by attach_symmetric(): device pointers of every rank's position buffer
+    _symm = None
+
+    def attach_symmetric(self, handle):
+        """`handle`: torch.distributed._symmetric_memory rendezvous handle of the position buffer."""
+        self._symm = handle
+        self.peer_ptrs = (ctypes.c_void_p * handle.world_size)(*[int(p) for p in handle.buffer_ptrs])
+
+    def normalise_and_push(self, pos, vb, ve, n_total, stats):
+        ws = self._ws(ve - vb)
+        ws[: stats.numel() * 8].view(torch.float64).copy_(stats)
+        own = pos[vb:ve]
+        _cabi.check(self.lib.gem_update_normalise_push(self.peer_ptrs, len(self.peer_ptrs), _ptr(own), vb, ve - vb, n_total,
+                                                       self.d, _ptr(ws), self._s()), "gem_update_normalise_push")
+        self._symm.barrier(channel=0)        # every rank's rows have landed everywhere before anyone reads them
 
     def begin_step(self):
         main = torch.cuda.current_stream(self.device)
@@ -271,7 +294,7 @@ class ShardedGraphEmbedder(GraphEmbedderPyTorch):
     per GPU, backend nccl).  Same constructor; every rank passes the same adjacency / seed and ends
     every iteration with the same replicated positions."""
 
-    def __init__(self, adjacency, n_components=2, *args, process_group=None, **kwargs):
+    def __init__(self, adjacency, n_components=2, *args, process_group=None, use_symmetric_memory=True, **kwargs):
         if not dist.is_initialized():
             raise RuntimeError("ShardedGraphEmbedder needs an initialised torch.distributed process group")
         self._group = process_group
@@ -285,6 +308,25 @@ class ShardedGraphEmbedder(GraphEmbedderPyTorch):
         self._engine = ShardedLayoutEngine(self._layout, self._rank, stages, n_components=self.n_components,
                                            n_neighbors=self.n_neighbors, sample_size=self.sample_size,
                                            group=self._group, pos=self._pos)
+        # the replicated position buffer lives in symmetric memory: every rank can store into every replica
+        self._symm_handle = None
+        if self._world > 1 and use_symmetric_memory:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                buf = symm_mem.empty(tuple(self._pos.shape), dtype=torch.float32, device=self.device)
+                buf.copy_(self._pos)
+                self._symm_handle = symm_mem.rendezvous(buf, self._group if self._group is not None else dist.group.WORLD)
+                self._pos = buf
+                self._engine.pos = buf
+                stages.attach_symmetric(self._symm_handle)
+            except Exception as exc:  # pylint: disable=broad-exception-caught
+                if self.verbose:
+                    self.logger.warning("symmetric memory unavailable (%s): falling back to the NCCL all-gather", exc)
+            # the exchange method is part of the collective sequence: every rank must take the same one
+            ok = torch.tensor([1 if stages.peer_ptrs is not None else 0], device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self._group)
+            if int(ok.item()) == 0:
+                stages.peer_ptrs = None
         # rank 0's initial positions are the truth (ARPACK start vectors are not reproducible across processes)
         dist.broadcast(self._pos, src=dist.get_global_rank(self._group, 0) if self._group is not None else 0,
                        group=self._group)

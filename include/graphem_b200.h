@@ -178,6 +178,16 @@ int gem_update_workspace_bytes(int64_t n, int d, size_t *bytes);
 int gem_update_positions(float *pos, const float *f_spring, const float *f_inter, int64_t n,
                          int64_t n_total, int d, void *stats_ws, int phase, void *stream);
 
+/* Multi-GPU: pass 2 fused with the exchange of the updated positions.  The rank normalises its n own
+ * rows (read from `src`, row 0 = its first row) with the reduced column sums in stats_ws and stores
+ * every result row at row_begin + i of EACH of the `world` position buffers peer_pos_host[r]
+ * (host array of device pointers: the rank's own buffer and the peers' buffers mapped into this
+ * process, e.g. torch.distributed._symmetric_memory buffer_ptrs).  The stores to the peers travel
+ * over NVLink P2P inside this kernel; the caller separates iterations with a cross-rank barrier.
+ * d in {2, 3}, world <= 16. */
+int gem_update_normalise_push(float *const *peer_pos_host, int world, const float *src, int64_t row_begin,
+                              int64_t n, int64_t n_total, int d, void *stats_ws, void *stream);
+
 /* One whole iteration (update_positions, :776-806) on one GPU:
  *   side stream : sample -> query midpoints -> line-graph hint -> KNN bound/threshold   (needs pos only)
  *   `stream`    : spring forces + midpoints  ==join==>  KNN scan -> select + intersection forces -> update

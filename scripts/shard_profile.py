@@ -10,7 +10,8 @@ dist.init_process_group("nccl", device_id=dev)
 w = bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "c3"]
 adj = bench.make_graph(w)
 emb = ShardedGraphEmbedder(adj, n_components=w["d"], device=dev, n_neighbors=w["k"], sample_size=w["S"], verbose=False,
-                           seed=0, initial_positions=bench.initial_positions(adj.shape[0], w["d"]), use_cuda_graph=False)
+                           seed=0, initial_positions=bench.initial_positions(adj.shape[0], w["d"]), use_cuda_graph=False,
+                           use_symmetric_memory=False)
 g = emb._engine
 L = g.L
 print(f"[{rank}] rows {g.ve - g.vb} of slice {L.slice} edges {g.e_hi - g.e_lo} of {L.n_edges} hubs {emb._hubs.numel()}", flush=True)

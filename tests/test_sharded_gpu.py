@@ -109,8 +109,11 @@ def _nccl_worker(rank, world, port, out):
             ref = torch.from_numpy(got)
         # CUDA-graph replay of the whole sharded step (kernels on both streams + the NCCL collectives)
         # against eager launches of a second embedder with the same seed: same sample stream, same layout
+        # (emb: positions exchanged by P2P stores from the normalisation kernel over symmetric memory;
+        #  emb2: the NCCL all-gather fallback)
+        assert emb._engine.st.peer_ptrs is not None
         emb2 = ShardedGraphEmbedder(adj, n_components=d, device=dev, n_neighbors=k, sample_size=256, verbose=False,
-                                    seed=4, initial_positions=pos0, use_cuda_graph=False)
+                                    seed=4, initial_positions=pos0, use_cuda_graph=False, use_symmetric_memory=False)
         for it in range(3 + 4):
             emb2.update_positions()
         emb.run_layout_device(4)
