@@ -78,7 +78,8 @@ SIGNATURES = {
     "gem_update_positions": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p,
                                      c_int, c_void_p]),
     "gem_update_normalise_push": (c_int, [POINTER(c_void_p), c_int, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p,
-                                          c_void_p]),
+                                          c_void_p, c_void_p]),
+    "gem_push_bytes": (c_int, [POINTER(c_void_p), c_int, c_size_t, c_void_p, c_size_t, c_void_p]),
     "gem_layout_step": (c_int, [POINTER(GemPlan), c_void_p]),
     "gem_profile_step": (c_int, [POINTER(GemPlan), c_void_p, POINTER(c_float)]),
     "gem_pack_points": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),

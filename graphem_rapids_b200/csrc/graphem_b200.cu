@@ -1521,9 +1521,24 @@ struct PeerPtrs { float *p[kMaxPeers]; };
 template <int LD>
 __global__ void __launch_bounds__(kThreads) update_pass2_bcast_kernel(PeerPtrs peers, int world, const float *src,
                                                                       int64_t row_begin, int64_t n, int64_t n_total,
-                                                                      int d, const void *__restrict__ ws) {
+                                                                      int d, const void *__restrict__ ws,
+                                                                      const double *__restrict__ rank_sums) {
     using VT = typename std::conditional<LD == 2, float2, float4>::type;
-    const double *sums = reinterpret_cast<const double *>(ws);
+    // rank_sums != nullptr: the column sums arrive as one (2*LD)-double slot per rank (pushed by the peers);
+    // every rank adds them in rank order, so all ranks normalise with bit-identical statistics
+    __shared__ double s_sums[2 * LD];
+    if (threadIdx.x < 2 * LD) {
+        double a;
+        if (rank_sums != nullptr) {
+            a = 0.0;
+            for (int r = 0; r < world; ++r) a += rank_sums[r * 2 * LD + threadIdx.x];
+        } else {
+            a = reinterpret_cast<const double *>(ws)[threadIdx.x];
+        }
+        s_sums[threadIdx.x] = a;
+    }
+    __syncthreads();
+    const double *sums = s_sums;
     __shared__ float s_mean[LD], s_sd[LD];
     if (threadIdx.x < LD) {
         float m = 0.f, sdv = 1.f;
@@ -1541,6 +1556,16 @@ __global__ void __launch_bounds__(kThreads) update_pass2_bcast_kernel(PeerPtrs p
 #pragma unroll
         for (int j = 0; j < LD; ++j) pp[j] = __fdiv_rn(pp[j] - mean[j], sd[j]);   // :802, :804
         for (int r = 0; r < world; ++r) reinterpret_cast<VT *>(peers.p[r])[row_begin + v] = p;
+    }
+}
+
+// copy a small local block into the same offset of every rank's exchange buffer (peer-mapped pointers)
+__global__ void __launch_bounds__(kThreads) push_bytes_kernel(PeerPtrs peers, int world, size_t dst_offset,
+                                                              const uint4 *__restrict__ src, size_t n16) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 v = src[i];
+        for (int r = 0; r < world; ++r)
+            reinterpret_cast<uint4 *>(reinterpret_cast<char *>(peers.p[r]) + dst_offset)[i] = v;
     }
 }
 
@@ -2145,8 +2170,25 @@ static int layout_spring(const gem_plan *p, void *st, bool fuse) {
     return gem_spring_midpoints(p->pos, p->edges, p->n, p->e, p->d, p->k_attr, p->l_min, p->force, p->mid, st);
 }
 
+int gem_push_bytes(void *const *peer_base_host, int world, size_t dst_offset, const void *src, size_t nbytes,
+                   void *stream) {
+    if (!peer_base_host || world < 1 || world > kMaxPeers || !src || (nbytes & 15) || (dst_offset & 15) ||
+        ((uintptr_t)src & 15))
+        return GEM_E_BADARG;
+    if (nbytes == 0) return GEM_OK;
+    PeerPtrs pp;
+    for (int r = 0; r < kMaxPeers; ++r) pp.p[r] = r < world ? reinterpret_cast<float *>(peer_base_host[r]) : nullptr;
+    for (int r = 0; r < world; ++r)
+        if (!pp.p[r]) return GEM_E_BADARG;
+    const size_t n16 = nbytes / 16;
+    const int grid = (int)((n16 + kThreads - 1) / kThreads < 64 ? (n16 + kThreads - 1) / kThreads : 64);
+    push_bytes_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(pp, world, dst_offset, reinterpret_cast<const uint4 *>(src), n16);
+    GEM_CHECK_LAUNCH();
+    return GEM_OK;
+}
+
 int gem_update_normalise_push(float *const *peer_pos_host, int world, const float *src, int64_t row_begin, int64_t n,
-                              int64_t n_total, int d, void *stats_ws, void *stream) {
+                              int64_t n_total, int d, void *stats_ws, const double *rank_sums, void *stream) {
     if (!peer_pos_host || world < 1 || world > kMaxPeers || !src || !stats_ws || row_begin < 0 || n < 0 || n_total <= 0 ||
         (d != 2 && d != 3))
         return GEM_E_BADARG;
@@ -2158,8 +2200,8 @@ int gem_update_normalise_push(float *const *peer_pos_host, int world, const floa
         if (!pp.p[r]) return GEM_E_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = grid_for(n, 8);
-    if (d == 2) update_pass2_bcast_kernel<2><<<grid, kThreads, 0, st>>>(pp, world, src, row_begin, n, n_total, d, stats_ws);
-    else update_pass2_bcast_kernel<4><<<grid, kThreads, 0, st>>>(pp, world, src, row_begin, n, n_total, d, stats_ws);
+    if (d == 2) update_pass2_bcast_kernel<2><<<grid, kThreads, 0, st>>>(pp, world, src, row_begin, n, n_total, d, stats_ws, rank_sums);
+    else update_pass2_bcast_kernel<4><<<grid, kThreads, 0, st>>>(pp, world, src, row_begin, n, n_total, d, stats_ws, rank_sums);
     GEM_CHECK_LAUNCH();
     return GEM_OK;
 }

@@ -55,7 +55,7 @@ class ShardedLayoutEngine:
         self.knn_dist = a((S, kp1), torch.float32)
         # packed partial list of one rank: [idx int64 S*kp1 | dist fp32 S*kp1 (+pad to 8 bytes)]
         self._ib = S * kp1 * 8
-        self._nb = self._ib + (S * kp1 * 4 + 7) // 8 * 8
+        self._nb = (self._ib + S * kp1 * 4 + 15) // 16 * 16           # 16-byte granules (P2P push kernel)
         self.part = a((self._nb,), torch.uint8)
         self.gathered = a((self.world, self._nb), torch.uint8)
         self.part_idx = self.part[: self._ib].view(torch.int64).view(S, kp1)
@@ -64,6 +64,15 @@ class ShardedLayoutEngine:
         self.g_dist = self.gathered[:, self._ib: self._ib + S * kp1 * 4].view(torch.float32).view(self.world, S, kp1)
         self.stats = a((2 * ld,), torch.float64)                   # column sums | sums of squares
         self.iteration = 0
+
+    def bind_exchange(self, gathered: torch.Tensor):
+        """Use `gathered` ((world, nb) uint8, e.g. a view of a symmetric-memory buffer that the peers
+        store into) as the landing zone of the partial lists."""
+        S, kp1 = max(self.S, 1), self.kp1
+        assert gathered.shape == (self.world, self._nb) and gathered.dtype == torch.uint8
+        self.gathered = gathered
+        self.g_idx = gathered[:, : self._ib].view(torch.int64).view(self.world, S, kp1)
+        self.g_dist = gathered[:, self._ib: self._ib + S * kp1 * 4].view(torch.float32).view(self.world, S, kp1)
 
     # replicated state in / out (original vertex numbering on the host side)
     def set_positions(self, pos_nd: torch.Tensor):
@@ -116,26 +125,30 @@ class ShardedLayoutEngine:
         return self.pos[self.rank * self.L.slice: (self.rank + 1) * self.L.slice]
 
     def step(self, sampled_indices: Optional[torch.Tensor] = None):
+        st = self.st
+        p2p = self.world > 1 and getattr(st, "peer_ptrs", None) is not None
         self.phase_a(sampled_indices)
-        if self.world > 1:
+        if p2p:
+            # CUDA stages with symmetric memory: each exchange is a P2P store phase from this rank into every
+            # rank's buffer followed by one device-side cross-rank barrier -- no NCCL collective in the iteration
+            st.push_lists(self.part, self.rank)
+        elif self.world > 1:
             dist.all_gather_into_tensor(self.gathered.view(-1), self.part, group=self.group)
         else:
             self.gathered.view(-1).copy_(self.part)
         self.phase_b()
+        if p2p:
+            # the barrier inside also tells every rank that all ranks have finished READING the old positions
+            st.push_stats(self.stats, self.rank)
+            st.normalise_and_push(self.pos, self.vb, self.ve, self.L.n)
+            return
         if self.world > 1:
             dist.all_reduce(self.stats, group=self.group)
-        push = getattr(self.st, "normalise_and_push", None)
-        if self.world > 1 and push is not None and self.st.peer_ptrs is not None:
-            # CUDA stages with symmetric memory: pass 2 stores the normalised rows straight into every rank's
-            # replica (P2P stores inside the kernel), then one cross-rank barrier -- no all-gather collective.
-            # (The all-reduce above doubles as the "everyone has finished reading the old positions" barrier.)
-            push(self.pos, self.vb, self.ve, self.L.n, self.stats)
-        else:
-            self.phase_c()
-            if self.world > 1:
-                block = self.own_block()
-                dist.all_gather_into_tensor(self.pos.view(-1), (block if self.inplace else block.clone()).view(-1),
-                                            group=self.group)
+        self.phase_c()
+        if self.world > 1:
+            block = self.own_block()
+            dist.all_gather_into_tensor(self.pos.view(-1), (block if self.inplace else block.clone()).view(-1),
+                                        group=self.group)
 
 
 class CudaStages:
@@ -173,17 +186,41 @@ class CudaStages:
     peer_ptrs = None            # set by attach_symmetric(): device pointers of every rank's position buffer
     _symm = None
 
-    def attach_symmetric(self, handle):
-        """`handle`: torch.distributed._symmetric_memory rendezvous handle of the position buffer."""
-        self._symm = handle
-        self.peer_ptrs = (ctypes.c_void_p * handle.world_size)(*[int(p) for p in handle.buffer_ptrs])
+    def attach_symmetric(self, pos_handle, xchg_handle, xchg: torch.Tensor, list_bytes: int):
+        """pos_handle / xchg_handle: torch.distributed._symmetric_memory rendezvous handles of the position
+        buffer and of the small exchange buffer `xchg` = [world x list_bytes partial lists | world x 2*ld doubles]."""
+        self._symm = pos_handle
+        self._xsymm = xchg_handle
+        world = pos_handle.world_size
+        self.peer_ptrs = (ctypes.c_void_p * world)(*[int(p) for p in pos_handle.buffer_ptrs])
+        self.xchg_ptrs = (ctypes.c_void_p * world)(*[int(p) for p in xchg_handle.buffer_ptrs])
+        self._xchg = xchg
+        self._list_bytes = list_bytes
+        self._stats_off = world * list_bytes
+        self._stats_bytes = 2 * self.ld * 8
+        self._stage16 = torch.zeros((max(self._stats_bytes, 16),), device=self.device, dtype=torch.uint8)
 
-    def normalise_and_push(self, pos, vb, ve, n_total, stats):
+    def gathered_lists(self, world):
+        return self._xchg[: world * self._list_bytes].view(world, self._list_bytes)
+
+    def push_lists(self, part, rank):
+        _cabi.check(self.lib.gem_push_bytes(self.xchg_ptrs, len(self.xchg_ptrs), rank * self._list_bytes, _ptr(part),
+                                            part.numel(), self._s()), "gem_push_bytes(lists)")
+        self._xsymm.barrier(channel=0)
+
+    def push_stats(self, stats, rank):
+        src = stats.view(torch.uint8)
+        _cabi.check(self.lib.gem_push_bytes(self.xchg_ptrs, len(self.xchg_ptrs), self._stats_off + rank * self._stats_bytes,
+                                            _ptr(src), self._stats_bytes, self._s()), "gem_push_bytes(stats)")
+        self._xsymm.barrier(channel=1)
+
+    def normalise_and_push(self, pos, vb, ve, n_total):
         ws = self._ws(ve - vb)
-        ws[: stats.numel() * 8].view(torch.float64).copy_(stats)
         own = pos[vb:ve]
+        rank_sums = self._xchg[self._stats_off:]
         _cabi.check(self.lib.gem_update_normalise_push(self.peer_ptrs, len(self.peer_ptrs), _ptr(own), vb, ve - vb, n_total,
-                                                       self.d, _ptr(ws), self._s()), "gem_update_normalise_push")
+                                                       self.d, _ptr(ws), _ptr(rank_sums), self._s()),
+                    "gem_update_normalise_push")
         self._symm.barrier(channel=0)        # every rank's rows have landed everywhere before anyone reads them
 
     def begin_step(self):
@@ -315,10 +352,17 @@ class ShardedGraphEmbedder(GraphEmbedderPyTorch):
                 import torch.distributed._symmetric_memory as symm_mem
                 buf = symm_mem.empty(tuple(self._pos.shape), dtype=torch.float32, device=self.device)
                 buf.copy_(self._pos)
-                self._symm_handle = symm_mem.rendezvous(buf, self._group if self._group is not None else dist.group.WORLD)
+                grp = self._group if self._group is not None else dist.group.WORLD
+                self._symm_handle = symm_mem.rendezvous(buf, grp)
+                eng = self._engine
+                xbytes = self._world * eng._nb + self._world * 2 * self._ld * 8
+                xchg = symm_mem.empty(((xbytes + 255) // 256 * 256,), dtype=torch.uint8, device=self.device)
+                xchg.zero_()
+                self._xchg_handle = symm_mem.rendezvous(xchg, grp)
                 self._pos = buf
-                self._engine.pos = buf
-                stages.attach_symmetric(self._symm_handle)
+                eng.pos = buf
+                stages.attach_symmetric(self._symm_handle, self._xchg_handle, xchg, eng._nb)
+                eng.bind_exchange(stages.gathered_lists(self._world))
             except Exception as exc:  # pylint: disable=broad-exception-caught
                 if self.verbose:
                     self.logger.warning("symmetric memory unavailable (%s): falling back to the NCCL all-gather", exc)

@@ -184,9 +184,18 @@ int gem_update_positions(float *pos, const float *f_spring, const float *f_inter
  * (host array of device pointers: the rank's own buffer and the peers' buffers mapped into this
  * process, e.g. torch.distributed._symmetric_memory buffer_ptrs).  The stores to the peers travel
  * over NVLink P2P inside this kernel; the caller separates iterations with a cross-rank barrier.
- * d in {2, 3}, world <= 16. */
+ * d in {2, 3}, world <= 16.
+ * rank_sums (optional): world slots of 2*ld doubles, one per rank (its partial column sums, delivered by
+ * gem_push_bytes); when given they are added in rank order inside the kernel and stats_ws is not read,
+ * which replaces the all-reduce of the statistics and makes them bit-identical on every rank. */
 int gem_update_normalise_push(float *const *peer_pos_host, int world, const float *src, int64_t row_begin,
-                              int64_t n, int64_t n_total, int d, void *stats_ws, void *stream);
+                              int64_t n, int64_t n_total, int d, void *stats_ws, const double *rank_sums,
+                              void *stream);
+/* Copy nbytes (multiple of 16) from `src` to byte offset dst_offset of EVERY rank's exchange buffer
+ * (peer_base_host[r]: peer-mapped base pointers): the all-gather of a small per-rank block (partial
+ * top-(k+1) lists, column sums) as P2P stores. */
+int gem_push_bytes(void *const *peer_base_host, int world, size_t dst_offset, const void *src, size_t nbytes,
+                   void *stream);
 
 /* One whole iteration (update_positions, :776-806) on one GPU:
  *   side stream : sample -> query midpoints -> line-graph hint -> KNN bound/threshold   (needs pos only)
