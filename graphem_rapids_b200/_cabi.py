@@ -58,7 +58,9 @@ SIGNATURES = {
                                         c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "gem_knn_fast_path": (c_int, [c_int64, c_int64, c_int, c_int64, c_int]),
     "gem_knn_prepare": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p,
-                                c_void_p, c_size_t, c_void_p]),
+                                c_void_p, c_void_p, c_size_t, c_void_p]),
+    "gem_knn_query_prep": (c_int, [c_uint64, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
+                                   c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "gem_knn_scan": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_void_p,
                              c_void_p, c_size_t, c_void_p]),
     "gem_knn_linegraph_hint": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int,

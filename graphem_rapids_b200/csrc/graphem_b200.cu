@@ -1994,6 +1994,25 @@ int gem_knn_linegraph_hint(const float *pos, const int64_t *row_ptr, const int32
     return GEM_OK;
 }
 
+int gem_knn_query_prep(uint64_t seed, int64_t *iter_counter, int draw, const float *pos, const int64_t *row_ptr,
+                       const int32_t *col, const int32_t *edges, int64_t e, int64_t *samp, int64_t s, int d, int kp1,
+                       float *qmid, float *tau_hint, void *stream) {
+    if (!pos || !row_ptr || !col || !edges || !samp || !qmid || !tau_hint || s <= 0 || e <= 0 || kp1 <= 0 ||
+        (d != 2 && d != 3))
+        return GEM_E_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int2 *ed = reinterpret_cast<const int2 *>(edges);
+    const int grid = (int)((s + kWarps - 1) / kWarps);
+    if (d == 2)
+        knn_linegraph_hint_kernel<2><<<grid, kThreads, 0, st>>>(pos, row_ptr, col, ed, samp, (int)s, kp1, tau_hint, draw ? 1 : 0,
+                                                               seed, iter_counter, e, reinterpret_cast<float2 *>(qmid));
+    else
+        knn_linegraph_hint_kernel<3><<<grid, kThreads, 0, st>>>(pos, row_ptr, col, ed, samp, (int)s, kp1, tau_hint, draw ? 1 : 0,
+                                                               seed, iter_counter, e, reinterpret_cast<float4 *>(qmid));
+    GEM_CHECK_LAUNCH();
+    return GEM_OK;
+}
+
 int gem_knn_midpoints(const float *mid, int64_t e, int64_t idx_offset, int d, const float *qmid, int64_t s, int kp1,
                       int mm_mode, const float *tau_hint, int64_t *out_idx, float *out_dist, void *ws, size_t ws_bytes,
                       void *stream) {
@@ -2043,7 +2062,8 @@ int gem_knn_fast_path(int64_t e, int64_t e_total, int d, int64_t s, int kp1) {
 }
 
 int gem_knn_prepare(const float *mid, const float *pos, const int32_t *edges, int64_t e, int d, const float *qmid,
-                    int64_t s, int kp1, const float *tau_hint, void *ws, size_t ws_bytes, void *stream) {
+                    int64_t s, int kp1, const float *tau_hint, int64_t *bump_counter, void *ws, size_t ws_bytes,
+                    void *stream) {
     if (!qmid || e <= 0 || s <= 0 || kp1 <= 0 || (!mid && (!pos || !edges))) return GEM_E_BADARG;
     if (!gem_knn_fast_path(e, e, d, s, kp1)) return GEM_E_BADARG;
     const KnnLayout L = knn_layout(e, s, kp1);
@@ -2051,8 +2071,8 @@ int gem_knn_prepare(const float *mid, const float *pos, const int32_t *edges, in
     char *w = reinterpret_cast<char *>(ws);
     const int2 *ed = reinterpret_cast<const int2 *>(edges);
     cudaStream_t st = (cudaStream_t)stream;
-    return d == 2 ? knn_prepare<2>(L, w, mid, pos, ed, e, qmid, (int)s, kp1, tau_hint, st)
-                  : knn_prepare<3>(L, w, mid, pos, ed, e, qmid, (int)s, kp1, tau_hint, st);
+    return d == 2 ? knn_prepare<2>(L, w, mid, pos, ed, e, qmid, (int)s, kp1, tau_hint, st, bump_counter)
+                  : knn_prepare<3>(L, w, mid, pos, ed, e, qmid, (int)s, kp1, tau_hint, st, bump_counter);
 }
 
 int gem_knn_scan(const float *mid, int64_t e, int64_t idx_offset, int d, const float *qmid, int64_t s, int kp1,

@@ -177,6 +177,8 @@ class CudaStages:
         self._iter = torch.zeros((1,), device=self.device, dtype=torch.int64)   # device-side iteration counter
         self._knn_ws = None
         self._stats_ws = None
+        self._draw = False
+        self._bump = None
         # The KNN preparation (sample, query midpoints, line-graph hint, bound, thresholds) needs the
         # positions only: it runs on a side stream while the spring kernel runs on the current one.
         self._side = torch.cuda.Stream(device=self.device)
@@ -238,10 +240,10 @@ class CudaStages:
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def sample(self, iteration, n_edges, samp):
-        # the device counter advances by itself (bump = 1), so a captured CUDA graph replays correctly;
-        # every rank starts from 0 and therefore draws the same ids
-        _cabi.check(self.lib.gem_sample_edges(self.seed, _ptr(self._iter), 1, n_edges,
-                                              samp.numel(), _ptr(samp), self._side_ptr()), "gem_sample_edges")
+        # drawn by the fused preparation launch in hint(); the device counter advances by itself (bumped by the
+        # threshold kernel), so a captured CUDA graph replays correctly; every rank starts from 0 and therefore
+        # draws the same ids
+        self._draw = True
 
     def spring(self, pos, vb, ve, force, mid, e_lo):
         self._pos_ref = pos
@@ -251,14 +253,17 @@ class CudaStages:
             self.L_min, _ptr(force), _ptr(mid), e_lo, self._s()), "gem_spring_midpoints_csr")
 
     def query_mid(self, pos, samp, qmid):
-        _cabi.check(self.lib.gem_query_midpoints(_ptr(pos), _ptr(self.edges32), _ptr(samp), samp.numel(), self.d,
-                                                 _ptr(qmid), self._side_ptr()), "gem_query_midpoints")
+        self._qmid = qmid                                             # written by the fused launch in hint()
 
     def hint(self, pos, samp, kp1, tau_hint):
-        _cabi.check(self.lib.gem_knn_linegraph_hint(_ptr(pos), _ptr(self.row_ptr), _ptr(self.col), _ptr(self.edges32),
-                                                    _ptr(samp), samp.numel(), self.d, kp1, _ptr(tau_hint),
-                                                    self._side_ptr()),
-                    "gem_knn_linegraph_hint")
+        # sample (when not injected) + query midpoints + line-graph bound: one launch on the side stream
+        draw = 1 if self._draw else 0
+        _cabi.check(self.lib.gem_knn_query_prep(self.seed, _ptr(self._iter), draw, _ptr(pos), _ptr(self.row_ptr),
+                                                _ptr(self.col), _ptr(self.edges32), self.L.n_edges, _ptr(samp),
+                                                samp.numel(), self.d, kp1, _ptr(self._qmid), _ptr(tau_hint),
+                                                self._side_ptr()), "gem_knn_query_prep")
+        self._bump = _ptr(self._iter) if draw else None
+        self._draw = False
 
     def knn_local(self, mid, e_loc, e_total, e_lo, qmid, tau_hint, kp1, out_idx, out_dist):
         S = qmid.shape[0]
@@ -272,8 +277,9 @@ class CudaStages:
             # bound / thresholds from (pos, local edges) on the side stream, scan on the main one after the join
             e32 = self.edges32[e_lo: e_lo + e_loc]
             _cabi.check(self.lib.gem_knn_prepare(None, _ptr(self._pos_ref), _ptr(e32), e_loc, self.d, _ptr(qmid), S, kp1,
-                                                 _ptr(tau_hint), _ptr(self._knn_ws), self._knn_ws_bytes,
+                                                 _ptr(tau_hint), self._bump, _ptr(self._knn_ws), self._knn_ws_bytes,
                                                  self._side_ptr()), "gem_knn_prepare")
+            self._bump = None
             self._join.record(self._side)
             main.wait_event(self._join)
             _cabi.check(self.lib.gem_knn_scan(_ptr(mid), e_loc, e_lo, self.d, _ptr(qmid), S, kp1, _ptr(out_idx),
@@ -282,6 +288,9 @@ class CudaStages:
             return
         self._join.record(self._side)
         main.wait_event(self._join)
+        if self._bump is not None:                                    # no fast path here: bump the sample counter ourselves,
+            self._iter.add_(1)                                        # after the join (the fused launch reads it on the side stream)
+            self._bump = None
         mm = 1 if (S > 25 or e_total > 25) else 0                     # torch.cdist's rule on the WHOLE problem
         _cabi.check(self.lib.gem_knn_midpoints_shard(_ptr(mid), e_loc, e_total, e_lo, self.d, _ptr(qmid), S, kp1, mm,
                                                      _ptr(tau_hint), _ptr(out_idx), _ptr(out_dist), _ptr(self._knn_ws),

@@ -107,7 +107,8 @@ int gem_knn_midpoints_shard(const float *mid, int64_t e, int64_t e_total, int64_
 /* The two phases of the fast path of gem_knn_midpoints[_shard] as separate calls, for callers that
  * overlap them with other work (gem_layout_step does so internally; the multi-GPU host does it with
  * its own side stream):
- *   gem_knn_prepare  bound pass -> thresholds -> query coefficients into the constant bank.  With
+ *   gem_knn_prepare  bound pass -> thresholds -> query coefficients into the constant bank (and, when
+ *                    bump_counter != NULL, *bump_counter += 1: see gem_knn_query_prep).  With
  *                    mid == NULL the sampled candidates are recomputed from (pos, edges) -- `edges`
  *                    points at the first of the e local edges -- so the call depends on the positions
  *                    only and can run while the spring kernel is still producing `mid`;
@@ -118,7 +119,16 @@ int gem_knn_midpoints_shard(const float *mid, int64_t e, int64_t e_total, int64_
  * per device at a time. */
 int gem_knn_fast_path(int64_t e, int64_t e_total, int d, int64_t s, int kp1);
 int gem_knn_prepare(const float *mid, const float *pos, const int32_t *edges, int64_t e, int d, const float *qmid,
-                    int64_t s, int kp1, const float *tau_hint, void *ws, size_t ws_bytes, void *stream);
+                    int64_t s, int kp1, const float *tau_hint, int64_t *bump_counter, void *ws, size_t ws_bytes,
+                    void *stream);
+/* The three per-query preparation steps in ONE launch (what gem_layout_step uses): draw the sample
+ * (draw != 0: like gem_sample_edges from (seed, *iter_counter), without incrementing the counter --
+ * pass it as bump_counter to the gem_knn_prepare that follows in the same stream), the query
+ * midpoints (gem_query_midpoints) and the line-graph bound (gem_knn_linegraph_hint).  d in {2,3};
+ * `edges` is the full (e, 2) list. */
+int gem_knn_query_prep(uint64_t seed, int64_t *iter_counter, int draw, const float *pos, const int64_t *row_ptr,
+                       const int32_t *col, const int32_t *edges, int64_t e, int64_t *samp, int64_t s, int d,
+                       int kp1, float *qmid, float *tau_hint, void *stream);
 int gem_knn_scan(const float *mid, int64_t e, int64_t idx_offset, int d, const float *qmid, int64_t s, int kp1,
                  int64_t *out_idx, float *out_dist, void *ws, size_t ws_bytes, void *stream);
 /* Optional search radius per query for gem_knn_midpoints (tau_hint, may be NULL): only
