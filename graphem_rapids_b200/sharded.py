@@ -188,14 +188,29 @@ class CudaStages:
     peer_ptrs = None            # set by attach_symmetric(): device pointers of every rank's position buffer
     _symm = None
 
-    def attach_symmetric(self, pos_handle, xchg_handle, xchg: torch.Tensor, list_bytes: int):
+    multicast = False
+
+    def attach_symmetric(self, pos_handle, xchg_handle, xchg: torch.Tensor, list_bytes: int, use_multicast: bool = False):
         """pos_handle / xchg_handle: torch.distributed._symmetric_memory rendezvous handles of the position
         buffer and of the small exchange buffer `xchg` = [world x list_bytes partial lists | world x 2*ld doubles]."""
         self._symm = pos_handle
         self._xsymm = xchg_handle
         world = pos_handle.world_size
-        self.peer_ptrs = (ctypes.c_void_p * world)(*[int(p) for p in pos_handle.buffer_ptrs])
-        self.xchg_ptrs = (ctypes.c_void_p * world)(*[int(p) for p in xchg_handle.buffer_ptrs])
+        mc_pos = int(getattr(pos_handle, "multicast_ptr", 0) or 0) if use_multicast else 0
+        mc_x = int(getattr(xchg_handle, "multicast_ptr", 0) or 0) if use_multicast else 0
+        if mc_pos and mc_x:
+            # EXPERIMENTAL, off by default.  NVSwitch multicast mapping of the same buffers: ONE store to this
+            # address lands in every rank's replica (the switch replicates it), so a row leaves the GPU once
+            # instead of world-1 times.  Measured on 2 B200: plain stores to the multicast address followed by the
+            # symmetric-memory barrier give WRONG positions on the peers (the unicast signal overtakes the posted
+            # multicast writes); it needs multimem.st + a system-scope fence/flag protocol inside the kernel.
+            self.peer_ptrs = (ctypes.c_void_p * 1)(mc_pos)
+            self.xchg_ptrs = (ctypes.c_void_p * 1)(mc_x)
+            self.multicast = True
+        else:
+            self.peer_ptrs = (ctypes.c_void_p * world)(*[int(p) for p in pos_handle.buffer_ptrs])
+            self.xchg_ptrs = (ctypes.c_void_p * world)(*[int(p) for p in xchg_handle.buffer_ptrs])
+            self.multicast = False
         self._xchg = xchg
         self._list_bytes = list_bytes
         self._stats_off = world * list_bytes
@@ -340,7 +355,8 @@ class ShardedGraphEmbedder(GraphEmbedderPyTorch):
     per GPU, backend nccl).  Same constructor; every rank passes the same adjacency / seed and ends
     every iteration with the same replicated positions."""
 
-    def __init__(self, adjacency, n_components=2, *args, process_group=None, use_symmetric_memory=True, **kwargs):
+    def __init__(self, adjacency, n_components=2, *args, process_group=None, use_symmetric_memory=True,
+                 use_multicast=False, **kwargs):
         if not dist.is_initialized():
             raise RuntimeError("ShardedGraphEmbedder needs an initialised torch.distributed process group")
         self._group = process_group
@@ -370,7 +386,7 @@ class ShardedGraphEmbedder(GraphEmbedderPyTorch):
                 self._xchg_handle = symm_mem.rendezvous(xchg, grp)
                 self._pos = buf
                 eng.pos = buf
-                stages.attach_symmetric(self._symm_handle, self._xchg_handle, xchg, eng._nb)
+                stages.attach_symmetric(self._symm_handle, self._xchg_handle, xchg, eng._nb, use_multicast)
                 eng.bind_exchange(stages.gathered_lists(self._world))
             except Exception as exc:  # pylint: disable=broad-exception-caught
                 if self.verbose:

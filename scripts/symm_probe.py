@@ -12,6 +12,7 @@ try:
     t.fill_(float(rank + 1))
     hdl = symm_mem.rendezvous(t, dist.group.WORLD)
     log("rendezvous ok; world", hdl.world_size, "rank", hdl.rank, "ptrs", [hex(p) for p in hdl.buffer_ptrs], "multicast", hdl.has_multicast_support if hasattr(hdl, "has_multicast_support") else None)
+    log("multicast_ptr", hex(int(hdl.multicast_ptr or 0)))
     torch.cuda.synchronize(); dist.barrier()
     # push my rows [rank*512, (rank+1)*512) into every peer's buffer
     for r in range(world):
