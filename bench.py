@@ -369,7 +369,10 @@ def run_b200(args, w):
         "dtype": "f32", "data": "synthetic",
         "iters_per_s": 1e3 / ms_per_step,
         "config": {"workload": w["desc"], "N": n, "E": E, "sample_size": min(w["S"], E), "n_neighbors": w["k"],
-                   "parallelism": "single GPU" if world == 1 else f"vertex-range sharded x{world} (NCCL)",
+                   "parallelism": "single GPU" if world == 1 else
+                   (f"vertex-range sharded x{world}, exchanges = P2P stores over symmetric memory + device barriers"
+                    if getattr(emb._engine.st, "peer_ptrs", None) is not None
+                    else f"vertex-range sharded x{world}, NCCL all-gather / all-reduce"),
                    "l2": "flushed before every timed step (512 MiB write, untimed)",
                    "step": "one replay of the CUDA graph of one iteration (run_layout's production path)",
                    "sampler": "device (gem_sample_edges)", "init": "randn*0.1 default_rng(0)"},
