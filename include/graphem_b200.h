@@ -241,19 +241,20 @@ typedef struct gem_plan {
 
 int gem_layout_step(const gem_plan *plan_host, void *stream);
 
-/* Profiling variant (bench.py roofline): the same launches with a CUDA event after every stage;
+/* Profiling variant (bench.py roofline): the same kernels launched IN SERIES on `stream` (no side
+ * stream, separate sample / query-midpoint / hint launches) with a CUDA event after every stage;
  * SYNCHRONISES the stream and writes the GEM_NUM_STAGES stage durations (ms) to ms_host.
- * Only valid when the KNN needs a single query batch (s <= 2048). */
+ * Only valid when the KNN needs a single query batch (s <= 1024). */
 #define GEM_STAGE_SAMPLE 0
-#define GEM_STAGE_SPRING 1         /* memset + spring/midpoint kernel */
+#define GEM_STAGE_SPRING 1         /* spring/midpoint kernel (writes pos+F in the fused form) + column-sum pass */
 #define GEM_STAGE_QUERY_MID 2
-#define GEM_STAGE_KNN_BOUND 3      /* 2 memsets + bound kernel */
-#define GEM_STAGE_KNN_THRESHOLD 4
+#define GEM_STAGE_KNN_BOUND 3      /* line-graph hint + memset + bound kernel */
+#define GEM_STAGE_KNN_THRESHOLD 4  /* threshold kernel + coefficient copy to the constant bank */
 #define GEM_STAGE_KNN_SCAN 5       /* the dominant kernel */
-#define GEM_STAGE_KNN_SELECT 6
-#define GEM_STAGE_KNN_FALLBACK 7   /* exact kernel: overflow fallback (or the whole KNN for tiny / generic-d inputs) */
-#define GEM_STAGE_INTERSECT 8
-#define GEM_STAGE_UPDATE 9         /* both passes */
+#define GEM_STAGE_KNN_SELECT 6     /* select kernel (with the fused intersection forces in gem_layout_step) */
+#define GEM_STAGE_KNN_FALLBACK 7   /* exact kernel: the whole KNN for tiny / generic-d / k+1 > 64 inputs */
+#define GEM_STAGE_INTERSECT 8      /* stand-alone intersection kernel (general path only) */
+#define GEM_STAGE_UPDATE 9         /* normalisation pass (fused form) or both update passes */
 #define GEM_NUM_STAGES 10
 int gem_profile_step(const gem_plan *plan_host, void *stream, float *ms_host);
 
