@@ -49,6 +49,8 @@ SIGNATURES = {
     "gem_hub_degree": (c_int, []),
     "gem_spring_midpoints_csr": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64,
                                          c_int, c_float, c_float, c_void_p, c_void_p, c_int64, c_void_p]),
+    "gem_spring_update_csr": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64,
+                                      c_int, c_float, c_float, c_void_p, c_void_p, c_int64, c_void_p]),
     "gem_sample_edges": (c_int, [c_uint64, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p]),
     "gem_query_midpoints": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "gem_knn_workspace_bytes": (c_int, [c_int64, c_int, c_int64, c_int, POINTER(c_size_t)]),
@@ -72,6 +74,9 @@ SIGNATURES = {
     "gem_topk_merge": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "gem_topk_merge_strided": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int, c_void_p,
                                        c_void_p, c_void_p]),
+    "gem_topk_merge_intersect": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int, c_void_p, c_void_p,
+                                         c_void_p, c_void_p, c_void_p, c_int, c_float, c_int64, c_int64, c_void_p,
+                                         c_void_p, c_void_p]),
     "gem_intersection_forces": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64,
                                         c_int, c_float, c_void_p, c_void_p]),
     "gem_intersection_forces_range": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64,

@@ -1260,7 +1260,6 @@ __global__ void __launch_bounds__(kThreads) intersection_generic_kernel(const fl
     }
 }
 
-// per query: exact top-kp1 among n = counts[q] <= cap published keys (unique)
 // Optional fused tail (fx.force != nullptr): the CTA of query q then evaluates the k candidate
 // pairs (samp[q], neighbour c) of _compute_intersection_forces -- the separate intersection launch
 // and its dependency on this kernel disappear from the iteration's critical path.
@@ -1269,6 +1268,49 @@ struct FusedIntersect {
     float k_inter; int d, v_begin, v_end;
     double *sums;          // != nullptr: `force` holds new positions; correct these column sums (2*ld doubles)
 };
+// tail shared by the select and the merge kernel: thread c < k evaluates the candidate pair (query edge,
+// neighbour c) of the intersection stage; qi/qe/qa/qb4 = the query edge, its endpoints and their positions
+// (prefetched by the caller), s_nb = the selected neighbour ids in shared memory
+__device__ __forceinline__ void fused_intersect_tail(const FusedIntersect &fx, int q, int t, int kp1, int nfound,
+                                                     const int64_t *s_nb, int64_t qi, int2 qe, float4 qa, float4 qb4) {
+        __syncthreads();                                     // the list of this query is complete
+        double ds[3] = {0.0, 0.0, 0.0}, dq[3] = {0.0, 0.0, 0.0};
+        const int c = t;                                     // kp1 - 1 <= kMaxFastKp1 - 1 < kThreads: one pair per thread
+        if (c < kp1 - 1 && c + 1 < nfound) {
+            const int64_t j = s_nb[1 + c];                   // :421 column 0 dropped
+            if (fx.d == 2) {
+                const Vec<2> p1 = {qa.x, qa.y}, p2 = {qb4.x, qb4.y};
+                if (fx.sums == nullptr) intersect_pair_core<2, false>(fx.pos, fx.edges, qi, j, qe, p1, p2, fx.k_inter, fx.v_begin, fx.v_end, fx.force, ds, dq);
+                else intersect_pair_core<2, true>(fx.pos, fx.edges, qi, j, qe, p1, p2, fx.k_inter, fx.v_begin, fx.v_end, fx.force, ds, dq);
+            } else {
+                const Vec<3> p1 = {qa.x, qa.y, qa.z}, p2 = {qb4.x, qb4.y, qb4.z};
+                if (fx.sums == nullptr) intersect_pair_core<3, false>(fx.pos, fx.edges, qi, j, qe, p1, p2, fx.k_inter, fx.v_begin, fx.v_end, fx.force, ds, dq);
+                else intersect_pair_core<3, true>(fx.pos, fx.edges, qi, j, qe, p1, p2, fx.k_inter, fx.v_begin, fx.v_end, fx.force, ds, dq);
+            }
+        }
+        if (fx.sums != nullptr) {                            // CTA-level reduction, then 2*d fp64 atomics per query
+            const int ld = fx.d == 3 ? 4 : fx.d;
+            const bool active = t < ((kp1 - 1 + 31) / 32) * 32;           // whole warps that hold contributions
+            if (active) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        ds[c] += __shfl_down_sync(0xffffffffu, ds[c], o);
+                        dq[c] += __shfl_down_sync(0xffffffffu, dq[c], o);
+                    }
+                }
+                if ((t & 31) == 0) {
+                    for (int c = 0; c < fx.d; ++c) {
+                        if (ds[c] != 0.0) atomicAdd(fx.sums + c, ds[c]);
+                        if (dq[c] != 0.0) atomicAdd(fx.sums + ld + c, dq[c]);
+                    }
+                }
+            }
+        }
+}
+
+// per query: exact top-kp1 among n = counts[q] <= cap published keys (unique)
 __global__ void __launch_bounds__(kThreads) knn_select_kernel(const uint32_t *__restrict__ counts,
                                                               const uint64_t *__restrict__ keys, int cap, int kp1,
                                                               int64_t idx_offset, int64_t *__restrict__ out_idx,
@@ -1346,46 +1388,60 @@ __global__ void __launch_bounds__(kThreads) knn_select_kernel(const uint32_t *__
             if (r < kMaxFastKp1) s_nb[r] = id;
         }
     }
-    if (fx.force != nullptr) {
-        const int nfound = n < kp1 ? n : kp1;
-        __syncthreads();                                     // the list of this query is complete
-        double ds[3] = {0.0, 0.0, 0.0}, dq[3] = {0.0, 0.0, 0.0};
-        const int c = t;                                     // kp1 - 1 <= kMaxFastKp1 - 1 < kThreads: one pair per thread
-        if (c < kp1 - 1 && c + 1 < nfound) {
-            const int64_t j = s_nb[1 + c];                   // :421 column 0 dropped
-            if (fx.d == 2) {
-                const Vec<2> p1 = {qa.x, qa.y}, p2 = {qb4.x, qb4.y};
-                if (fx.sums == nullptr) intersect_pair_core<2, false>(fx.pos, fx.edges, qi, j, qe, p1, p2, fx.k_inter, fx.v_begin, fx.v_end, fx.force, ds, dq);
-                else intersect_pair_core<2, true>(fx.pos, fx.edges, qi, j, qe, p1, p2, fx.k_inter, fx.v_begin, fx.v_end, fx.force, ds, dq);
-            } else {
-                const Vec<3> p1 = {qa.x, qa.y, qa.z}, p2 = {qb4.x, qb4.y, qb4.z};
-                if (fx.sums == nullptr) intersect_pair_core<3, false>(fx.pos, fx.edges, qi, j, qe, p1, p2, fx.k_inter, fx.v_begin, fx.v_end, fx.force, ds, dq);
-                else intersect_pair_core<3, true>(fx.pos, fx.edges, qi, j, qe, p1, p2, fx.k_inter, fx.v_begin, fx.v_end, fx.force, ds, dq);
-            }
-        }
-        if (fx.sums != nullptr) {                            // CTA-level reduction, then 2*d fp64 atomics per query
-            const int ld = fx.d == 3 ? 4 : fx.d;
-            const bool active = t < ((kp1 - 1 + 31) / 32) * 32;           // whole warps that hold contributions
-            if (active) {
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        ds[c] += __shfl_down_sync(0xffffffffu, ds[c], o);
-                        dq[c] += __shfl_down_sync(0xffffffffu, dq[c], o);
-                    }
-                }
-                if ((t & 31) == 0) {
-                    for (int c = 0; c < fx.d; ++c) {
-                        if (ds[c] != 0.0) atomicAdd(fx.sums + c, ds[c]);
-                        if (dq[c] != 0.0) atomicAdd(fx.sums + ld + c, dq[c]);
-                    }
-                }
-            }
-        }
-    }
+    if (fx.force != nullptr) fused_intersect_tail(fx, q, t, kp1, n < kp1 ? n : kp1, s_nb, qi, qe, qa, qb4);
 }
 
+// merge of the per-rank partial lists (gem_topk_merge_strided) with the same fused tail as the select kernel:
+// on the multi-GPU path the CTA that has just merged query q's list evaluates its k candidate pairs
+__global__ void __launch_bounds__(kThreads) topk_merge_intersect_kernel(const float *__restrict__ dists,
+                                                                        const int64_t *__restrict__ idxs,
+                                                                        int64_t dist_stride, int64_t idx_stride, int parts,
+                                                                        int64_t s, int kp1, int64_t *__restrict__ out_idx,
+                                                                        float *__restrict__ out_dist, FusedIntersect fx) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ int64_t s_nb[kMaxFastKp1];
+    const int total = parts * kp1;
+    float *sd = reinterpret_cast<float *>(smem_raw);                        // total
+    int64_t *si = reinterpret_cast<int64_t *>(smem_raw + (((size_t)total * 4 + 15) / 16) * 16);   // total
+    const int q = blockIdx.x, t = threadIdx.x;
+    int64_t qi = 0;
+    int2 qe = make_int2(0, 0);
+    float4 qa = make_float4(0.f, 0.f, 0.f, 0.f), qb4 = qa;
+    if (fx.force != nullptr && t < kp1 - 1) {
+        qi = fx.samp[q];
+        qe = fx.edges[qi];
+        if (fx.d == 3) {
+            qa = __ldg(reinterpret_cast<const float4 *>(fx.pos) + qe.x);
+            qb4 = __ldg(reinterpret_cast<const float4 *>(fx.pos) + qe.y);
+        } else {
+            const float2 a2 = __ldg(reinterpret_cast<const float2 *>(fx.pos) + qe.x);
+            const float2 b2 = __ldg(reinterpret_cast<const float2 *>(fx.pos) + qe.y);
+            qa = make_float4(a2.x, a2.y, 0.f, 0.f); qb4 = make_float4(b2.x, b2.y, 0.f, 0.f);
+        }
+    }
+    for (int i = t; i < total; i += blockDim.x) {
+        const int p = i / kp1, r = i % kp1;
+        sd[i] = dists[(int64_t)p * dist_stride + (int64_t)q * kp1 + r] + 0.f;
+        si[i] = idxs[(int64_t)p * idx_stride + (int64_t)q * kp1 + r];
+    }
+    __syncthreads();
+    for (int i = t; i < total; i += blockDim.x) {
+        const float dv = sd[i];
+        const int64_t iv = si[i];
+        int r = 0;
+        for (int u = 0; u < total; ++u) {
+            const float du = sd[u];
+            r += (du < dv) || (du == dv && si[u] < iv);
+        }
+        // padding entries (+inf, -1) tie with each other: only real entries are written to the shared list
+        if (r < kp1) {
+            out_idx[(int64_t)q * kp1 + r] = iv; out_dist[(int64_t)q * kp1 + r] = dv;
+            if (r < kMaxFastKp1) s_nb[r] = iv;
+        }
+    }
+    // globally there are >= kp1 real candidates (k+1 <= E), so ranks 0..kp1-1 are all real and all written
+    if (fx.force != nullptr) fused_intersect_tail(fx, q, t, kp1, kp1, s_nb, qi, qe, qa, qb4);
+}
 
 // ==========================================================================================
 // (d) update (embedder_pytorch.py:796-804): two passes around one global reduction
@@ -1925,6 +1981,13 @@ int gem_spring_midpoints_csr(const float *pos, const int64_t *row_ptr, const int
                              false, stream);
 }
 
+int gem_spring_update_csr(const float *pos, const int64_t *row_ptr, const int32_t *col, const int64_t *up_ptr,
+                          int64_t v_begin, int64_t v_end, const int32_t *hubs, int64_t n_hubs, int d, float k_attr,
+                          float l_min, float *newpos, float *mid, int64_t mid_base, void *stream) {
+    return spring_csr_launch(pos, row_ptr, col, up_ptr, v_begin, v_end, hubs, n_hubs, d, k_attr, l_min, newpos, mid, mid_base,
+                             true, stream);
+}
+
 int gem_sample_edges(uint64_t seed, int64_t *iter_counter, int bump_counter, int64_t e, int64_t s, int64_t *samp,
                      void *stream) {
     if (!samp || e <= 0 || s <= 0) return GEM_E_BADARG;
@@ -2103,6 +2166,26 @@ int gem_topk_merge_strided(const float *dists, const int64_t *idxs, int64_t dist
     if (smem > 48 * 1024) return GEM_E_BADARG;
     topk_merge_kernel<<<(unsigned)s, kThreads, smem, (cudaStream_t)stream>>>(dists, idxs, dist_stride, idx_stride, parts, s, kp1,
                                                                              out_idx, out_dist);
+    GEM_CHECK_LAUNCH();
+    return GEM_OK;
+}
+
+int gem_topk_merge_intersect(const float *dists, const int64_t *idxs, int64_t dist_stride, int64_t idx_stride, int parts,
+                             int64_t s, int kp1, int64_t *out_idx, float *out_dist, const float *pos, const int32_t *edges,
+                             const int64_t *samp, int d, float k_inter, int64_t v_begin, int64_t v_end, float *newpos,
+                             double *sums, void *stream) {
+    if (!dists || !idxs || !out_idx || !out_dist || parts <= 0 || s <= 0 || kp1 <= 0 || kp1 > kMaxFastKp1) return GEM_E_BADARG;
+    if (!pos || !edges || !samp || !newpos || !sums || (d != 2 && d != 3) || v_begin < 0 || v_end < v_begin) return GEM_E_BADARG;
+    const int total = parts * kp1;
+    const size_t smem = (((size_t)total * 4 + 15) / 16) * 16 + (size_t)total * 8;
+    if (smem > 48 * 1024) return GEM_E_BADARG;
+    FusedIntersect fx = {};
+    if (kp1 > 1 && v_end > v_begin) {
+        fx.pos = pos; fx.edges = reinterpret_cast<const int2 *>(edges); fx.samp = samp; fx.force = newpos;
+        fx.k_inter = k_inter; fx.d = d; fx.v_begin = (int)v_begin; fx.v_end = (int)v_end; fx.sums = sums;
+    }
+    topk_merge_intersect_kernel<<<(unsigned)s, kThreads, smem, (cudaStream_t)stream>>>(dists, idxs, dist_stride, idx_stride, parts,
+                                                                                       s, kp1, out_idx, out_dist, fx);
     GEM_CHECK_LAUNCH();
     return GEM_OK;
 }

@@ -136,6 +136,15 @@ class ShardedLayoutEngine:
             dist.all_gather_into_tensor(self.gathered.view(-1), self.part, group=self.group)
         else:
             self.gathered.view(-1).copy_(self.part)
+        if p2p and getattr(st, "fused", False):
+            # fused form (CUDA stages): the spring kernel has written pos+F of the owned rows into self.force and a
+            # side-stream pass has taken its column sums; the merge kernel adds the intersection forces with a
+            # correction of the sums; the sums go to the peers straight from the workspace
+            st.merge_intersect(self.g_idx, self.g_dist, self.knn_idx, self.knn_dist, self.pos, self.samp, self.vb,
+                               self.ve, self.force)
+            st.push_stats(None, self.rank)
+            st.normalise_and_push(self.pos, self.vb, self.ve, self.L.n, src=self.force)
+            return
         self.phase_b()
         if p2p:
             # the barrier inside also tells every rank that all ranks have finished READING the old positions
@@ -190,7 +199,8 @@ class CudaStages:
 
     multicast = False
 
-    def attach_symmetric(self, pos_handle, xchg_handle, xchg: torch.Tensor, list_bytes: int, use_multicast: bool = False):
+    def attach_symmetric(self, pos_handle, xchg_handle, xchg: torch.Tensor, list_bytes: int, use_multicast: bool = False,
+                         fused: bool = True):
         """pos_handle / xchg_handle: torch.distributed._symmetric_memory rendezvous handles of the position
         buffer and of the small exchange buffer `xchg` = [world x list_bytes partial lists | world x 2*ld doubles]."""
         self._symm = pos_handle
@@ -215,7 +225,10 @@ class CudaStages:
         self._list_bytes = list_bytes
         self._stats_off = world * list_bytes
         self._stats_bytes = 2 * self.ld * 8
-        self._stage16 = torch.zeros((max(self._stats_bytes, 16),), device=self.device, dtype=torch.uint8)
+        self._spring_done = torch.cuda.Event()
+        self._stats_done = torch.cuda.Event()
+        self._force_ref = None
+        self.fused = bool(fused) and self.L.n_edges > 0
 
     def gathered_lists(self, world):
         return self._xchg[: world * self._list_bytes].view(world, self._list_bytes)
@@ -226,14 +239,14 @@ class CudaStages:
         self._xsymm.barrier(channel=0)
 
     def push_stats(self, stats, rank):
-        src = stats.view(torch.uint8)
+        src = stats.view(torch.uint8) if stats is not None else self._ws(1)       # fused form: straight from the workspace
         _cabi.check(self.lib.gem_push_bytes(self.xchg_ptrs, len(self.xchg_ptrs), self._stats_off + rank * self._stats_bytes,
                                             _ptr(src), self._stats_bytes, self._s()), "gem_push_bytes(stats)")
         self._xsymm.barrier(channel=1)
 
-    def normalise_and_push(self, pos, vb, ve, n_total):
+    def normalise_and_push(self, pos, vb, ve, n_total, src=None):
         ws = self._ws(ve - vb)
-        own = pos[vb:ve]
+        own = pos[vb:ve] if src is None else src
         rank_sums = self._xchg[self._stats_off:]
         _cabi.check(self.lib.gem_update_normalise_push(self.peer_ptrs, len(self.peer_ptrs), _ptr(own), vb, ve - vb, n_total,
                                                        self.d, _ptr(ws), _ptr(rank_sums), self._s()),
@@ -260,8 +273,20 @@ class CudaStages:
         # draws the same ids
         self._draw = True
 
+    fused = False               # set with attach_symmetric(): fused spring+update form of the iteration
+
     def spring(self, pos, vb, ve, force, mid, e_lo):
         self._pos_ref = pos
+        if self.fused and self.peer_ptrs is not None and ve > vb:
+            main = torch.cuda.current_stream(self.device)
+            _cabi.check(self.lib.gem_spring_update_csr(
+                _ptr(pos), _ptr(self.row_ptr), _ptr(self.col), _ptr(self.up_ptr), vb, ve,
+                _ptr(self.hubs) if self.hubs.numel() else None, int(self.hubs.numel()), self.d, self.k_attr,
+                self.L_min, _ptr(force), _ptr(mid), e_lo, self._s()), "gem_spring_update_csr")
+            self._spring_done.record(main)
+            self._n_own = ve - vb
+            self._force_ref = force
+            return
         _cabi.check(self.lib.gem_spring_midpoints_csr(
             _ptr(pos), _ptr(self.row_ptr), _ptr(self.col), _ptr(self.up_ptr), vb, ve,
             _ptr(self.hubs) if self.hubs.numel() else None, int(self.hubs.numel()), self.d, self.k_attr,
@@ -297,12 +322,14 @@ class CudaStages:
             self._bump = None
             self._join.record(self._side)
             main.wait_event(self._join)
+            self._side_stats_pass()
             _cabi.check(self.lib.gem_knn_scan(_ptr(mid), e_loc, e_lo, self.d, _ptr(qmid), S, kp1, _ptr(out_idx),
                                               _ptr(out_dist), _ptr(self._knn_ws), self._knn_ws_bytes, self._s()),
                         "gem_knn_scan")
             return
         self._join.record(self._side)
         main.wait_event(self._join)
+        self._side_stats_pass()
         if self._bump is not None:                                    # no fast path here: bump the sample counter ourselves,
             self._iter.add_(1)                                        # after the join (the fused launch reads it on the side stream)
             self._bump = None
@@ -310,6 +337,25 @@ class CudaStages:
         _cabi.check(self.lib.gem_knn_midpoints_shard(_ptr(mid), e_loc, e_total, e_lo, self.d, _ptr(qmid), S, kp1, mm,
                                                      _ptr(tau_hint), _ptr(out_idx), _ptr(out_dist), _ptr(self._knn_ws),
                                                      self._knn_ws_bytes, self._s()), "gem_knn_midpoints_shard")
+
+    def _side_stats_pass(self):
+        """Fused form: column sums of the new positions (pos+F of the owned rows) on the side stream, next to the scan."""
+        if not (self.fused and self.peer_ptrs is not None and getattr(self, "_force_ref", None) is not None):
+            return
+        ws = self._ws(self._n_own)
+        self._side.wait_event(self._spring_done)
+        _cabi.check(self.lib.gem_update_positions(_ptr(self._force_ref), None, None, self._n_own, self._n_own, self.d,
+                                                  _ptr(ws), 3, self._side_ptr()), "gem_update_positions(phase 3)")
+        self._stats_done.record(self._side)
+
+    def merge_intersect(self, g_idx, g_dist, out_idx, out_dist, pos, samp, vb, ve, newpos):
+        parts, S, kp1 = g_idx.shape
+        ws = self._ws(ve - vb)
+        torch.cuda.current_stream(self.device).wait_event(self._stats_done)     # the sums it corrects must be there
+        _cabi.check(self.lib.gem_topk_merge_intersect(_ptr(g_dist), _ptr(g_idx), g_dist.stride(0), g_idx.stride(0), parts,
+                                                      S, kp1, _ptr(out_idx), _ptr(out_dist), _ptr(pos), _ptr(self.edges32),
+                                                      _ptr(samp), self.d, self.k_inter, vb, ve, _ptr(newpos), _ptr(ws),
+                                                      self._s()), "gem_topk_merge_intersect")
 
     def merge(self, g_idx, g_dist, out_idx, out_dist):
         parts, S, kp1 = g_idx.shape
@@ -356,7 +402,7 @@ class ShardedGraphEmbedder(GraphEmbedderPyTorch):
     every iteration with the same replicated positions."""
 
     def __init__(self, adjacency, n_components=2, *args, process_group=None, use_symmetric_memory=True,
-                 use_multicast=False, **kwargs):
+                 use_multicast=False, fused_update=True, **kwargs):
         if not dist.is_initialized():
             raise RuntimeError("ShardedGraphEmbedder needs an initialised torch.distributed process group")
         self._group = process_group
@@ -386,7 +432,8 @@ class ShardedGraphEmbedder(GraphEmbedderPyTorch):
                 self._xchg_handle = symm_mem.rendezvous(xchg, grp)
                 self._pos = buf
                 eng.pos = buf
-                stages.attach_symmetric(self._symm_handle, self._xchg_handle, xchg, eng._nb, use_multicast)
+                stages.attach_symmetric(self._symm_handle, self._xchg_handle, xchg, eng._nb, use_multicast,
+                                        fused=bool(fused_update) and self.n_neighbors + 1 <= 64)
                 eng.bind_exchange(stages.gathered_lists(self._world))
             except Exception as exc:  # pylint: disable=broad-exception-caught
                 if self.verbose:

@@ -73,6 +73,15 @@ int gem_spring_midpoints_csr(const float *pos, const int64_t *row_ptr, const int
                              int64_t v_begin, int64_t v_end, const int32_t *hubs, int64_t n_hubs, int d,
                              float k_attr, float l_min, float *force, float *mid, int64_t mid_base, void *stream);
 
+/* The same kernel in its fused spring+update form: `newpos` (row 0 = vertex v_begin) receives
+ * pos + F_spring -- the add of the update's pass 1 (:799) without materialising F.  Follow with
+ * gem_update_positions(newpos, ..., phase = 3) for the column sums, add the intersection forces with
+ * the sum-correcting form (gem_topk_merge_intersect, or the select kernel inside gem_layout_step) and
+ * finish with gem_update_normalise_push or pass 2. */
+int gem_spring_update_csr(const float *pos, const int64_t *row_ptr, const int32_t *col, const int64_t *up_ptr,
+                          int64_t v_begin, int64_t v_end, const int32_t *hubs, int64_t n_hubs, int d,
+                          float k_attr, float l_min, float *newpos, float *mid, int64_t mid_base, void *stream);
+
 /* Sampling of the query edges.  Replaces `torch.randperm(E, device)[:S]` / `arange(E)`
  * (_locate_knn_midpoints, :404-413) by a keyed bijection of [0,e) evaluated at 0..s-1
  * (Feistel network with cycle walking, key = (seed, *iter_counter)); s distinct ids, no host
@@ -161,6 +170,16 @@ int gem_topk_merge(const float *dists, const int64_t *idxs, int parts, int64_t s
  * lets one all-gather of a packed {dist | idx} block per rank feed the merge without repacking. */
 int gem_topk_merge_strided(const float *dists, const int64_t *idxs, int64_t dist_stride, int64_t idx_stride,
                            int parts, int64_t s, int kp1, int64_t *out_idx, float *out_dist, void *stream);
+
+/* gem_topk_merge_strided with the intersection stage fused into its tail (multi-GPU form of what the
+ * select kernel does inside gem_layout_step): the CTA that merged query q's list evaluates its k
+ * candidate pairs and adds the repulsion to the rows of `newpos` (fused spring+update form, row 0 =
+ * vertex v_begin, only vertices in [v_begin, v_end)) with atomics that return the old row; the exact
+ * change of the column sums is added to `sums` (2*ld doubles: sum | sum of squares). */
+int gem_topk_merge_intersect(const float *dists, const int64_t *idxs, int64_t dist_stride, int64_t idx_stride,
+                             int parts, int64_t s, int kp1, int64_t *out_idx, float *out_dist, const float *pos,
+                             const int32_t *edges, const int64_t *samp, int d, float k_inter, int64_t v_begin,
+                             int64_t v_end, float *newpos, double *sums, void *stream);
 
 /* (c) intersection repulsion.  Replaces _compute_intersection_forces (:638-736) and
  * _check_line_intersections (:738-774).  knn_full is the (s, kp1) list INCLUDING column 0,

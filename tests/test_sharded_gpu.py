@@ -112,7 +112,8 @@ def _nccl_worker(rank, world, port, out):
         # (emb: positions exchanged by P2P stores from the normalisation kernel over symmetric memory;
         #  emb2: the NCCL all-gather fallback)
         assert emb._engine.st.peer_ptrs is not None
-        print(f'[{rank}] exchange: symmetric memory, multicast={emb._engine.st.multicast}', flush=True)
+        print(f'[{rank}] exchange: symmetric memory, multicast={emb._engine.st.multicast} fused={emb._engine.st.fused}', flush=True)
+        assert emb._engine.st.fused
         emb2 = ShardedGraphEmbedder(adj, n_components=d, device=dev, n_neighbors=k, sample_size=256, verbose=False,
                                     seed=4, initial_positions=pos0, use_cuda_graph=False, use_symmetric_memory=False)
         for it in range(3 + 4):
