@@ -72,57 +72,89 @@ def initial_positions(n, d):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons DURING the timed region.  The region is short (K steps of ~0.3 ms), so
+    the sampler is an NVML thread polling every ~2 ms (nvidia-smi -lms cannot start that fast); falls back
+    to the nvidia-smi query of B200_PROFILING.md when pynvml is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index=0):
         self.gpu_index = gpu_index
-        self.proc = None
-        self.lines = []
+        self.samples = []           # (sm_mhz, reasons bitmask)
+        self.sm_max = None
+        self._stop = threading.Event()
+        self.thread = None
+        self.nvml = None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [x.strip() for x in vis.split(",") if x.strip()]
+            if self.gpu_index < len(ids) and ids[self.gpu_index].isdigit():
+                return int(ids[self.gpu_index])
+        return self.gpu_index
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu_index)],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
             self.thread.start()
         except Exception:
-            self.proc = None
+            self.nvml = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _poll(self):
+        n = self.nvml
+        while not self._stop.is_set():
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                try:
+                    rs = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    rs = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.samples.append((sm, rs))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def _smi_once(self):
+        try:
+            out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                  str(self._physical_index())], capture_output=True, text=True, timeout=10).stdout
+            parts = [x.strip() for x in out.strip().splitlines()[-1].split(",")]
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            reasons = [nm for nm, val in zip(names, parts[5:9]) if val.lower().startswith("active")]
+            return {"sm_mhz": float(parts[1]), "sm_max_mhz": float(parts[2]), "reasons": reasons, "samples": 1,
+                    "source": "nvidia-smi query right after the timed region (pynvml unavailable)"}
+        except Exception:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            parts = [p.strip() for p in ln.split(",")]
-            if len(parts) < 9:
-                continue
-            try:
-                sm.append(float(parts[1]))
-                smax.append(float(parts[2]))
-            except ValueError:
-                continue
-            for nm, val in zip(names, parts[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(smax)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        if self.nvml is None:
+            return self._smi_once()
+        self._stop.set()
+        self.thread.join(timeout=1.0)
+        n = self.nvml
+        if not self.samples:
+            return self._smi_once()
+        def bit(new_name, old_name, default):
+            return getattr(n, new_name, getattr(n, old_name, default))
+        bits = {"hw_slowdown": bit("nvmlClocksEventReasonHwSlowdown", "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": bit("nvmlClocksEventReasonHwThermalSlowdown",
+                                           "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": bit("nvmlClocksEventReasonSwThermalSlowdown",
+                                           "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": bit("nvmlClocksEventReasonSwPowerCap", "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        seen = 0
+        for _, rs in self.samples:
+            seen |= rs
+        reasons = sorted(nm for nm, bit in bits.items() if seen & bit)
+        return {"sm_mhz": float(np.median([sm for sm, _ in self.samples])), "sm_max_mhz": self.sm_max, "reasons": reasons,
+                "samples": len(self.samples), "source": "NVML polled every ~2 ms during the timed region"}
 
 
 def measured_peaks():
