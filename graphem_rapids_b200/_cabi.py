@@ -89,6 +89,9 @@ SIGNATURES = {
     "gem_push_bytes": (c_int, [POINTER(c_void_p), c_int, c_size_t, c_void_p, c_size_t, c_void_p]),
     "gem_layout_step": (c_int, [POINTER(GemPlan), c_void_p]),
     "gem_profile_step": (c_int, [POINTER(GemPlan), c_void_p, POINTER(c_float)]),
+    "gem_spmv_cols": (c_int, []),
+    "gem_spmv_normalized_adjacency": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float,
+                                              c_void_p, c_float, c_void_p]),
     "gem_pack_points": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "gem_check_line_intersections": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
                                              c_void_p, c_void_p]),

@@ -1680,6 +1680,67 @@ __global__ void __launch_bounds__(kThreads) update_pass2_generic_kernel(float *_
     }
 }
 
+// ==========================================================================================
+// SURVEY 8(f).1 -- initial embedding: block SpMV with the normalised adjacency  Y = D^-1/2 A D^-1/2 X
+// over the same symmetric CSR as the spring kernel (pull form: one lane group per vertex, no atomics).
+// X, Y are row-major (n, 8) fp32: the block of the Chebyshev-filtered subspace iteration run by the host
+// (embedder._laplacian_embedding_device), which replaces ARPACK eigsh(which='SM') of
+// _compute_laplacian_embedding (embedder_pytorch.py:337-379) for large graphs.
+// ==========================================================================================
+constexpr int kSpmvCols = 8;
+__global__ void __launch_bounds__(kThreads) spmv_norm_adj_kernel(const int64_t *__restrict__ row_ptr,
+                                                                 const int32_t *__restrict__ col,
+                                                                 const float *__restrict__ dinv,     // deg^-1/2 (0 if isolated)
+                                                                 const float *__restrict__ x, float *__restrict__ y,
+                                                                 int64_t n, float alpha, float beta,
+                                                                 const float *__restrict__ z, float gamma) {
+    // y = alpha * (M x) + beta * z + gamma * x   (z may be nullptr): one step of the three-term Chebyshev recurrence
+    // Y_{k+1} = (2/e) M Y_k - (2c/e) Y_k - Y_{k-1} in a single pass
+    const int g = threadIdx.x & (kGrp - 1);
+    const int64_t stride = ((int64_t)gridDim.x * kThreads) / kGrp;
+    const int64_t first = ((int64_t)blockIdx.x * kThreads + threadIdx.x) / kGrp;
+    const int64_t warp_first = ((int64_t)blockIdx.x * kThreads + (threadIdx.x & ~31)) / kGrp;
+    for (int64_t base = warp_first, v = first; base < n; base += stride, v += stride) {
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+        const bool valid = v < n;
+        if (valid) {
+            const int64_t r0 = row_ptr[v], r1 = row_ptr[v + 1];
+            for (int64_t t = r0 + g; t < r1; t += kGrp) {
+                const int w = __ldg(col + t);
+                const float dw = __ldg(dinv + w);
+                const float4 x0 = __ldg(reinterpret_cast<const float4 *>(x) + 2 * (int64_t)w);
+                const float4 x1 = __ldg(reinterpret_cast<const float4 *>(x) + 2 * (int64_t)w + 1);
+                a0.x = fmaf(dw, x0.x, a0.x); a0.y = fmaf(dw, x0.y, a0.y); a0.z = fmaf(dw, x0.z, a0.z); a0.w = fmaf(dw, x0.w, a0.w);
+                a1.x = fmaf(dw, x1.x, a1.x); a1.y = fmaf(dw, x1.y, a1.y); a1.z = fmaf(dw, x1.z, a1.z); a1.w = fmaf(dw, x1.w, a1.w);
+            }
+        }
+#pragma unroll
+        for (int m = 1; m < kGrp; m <<= 1) {
+            a0.x += __shfl_xor_sync(0xffffffffu, a0.x, m); a0.y += __shfl_xor_sync(0xffffffffu, a0.y, m);
+            a0.z += __shfl_xor_sync(0xffffffffu, a0.z, m); a0.w += __shfl_xor_sync(0xffffffffu, a0.w, m);
+            a1.x += __shfl_xor_sync(0xffffffffu, a1.x, m); a1.y += __shfl_xor_sync(0xffffffffu, a1.y, m);
+            a1.z += __shfl_xor_sync(0xffffffffu, a1.z, m); a1.w += __shfl_xor_sync(0xffffffffu, a1.w, m);
+        }
+        if (valid && g == 0) {
+            const float s = alpha * dinv[v];
+            float4 o0 = make_float4(s * a0.x, s * a0.y, s * a0.z, s * a0.w);
+            float4 o1 = make_float4(s * a1.x, s * a1.y, s * a1.z, s * a1.w);
+            if (z != nullptr) {
+                const float4 z0 = reinterpret_cast<const float4 *>(z)[2 * v], z1 = reinterpret_cast<const float4 *>(z)[2 * v + 1];
+                o0.x = fmaf(beta, z0.x, o0.x); o0.y = fmaf(beta, z0.y, o0.y); o0.z = fmaf(beta, z0.z, o0.z); o0.w = fmaf(beta, z0.w, o0.w);
+                o1.x = fmaf(beta, z1.x, o1.x); o1.y = fmaf(beta, z1.y, o1.y); o1.z = fmaf(beta, z1.z, o1.z); o1.w = fmaf(beta, z1.w, o1.w);
+            }
+            if (gamma != 0.f) {
+                const float4 x0 = reinterpret_cast<const float4 *>(x)[2 * v], x1 = reinterpret_cast<const float4 *>(x)[2 * v + 1];
+                o0.x = fmaf(gamma, x0.x, o0.x); o0.y = fmaf(gamma, x0.y, o0.y); o0.z = fmaf(gamma, x0.z, o0.z); o0.w = fmaf(gamma, x0.w, o0.w);
+                o1.x = fmaf(gamma, x1.x, o1.x); o1.y = fmaf(gamma, x1.y, o1.y); o1.z = fmaf(gamma, x1.z, o1.z); o1.w = fmaf(gamma, x1.w, o1.w);
+            }
+            reinterpret_cast<float4 *>(y)[2 * v] = o0;
+            reinterpret_cast<float4 *>(y)[2 * v + 1] = o1;
+        }
+    }
+}
+
 // FP32 FMA peak probe: 8 independent chains per thread
 __global__ void __launch_bounds__(kThreads) fma_probe_kernel(float *out, int iters, float a, float b) {
     float r[8];
@@ -2474,6 +2535,18 @@ int gem_profile_step(const gem_plan *p, void *stream, float *ms_host) {
     for (int i = 0; i <= GEM_NUM_STAGES; ++i) cudaEventDestroy(t.ev[i]);
     if (rc) return rc;
     return se == cudaSuccess ? GEM_OK : (int)se;
+}
+
+int gem_spmv_cols(void) { return kSpmvCols; }
+
+int gem_spmv_normalized_adjacency(const int64_t *row_ptr, const int32_t *col, const float *dinv_sqrt, const float *x,
+                                  float *y, int64_t n, float alpha, float beta, const float *z, float gamma, void *stream) {
+    if (!row_ptr || !col || !dinv_sqrt || !x || !y || n <= 0 || y == x || y == z) return GEM_E_BADARG;
+    if (((uintptr_t)x & 15) || ((uintptr_t)y & 15) || (z && ((uintptr_t)z & 15))) return GEM_E_BADARG;
+    const int grid = grid_for(n * kGrp, 8);
+    spmv_norm_adj_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(row_ptr, col, dinv_sqrt, x, y, n, alpha, beta, z, gamma);
+    GEM_CHECK_LAUNCH();
+    return GEM_OK;
 }
 
 int gem_pack_points(const float *pts, int64_t n, int d, float *out, void *stream) {

@@ -10,7 +10,9 @@ Deliberate differences (DESIGN.md "Boundary"):
     MemoryManager are removed).
   * the S query edges are drawn on the device by a keyed bijection (gem_sample_edges) instead of
     torch.randperm(E)[:S]; `sampler='torch'` restores the reference's call and RNG stream.
-  * extra keyword-only arguments: initial_positions, sampler, use_cuda_graph.
+  * extra keyword-only arguments: initial_positions, sampler, use_cuda_graph, init_method
+    ('auto' | 'arpack' | 'device': the Laplacian initial embedding on the host like the reference, or by
+    a device subspace iteration -- default for graphs of 20 000+ vertices).
 """
 from __future__ import annotations
 
@@ -41,7 +43,7 @@ class GraphEmbedderPyTorch:
     def __init__(self, adjacency, n_components=2, device=None, dtype=torch.float32, L_min=1.0,
                  k_attr=0.2, k_inter=0.5, n_neighbors=10, sample_size=256, batch_size=None,
                  memory_efficient=True, verbose=True, logger_instance=None, seed=None, *,
-                 initial_positions=None, sampler="device", use_cuda_graph=True):
+                 initial_positions=None, sampler="device", use_cuda_graph=True, init_method="auto"):
         # seeding contract (embedder_pytorch.py:106-111)
         if seed is not None:
             np.random.seed(seed)
@@ -92,6 +94,9 @@ class GraphEmbedderPyTorch:
             raise ValueError("sampler must be 'device' or 'torch'")
         self.sampler = sampler
         self.use_cuda_graph = bool(use_cuda_graph)
+        if init_method not in ("auto", "arpack", "device"):
+            raise ValueError("init_method must be 'auto', 'arpack' or 'device'")
+        self.init_method = init_method
 
         _cabi.load()
         _cabi.init_device(self.device.index)
@@ -213,22 +218,98 @@ class GraphEmbedderPyTorch:
 
     def _compute_laplacian_embedding(self):
         """Initial embedding (embedder_pytorch.py:337-379): eigenvectors 2..d+1 of the normalised
-        Laplacian via ARPACK on the host; random*0.1 if that fails.  One-off, outside the timed
-        path (SURVEY.md section 8(f) lists a device eigensolver as the next step)."""
-        import scipy.sparse.linalg as spla
-        from scipy.sparse.csgraph import laplacian
+        Laplacian; random*0.1 if the solver fails.  Small graphs use ARPACK on the host exactly like the
+        reference; from `_DEVICE_INIT_MIN_N` vertices on (ARPACK takes ~1 min at 200 K vertices) a
+        Chebyshev-filtered subspace iteration runs on the device.  One-off,
+        outside the timed path."""
         self.logger.info("Computing Laplacian embedding")
-        sym = sp.csr_matrix(self.adjacency + self.adjacency.transpose())
-        sym.data = np.ones_like(sym.data)
-        lap = laplacian(sym, normed=True)
-        k = self.n_components + 1
+        method = self.init_method
+        if method == "auto":
+            method = "device" if (self.n >= self._DEVICE_INIT_MIN_N and self.n_components + 1 <= 6
+                                  and self.n_edges > 0) else "arpack"
         try:
-            _, vecs = spla.eigsh(lap, k, which="SM")
-            emb = vecs[:, 1:k]
+            if method == "device":
+                emb = self._laplacian_embedding_device()
+                return emb.to(device=self.device, dtype=torch.float32)
+            emb = self._laplacian_embedding_arpack()
         except Exception as exc:  # pylint: disable=broad-exception-caught
             self.logger.warning("Eigendecomposition failed: %s", exc)
             emb = np.random.randn(self.n, self.n_components) * 0.1
         return torch.tensor(emb, device=self.device, dtype=torch.float32)
+
+    _DEVICE_INIT_MIN_N = 20000
+
+    def _laplacian_embedding_arpack(self):
+        import scipy.sparse.linalg as spla
+        from scipy.sparse.csgraph import laplacian
+        sym = sp.csr_matrix(self.adjacency + self.adjacency.transpose())
+        sym.data = np.ones_like(sym.data)
+        lap = laplacian(sym, normed=True)
+        k = self.n_components + 1
+        _, vecs = spla.eigsh(lap, k, which="SM")
+        return vecs[:, 1:k]
+
+    def _laplacian_embedding_device(self, tol=2e-4, max_outer=80, degree=12, return_info=False):
+        """Eigenvectors of M = D^-1/2 A D^-1/2 with the largest eigenvalues (= smallest of L = I - M) by
+        Chebyshev-filtered subspace iteration on a block of 8 vectors; the operator is the library's pull SpMV
+        (gem_spmv_normalized_adjacency) over the symmetric CSR the spring kernel uses, the small dense algebra
+        (thin QR, 8x8 Rayleigh-Ritz) is torch.  Returns the (n, d) tensor of Ritz vectors 2..d+1."""
+        lib, dev = self._lib, self.device
+        m = lib.gem_spmv_cols()
+        k = int(self.n_components) + 1
+        if k > m - 2:
+            raise ValueError("device initial embedding supports n_components <= 5")
+        rows = self._layout.n_pad
+        deg = (self._row_ptr[1:] - self._row_ptr[:-1]).to(torch.float32)
+        dinv = torch.where(deg > 0, deg.clamp_min(1).rsqrt(), torch.zeros_like(deg)).contiguous()
+        live = (deg > 0).to(torch.float32).unsqueeze(1)
+        st = self._stream()
+
+        def spmv(x, alpha=1.0, beta=0.0, z=None, gamma=0.0):
+            y = torch.empty_like(x)
+            _cabi.check(lib.gem_spmv_normalized_adjacency(_ptr(self._row_ptr), _ptr(self._col), _ptr(dinv), _ptr(x), _ptr(y),
+                                                          rows, float(alpha), float(beta), _ptr(z), float(gamma), st),
+                        "gem_spmv_normalized_adjacency")
+            return y
+
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(int(self._sampler_seed) & 0x7FFFFFFF)
+        with torch.cuda.device(dev):
+            x = torch.randn((rows, m), device=dev, dtype=torch.float32, generator=gen) * live
+            x, _ = torch.linalg.qr(x)
+            lower, cut = -1.0, 0.0
+            theta = None
+            info = {"outer": 0, "spmv": 0, "residual": float("inf")}
+            for it in range(max_outer):
+                c, e = 0.5 * (lower + cut), 0.5 * (cut - lower)
+                y0 = x
+                y1 = spmv(x, 1.0 / e, 0.0, None, -c / e)
+                for _ in range(2, degree + 1):
+                    y0, y1 = y1, spmv(y1, 2.0 / e, -1.0, y0, -2.0 * c / e)
+                info["spmv"] += degree
+                x, _ = torch.linalg.qr(y1.contiguous())
+                mx = spmv(x.contiguous())
+                info["spmv"] += 1
+                t = x.T @ mx
+                theta, s = torch.linalg.eigh(0.5 * (t + t.T))           # ascending
+                x = (x @ s).contiguous()
+                mx = mx @ s
+                res = (mx - x * theta.unsqueeze(0)).norm(dim=0)
+                worst = float(res[m - k:].max())                         # the k wanted ones are the last (largest theta)
+                info.update(outer=it + 1, residual=worst)
+                cut = float(theta[0])                                    # damp everything below the block's smallest Ritz value
+                cut = min(max(cut, -0.9), 0.999)
+                if worst < tol:
+                    break
+            order = torch.argsort(theta, descending=True)
+            vecs = x[:, order][:, 1:k]                                   # skip the trivial eigenvector (theta = 1)
+            if self._pad_index is not None:
+                vecs = vecs[self._pad_index]
+            info["theta"] = theta[order][:k].tolist()
+        if self.verbose:
+            self.logger.info("device Laplacian embedding: %d outer iterations, %d SpMV, residual %.2e", info["outer"],
+                             info["spmv"], info["residual"])
+        return (vecs.contiguous(), info) if return_info else vecs.contiguous()
 
     # ------------------------------------------------------------------ buffers / plan
     def _stream(self):

@@ -277,6 +277,17 @@ int gem_layout_step(const gem_plan *plan_host, void *stream);
 #define GEM_NUM_STAGES 10
 int gem_profile_step(const gem_plan *plan_host, void *stream, float *ms_host);
 
+/* SURVEY 8(f).1, initial embedding.  Replaces the operator inside ARPACK's eigsh(L, k, which='SM') of
+ * _compute_laplacian_embedding (embedder_pytorch.py:337-379): the eigenvectors of the normalised
+ * Laplacian L = I - M with the smallest eigenvalues are those of M = D^-1/2 A D^-1/2 with the largest.
+ *   y = alpha * (M x) + beta * z + gamma * x     x, y, z row-major (n, gem_spmv_cols() = 8) fp32, y != x, y != z,
+ * z may be NULL (one pass = one step of the Chebyshev three-term recurrence), pull form over the symmetric CSR
+ * (row_ptr (n+1) int64, col int32), dinv_sqrt[v] = deg(v)^-1/2 (0 for isolated vertices). */
+int gem_spmv_cols(void);
+int gem_spmv_normalized_adjacency(const int64_t *row_ptr, const int32_t *col, const float *dinv_sqrt, const float *x,
+                                  float *y, int64_t n, float alpha, float beta, const float *z, float gamma,
+                                  void *stream);
+
 /* Helpers behind the reference's private, unit-tested methods:
  * gem_pack_points: arbitrary (n,d) row-major points -> midpoint layout, for
  *   _compute_knn_chunked(query, reference, k) / _compute_knn_torch (:426-483, :543-593);

@@ -463,3 +463,41 @@ def test_paths_outside_the_fast_path_limits(S, k):
     assert rel_inf(emb.positions, ref["new_pos"].numpy()) <= TOL
     p = emb.run_layout(3)                               # graph replay of the general path
     assert np.all(np.isfinite(p))
+
+
+# ----------------------------------------------------------------------------- device initial embedding
+def test_device_laplacian_embedding_matches_arpack_subspace():
+    """Chebyshev-filtered subspace iteration with the library's SpMV vs ARPACK on a graph with a clear
+    spectral gap (4 planted communities: eigenvectors 2..4 of the normalised Laplacian are the community
+    indicators).  Eigenvectors are defined up to sign / rotation inside (near-)degenerate eigenspaces, so
+    the comparison is eigenvalues + the subspace (principal angles), as SURVEY 8(f) prescribes."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    import graphem_rapids_b200 as gr
+    n = 8000
+    adj = gr.generate_sbm(n // 4, 4, 0.02, 0.0005, seed=3)
+    emb = gr.GraphEmbedderPyTorch(adj, n_components=3, device="cuda:0", verbose=False, seed=1,
+                                  initial_positions=np.zeros((n, 3), np.float32))
+    vecs, info = emb._laplacian_embedding_device(return_info=True)
+    assert info["residual"] < 2e-4 and vecs.shape == (n, 3)
+    sym = sp.csr_matrix(adj + adj.T)
+    sym.data = np.ones_like(sym.data, dtype=np.float64)
+    dinv = 1.0 / np.sqrt(np.maximum(np.asarray(sym.sum(1)).ravel(), 1.0))
+    M = sp.diags(dinv) @ sym @ sp.diags(dinv)
+    w, v = spla.eigsh(M, 4, which="LA")                    # largest of M == smallest of L = I - M (what the reference asks for)
+    order = np.argsort(-w)
+    w, v = w[order], v[:, order]
+    assert abs(w[0] - 1.0) < 1e-6
+    assert np.allclose(np.array(info["theta"]), w, atol=2e-4)
+    q = vecs.cpu().numpy().astype(np.float64)
+    assert np.allclose(q.T @ q, np.eye(3), atol=1e-3)      # orthonormal
+    sv = np.linalg.svd(v[:, 1:4].T @ q, compute_uv=False)  # cosines of the principal angles
+    assert sv.min() > 0.999, sv
+    # end to end: the constructor path and a layout on top of it
+    e2 = gr.GraphEmbedderPyTorch(adj, n_components=3, device="cuda:0", verbose=False, seed=1, init_method="device")
+    p = e2.run_layout(5)
+    assert p.shape == (n, 3) and np.all(np.isfinite(p))
+    # 'auto' switches to the device solver from 20 000 vertices on
+    big = gr.generate_random_regular(30000, 6, seed=1)
+    e3 = gr.GraphEmbedderPyTorch(big, n_components=2, device="cuda:0", verbose=False, seed=1)
+    assert np.all(np.isfinite(e3.positions)) and abs(np.linalg.norm(e3.positions[:, 0]) - 1.0) < 1e-2
