@@ -112,10 +112,15 @@ def build_layout(edges: np.ndarray, n: int, world: int = 1, hub_degree: int = 12
     row_ptr = np.concatenate([[0], np.cumsum(deg_pad)]).astype(np.int64)
     up_ptr = np.concatenate([[0], np.cumsum(up_pad)]).astype(np.int64)
     if E:
+        # COO -> CSR by scipy's counting sort + per-row index sort (a lexsort of 2E keys took 20 s at E = 5e7)
+        import scipy.sparse as sp
         src = np.concatenate([ep[:, 0], ep[:, 1]])
         dst = np.concatenate([ep[:, 1], ep[:, 0]])
-        order = np.lexsort((dst, src))
-        col = dst[order].astype(np.int32)
+        sym = sp.csr_matrix((np.ones(2 * E, dtype=np.int8), (src, dst)), shape=(n_pad, n_pad))
+        sym.sort_indices()
+        assert sym.nnz == 2 * E, "duplicate edges in the edge list"
+        col = sym.indices.astype(np.int32)
+        assert np.array_equal(sym.indptr.astype(np.int64), row_ptr)
     else:
         col = np.zeros(0, np.int32)
     up_cum = np.concatenate([[0], np.cumsum(up)])

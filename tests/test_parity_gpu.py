@@ -501,3 +501,15 @@ def test_device_laplacian_embedding_matches_arpack_subspace():
     big = gr.generate_random_regular(30000, 6, seed=1)
     e3 = gr.GraphEmbedderPyTorch(big, n_components=2, device="cuda:0", verbose=False, seed=1)
     assert np.all(np.isfinite(e3.positions)) and abs(np.linalg.norm(e3.positions[:, 0]) - 1.0) < 1e-2
+
+
+def test_seed_selection_on_device_matches_reference_formula():
+    """graphem_seed_selection (influence.py:28-37): device top-k of the radial norm == argsort of the host copy."""
+    import graphem_rapids_b200 as gr
+    adj = gr.generate_ba(5000, 3, seed=2)
+    pos0 = np.random.default_rng(2).standard_normal((5000, 3)).astype(np.float32)
+    emb = gr.GraphEmbedderPyTorch(adj, n_components=3, device="cuda:0", verbose=False, seed=3, initial_positions=pos0)
+    seeds = gr.graphem_seed_selection(emb, 25, num_iterations=6)
+    assert isinstance(seeds, list) and len(seeds) == 25 and all(isinstance(v, int) for v in seeds)
+    radial = np.linalg.norm(emb.positions, axis=1)
+    assert seeds == np.argsort(-radial)[:25].tolist()
