@@ -86,6 +86,7 @@ SIGNATURES = {
                                      c_int, c_void_p]),
     "gem_update_normalise_push": (c_int, [POINTER(c_void_p), c_int, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p,
                                           c_void_p, c_void_p]),
+    "gem_remap_indices": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "gem_push_bytes": (c_int, [POINTER(c_void_p), c_int, c_size_t, c_void_p, c_size_t, c_void_p]),
     "gem_layout_step": (c_int, [POINTER(GemPlan), c_void_p]),
     "gem_profile_step": (c_int, [POINTER(GemPlan), c_void_p, POINTER(c_float)]),

@@ -1615,6 +1615,15 @@ __global__ void __launch_bounds__(kThreads) update_pass2_bcast_kernel(PeerPtrs p
     }
 }
 
+// local-order edge numbers -> original edge ids (multi-GPU, strided vertex ownership); -1 padding is kept
+__global__ void remap_indices_kernel(int64_t *__restrict__ idx, int64_t n, const int64_t *__restrict__ table) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const int64_t v = idx[i];
+        if (v >= 0) idx[i] = table[v];
+    }
+}
+
 // copy a small local block into the same offset of every rank's exchange buffer (peer-mapped pointers)
 __global__ void __launch_bounds__(kThreads) push_bytes_kernel(PeerPtrs peers, int world, size_t dst_offset,
                                                               const uint4 *__restrict__ src, size_t n16) {
@@ -2332,6 +2341,14 @@ static int layout_spring(const gem_plan *p, void *st, bool fuse) {
         return spring_csr_launch(p->pos, p->row_ptr, p->col, p->up_ptr, 0, p->n, p->hubs, p->n_hubs, p->d, p->k_attr,
                                  p->l_min, p->force, p->mid, 0, fuse, st);
     return gem_spring_midpoints(p->pos, p->edges, p->n, p->e, p->d, p->k_attr, p->l_min, p->force, p->mid, st);
+}
+
+int gem_remap_indices(int64_t *idx, int64_t n, const int64_t *table, void *stream) {
+    if (!idx || !table || n < 0) return GEM_E_BADARG;
+    if (n == 0) return GEM_OK;
+    remap_indices_kernel<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(idx, n, table);
+    GEM_CHECK_LAUNCH();
+    return GEM_OK;
 }
 
 int gem_push_bytes(void *const *peer_base_host, int world, size_t dst_offset, const void *src, size_t nbytes,

@@ -114,7 +114,8 @@ class GraphEmbedderPyTorch:
         # int32 edge endpoints, symmetric CSR + per-vertex upper-edge offsets for the pull kernels
         self._world, self._rank = self._world_and_rank()
         self._layout = build_layout(np.asarray(edges, dtype=np.int64).reshape(-1, 2), self.n, self._world,
-                                    hub_degree=int(self._lib.gem_hub_degree()))
+                                    hub_degree=int(self._lib.gem_hub_degree()),
+                                    ownership=getattr(self, "_ownership", "strided"))
         L = self._layout
         self._edges32 = torch.from_numpy(L.edges32).to(self.device).contiguous()
         self._row_ptr = torch.from_numpy(L.row_ptr).to(self.device)

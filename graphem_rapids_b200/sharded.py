@@ -183,6 +183,15 @@ class CudaStages:
         self.col = a["col"] if "col" in a else up(layout.col)
         self.up_ptr = a["up_ptr"] if "up_ptr" in a else up(layout.up_ptr)
         self.hubs = up(layout.hubs[rank])
+        # the rank's own edges in the order its spring kernel writes their midpoints (= its KNN candidates)
+        own = layout.local_edge_ids(rank)
+        if layout.edge_orig is None:                                  # monotonic numbering: a slice of the edge list
+            lo = int(layout.e_lo[rank])
+            self.edges32_local = self.edges32[lo: lo + len(own)]
+            self.l2g = None
+        else:
+            self.edges32_local = up(np.ascontiguousarray(layout.edges32[own]))
+            self.l2g = up(np.ascontiguousarray(own))
         self._iter = torch.zeros((1,), device=self.device, dtype=torch.int64)   # device-side iteration counter
         self._knn_ws = None
         self._stats_ws = None
@@ -315,7 +324,8 @@ class CudaStages:
         main = torch.cuda.current_stream(self.device)
         if self.lib.gem_knn_fast_path(e_loc, e_total, self.d, S, kp1):
             # bound / thresholds from (pos, local edges) on the side stream, scan on the main one after the join
-            e32 = self.edges32[e_lo: e_lo + e_loc]
+            e32 = self.edges32_local
+            off = e_lo if self.l2g is None else 0                     # strided ownership: local numbers, mapped below
             _cabi.check(self.lib.gem_knn_prepare(None, _ptr(self._pos_ref), _ptr(e32), e_loc, self.d, _ptr(qmid), S, kp1,
                                                  _ptr(tau_hint), self._bump, _ptr(self._knn_ws), self._knn_ws_bytes,
                                                  self._side_ptr()), "gem_knn_prepare")
@@ -323,9 +333,10 @@ class CudaStages:
             self._join.record(self._side)
             main.wait_event(self._join)
             self._side_stats_pass()
-            _cabi.check(self.lib.gem_knn_scan(_ptr(mid), e_loc, e_lo, self.d, _ptr(qmid), S, kp1, _ptr(out_idx),
+            _cabi.check(self.lib.gem_knn_scan(_ptr(mid), e_loc, off, self.d, _ptr(qmid), S, kp1, _ptr(out_idx),
                                               _ptr(out_dist), _ptr(self._knn_ws), self._knn_ws_bytes, self._s()),
                         "gem_knn_scan")
+            self._remap(out_idx)
             return
         self._join.record(self._side)
         main.wait_event(self._join)
@@ -334,9 +345,18 @@ class CudaStages:
             self._iter.add_(1)                                        # after the join (the fused launch reads it on the side stream)
             self._bump = None
         mm = 1 if (S > 25 or e_total > 25) else 0                     # torch.cdist's rule on the WHOLE problem
-        _cabi.check(self.lib.gem_knn_midpoints_shard(_ptr(mid), e_loc, e_total, e_lo, self.d, _ptr(qmid), S, kp1, mm,
+        off = e_lo if self.l2g is None else 0
+        _cabi.check(self.lib.gem_knn_midpoints_shard(_ptr(mid), e_loc, e_total, off, self.d, _ptr(qmid), S, kp1, mm,
                                                      _ptr(tau_hint), _ptr(out_idx), _ptr(out_dist), _ptr(self._knn_ws),
                                                      self._knn_ws_bytes, self._s()), "gem_knn_midpoints_shard")
+        self._remap(out_idx)
+
+    def _remap(self, out_idx):
+        """local-order edge numbers -> original edge ids (ties in the merge are broken by ORIGINAL index; inside
+        a rank the local order is the original order restricted to its edges, so its own top-(k+1) is unaffected)"""
+        if self.l2g is not None:
+            _cabi.check(self.lib.gem_remap_indices(_ptr(out_idx), out_idx.numel(), _ptr(self.l2g), self._s()),
+                        "gem_remap_indices")
 
     def _side_stats_pass(self):
         """Fused form: column sums of the new positions (pos+F of the owned rows) on the side stream, next to the scan."""
@@ -402,10 +422,11 @@ class ShardedGraphEmbedder(GraphEmbedderPyTorch):
     every iteration with the same replicated positions."""
 
     def __init__(self, adjacency, n_components=2, *args, process_group=None, use_symmetric_memory=True,
-                 use_multicast=False, fused_update=True, **kwargs):
+                 use_multicast=False, fused_update=True, ownership="strided", **kwargs):
         if not dist.is_initialized():
             raise RuntimeError("ShardedGraphEmbedder needs an initialised torch.distributed process group")
         self._group = process_group
+        self._ownership = ownership            # 'strided' (v mod G: balanced for any vertex order) | 'contiguous'
         super().__init__(adjacency, n_components, *args, **kwargs)
         if self.sampler != "device":
             raise NotImplementedError("the multi-GPU path uses the device sampler (identical ids on every rank)")

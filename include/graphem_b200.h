@@ -220,6 +220,11 @@ int gem_update_positions(float *pos, const float *f_spring, const float *f_inter
 int gem_update_normalise_push(float *const *peer_pos_host, int world, const float *src, int64_t row_begin,
                               int64_t n, int64_t n_total, int d, void *stats_ws, const double *rank_sums,
                               void *stream);
+/* idx[i] = table[idx[i]] for idx[i] >= 0 (the -1 padding of short lists is kept): a rank's KNN runs over
+ * its own edges in the order its spring kernel produced their midpoints; with strided vertex ownership
+ * that numbering is not the original one, and the partial lists are mapped back before the merge (which
+ * breaks distance ties by ORIGINAL index). */
+int gem_remap_indices(int64_t *idx, int64_t n, const int64_t *table, void *stream);
 /* Copy nbytes (multiple of 16) from `src` to byte offset dst_offset of EVERY rank's exchange buffer
  * (peer_base_host[r]: peer-mapped base pointers): the all-gather of a small per-rank block (partial
  * top-(k+1) lists, column sums) as P2P stores. */

@@ -27,38 +27,54 @@ def _edges(adj):
 
 
 # ----------------------------------------------------------------------------- partition
+@pytest.mark.parametrize("ownership", ["strided", "contiguous"])
 @pytest.mark.parametrize("world", [1, 2, 3, 8])
 @pytest.mark.parametrize("kind", ["ba", "rr", "er"])
-def test_layout_invariants(world, kind):
+def test_layout_invariants(world, kind, ownership):
     n = 3000
     adj = {"ba": lambda: gen.generate_ba(n, 4, seed=0), "rr": lambda: gen.generate_random_regular(n, 6, seed=0),
            "er": lambda: gen.erdos_renyi_graph(n, 8.0 / n, seed=0)}[kind]()
     e = _edges(adj)
-    L = build_layout(e, n, world, hub_degree=32)
+    L = build_layout(e, n, world, hub_degree=32, ownership=ownership)
     assert L.sorted_edges and L.n_pad == world * L.slice and L.n_edges == len(e)
-    # ranges tile [0, n), every rank non-empty, padded ids monotonic and inside the rank's block
-    assert L.v_lo[0] == 0 and L.v_hi[-1] == n and np.all(L.v_lo[1:] == L.v_hi[:-1]) and np.all(L.v_hi > L.v_lo)
-    assert np.all(np.diff(L.pad_of) > 0)
+    assert int(L.rank_count.sum()) == n and np.all(L.rank_count >= 1)
+    # every vertex has exactly one padded row, inside the valid part of its rank's block
+    assert len(np.unique(L.pad_of)) == n
+    owner = L.pad_of // L.slice
+    assert np.all(L.pad_of - owner * L.slice < L.rank_count[owner])
+    if world == 1 or ownership == "contiguous":
+        assert np.all(np.diff(L.pad_of) > 0) and L.edge_orig is None      # monotonic numbering
+        assert L.v_lo[0] == 0 and L.v_hi[-1] == n and np.all(L.v_lo[1:] == L.v_hi[:-1])
+    else:
+        assert np.array_equal(owner, np.arange(n) % world)                # v mod G
+        assert L.rank_count.max() - L.rank_count.min() <= 1               # balanced rows for ANY vertex order
+        own_edges = L.e_hi - L.e_lo
+        assert own_edges.max() <= 1.35 * own_edges.mean() + 50            # and (statistically) balanced edges
+    deg = np.diff(L.row_ptr)
+    upc = np.diff(L.up_ptr)
     for r in range(world):
         b, t = L.rank_rows(r)
-        assert np.array_equal(L.pad_of[L.v_lo[r]:L.v_hi[r]], np.arange(b, t))
-        # the rank's vertices are exactly the first endpoints of its edge range
-        own = e[L.e_lo[r]:L.e_hi[r], 0]
-        assert own.size == 0 or (own.min() >= L.v_lo[r] and own.max() < L.v_hi[r])
-        # hubs: the rows of the block with degree > threshold
-        deg = np.diff(L.row_ptr)
         assert np.array_equal(L.hubs[r], np.nonzero(deg[b:t] > 32)[0] + b)
+        ids = L.local_edge_ids(r)                                         # the rank owns the edges whose first endpoint it owns
+        assert np.all(L.pad_of[e[ids, 0]] // L.slice == r) and len(ids) == L.e_hi[r] - L.e_lo[r]
+        assert np.all(np.diff(ids) > 0)                                   # local order == original order restricted
     assert L.e_lo[0] == 0 and L.e_hi[-1] == len(e) and np.all(L.e_lo[1:] == L.e_hi[:-1])
-    # edges32 = padded endpoints; CSR rows ascending; w > v entries enumerate the edge list in order
+    all_ids = np.concatenate([L.local_edge_ids(r) for r in range(world)])
+    assert np.array_equal(np.sort(all_ids), np.arange(len(e)))
+    # edges32 = padded endpoints by ORIGINAL edge id; the last up(v) entries of row v are its owned edges, in
+    # edge-list order: enumerating them over the padded rows gives the local-order edge numbering
     assert np.array_equal(L.edges32, L.pad_of[e].astype(np.int32))
-    src = np.repeat(np.arange(L.n_pad), np.diff(L.row_ptr))
     assert len(L.col) == 2 * len(e)
-    up = L.col > src
-    assert np.array_equal(np.column_stack([src[up], L.col[up]]), L.edges32)
-    assert np.array_equal(np.diff(L.up_ptr), np.bincount(L.edges32[:, 0], minlength=L.n_pad))
+    src = np.repeat(np.arange(L.n_pad), deg)
+    tpos = np.arange(len(L.col)) - np.repeat(L.row_ptr[:-1], deg)
+    upper = tpos >= np.repeat(deg - upc, deg)
+    assert np.array_equal(np.column_stack([src[upper], L.col[upper]]), L.edges32[all_ids])
+    assert np.array_equal(upc, np.bincount(L.edges32[:, 0], minlength=L.n_pad))
+    inv = np.full(L.n_pad, -1, np.int64)
+    inv[L.pad_of] = np.arange(n)
     for v in np.random.default_rng(0).integers(0, L.n_pad, 50):
         row = L.col[L.row_ptr[v]:L.row_ptr[v + 1]]
-        assert np.all(np.diff(row) > 0)
+        assert np.all(np.diff(inv[row]) > 0)                              # rows ordered by ORIGINAL neighbour id
     # positions round trip through the padding
     pos = np.random.default_rng(1).standard_normal((n, 3)).astype(np.float32)
     padded = L.pad_positions(pos, 4)
@@ -96,6 +112,8 @@ class OracleStages:
         self.device = torch.device("cpu")
         self.edges = torch.from_numpy(layout.edges32.astype(np.int64))
         self.row_ptr = torch.from_numpy(layout.row_ptr)
+        self.up_ptr = torch.from_numpy(layout.up_ptr)
+        self.edge_orig = None if layout.edge_orig is None else torch.from_numpy(layout.edge_orig)
         self.col = torch.from_numpy(layout.col.astype(np.int64))
 
     def alloc(self, shape, dtype):
@@ -106,20 +124,23 @@ class OracleStages:
         samp.copy_(oracle.draw_sample(n_edges, samp.numel(), g))
 
     def spring(self, pos, vb, ve, force, mid, e_lo):
-        # pull form over the CSR rows [vb, ve): F[v] = sum_w fm*((pos[w]-pos[v])/dist)
+        # pull form over the CSR rows [vb, ve): F[v] = sum_w fm*((pos[w]-pos[v])/dist); the last up(v) entries of a
+        # row are the edges v owns, in edge-list order
         r0, r1 = int(self.row_ptr[vb]), int(self.row_ptr[ve])
         deg = (self.row_ptr[vb + 1: ve + 1] - self.row_ptr[vb:ve])
+        upc = (self.up_ptr[vb + 1: ve + 1] - self.up_ptr[vb:ve])
         src = torch.repeat_interleave(torch.arange(vb, ve), deg)
         dst = self.col[r0:r1]
+        tpos = torch.arange(r1 - r0) - torch.repeat_interleave(self.row_ptr[vb:ve] - r0, deg)
+        up = tpos >= torch.repeat_interleave(deg - upc, deg)
         diff = pos[dst] - pos[src]
         dd = torch.norm(diff, dim=1, keepdim=True) + 1e-6
         term = (-self.k_attr * (dd - self.L_min)) * (diff / dd)
         force.zero_()
         force.index_add_(0, src - vb, term)
-        up = dst > src
         m = (pos[src[up]] + pos[dst[up]]) / 2.0
         mid[: m.shape[0]] = m
-        assert m.shape[0] == mid.shape[0] - 1
+        assert m.shape[0] == mid.shape[0] - 1 and int(self.up_ptr[vb]) == e_lo
 
     def query_mid(self, pos, samp, qmid):
         e = self.edges[samp]
@@ -138,7 +159,8 @@ class OracleStages:
         dd = np.sqrt(d2)
         for q in range(qmid.shape[0]):
             order = np.lexsort((np.arange(e_loc), dd[q]))[:kp1]
-            out_idx[q, : len(order)] = torch.from_numpy(order + e_lo)
+            ids = torch.from_numpy(order + e_lo)                     # local-order numbers -> original edge ids
+            out_idx[q, : len(order)] = ids if self.edge_orig is None else self.edge_orig[ids]
             out_dist[q, : len(order)] = torch.from_numpy(dd[q][order])
 
     def merge(self, g_idx, g_dist, out_idx, out_dist):
@@ -174,14 +196,14 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, kind, n, d, k, S, steps, out):
+def _worker(rank, world, port, kind, n, d, k, S, steps, out, ownership="strided"):
     from graphem_rapids_b200.sharded import ShardedLayoutEngine
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         adj = gen.generate_ba(n, 3, seed=2) if kind == "ba" else gen.generate_random_regular(n, 6, seed=2)
         e = _edges(adj)
-        L = build_layout(e, n, world, hub_degree=16)
+        L = build_layout(e, n, world, hub_degree=16, ownership=ownership)
         st = OracleStages(L, d, seed=5)
         eng = ShardedLayoutEngine(L, rank, st, n_components=d, n_neighbors=k, sample_size=S, inplace_allgather=False)
         pos0 = torch.from_numpy((np.random.default_rng(3).standard_normal((n, d)) * 0.5).astype(np.float32))
@@ -211,14 +233,17 @@ def _worker(rank, world, port, kind, n, d, k, S, steps, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,kind,n,d,k", [(2, "ba", 400, 3, 10), (3, "rr", 400, 2, 5), (2, "rr", 400, 3, 40),
-                                              (3, "rr", 60, 2, 45)])      # last: shards hold fewer than k+1 edges
-def test_sharded_engine_matches_single_process_oracle(world, kind, n, d, k):
+@pytest.mark.parametrize("world,kind,n,d,k,ownership", [
+    (2, "ba", 400, 3, 10, "strided"), (3, "rr", 400, 2, 5, "strided"), (2, "rr", 400, 3, 40, "contiguous"),
+    (3, "rr", 60, 2, 45, "strided"),                  # shards hold fewer than k+1 edges
+    (3, "ba", 401, 3, 10, "strided"), (2, "ba", 400, 3, 10, "contiguous")])
+def test_sharded_engine_matches_single_process_oracle(world, kind, n, d, k, ownership):
     ctx = mp.get_context("spawn")
     out = ctx.SimpleQueue()
     port = _free_port()
     S, steps = 48, 3
-    procs = [ctx.Process(target=_worker, args=(r, world, port, kind, n, d, k, S, steps, out)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, kind, n, d, k, S, steps, out, ownership))
+             for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:

@@ -31,15 +31,17 @@ def _graph(kind, n):
             "sbm": lambda: gr.generate_sbm(n // 4, 4, 8.0 / (n // 4), 2.0 / n, seed=1)}[kind]()
 
 
-@pytest.mark.parametrize("kind,n,d,k,R", [("ba", 30000, 3, 10, 2), ("rr", 20000, 2, 10, 4), ("sbm", 20000, 3, 32, 3),
-                                          ("rr", 64, 3, 20, 8)])       # last: shards shorter than k+1
-def test_virtual_ranks_one_gpu(kind, n, d, k, R):
+@pytest.mark.parametrize("kind,n,d,k,R,ownership", [
+    ("ba", 30000, 3, 10, 2, "strided"), ("rr", 20000, 2, 10, 4, "strided"), ("sbm", 20000, 3, 32, 3, "strided"),
+    ("rr", 64, 3, 20, 8, "strided"),                                   # shards shorter than k+1
+    ("ba", 30000, 3, 10, 3, "contiguous"), ("ba", 30001, 3, 10, 8, "strided")])
+def test_virtual_ranks_one_gpu(kind, n, d, k, R, ownership):
     from graphem_rapids_b200.partition import build_layout
     from graphem_rapids_b200.sharded import CudaStages, ShardedLayoutEngine
     from graphem_rapids_b200 import _cabi
     adj = _graph(kind, n)
     e = oracle.extract_edges(adj).astype(np.int64)
-    L = build_layout(e, n, R, hub_degree=_cabi.load().gem_hub_degree())
+    L = build_layout(e, n, R, hub_degree=_cabi.load().gem_hub_degree(), ownership=ownership)
     dev = torch.device("cuda:0")
     engines = []
     for r in range(R):
@@ -115,7 +117,8 @@ def _nccl_worker(rank, world, port, out):
         print(f'[{rank}] exchange: symmetric memory, multicast={emb._engine.st.multicast} fused={emb._engine.st.fused}', flush=True)
         assert emb._engine.st.fused
         emb2 = ShardedGraphEmbedder(adj, n_components=d, device=dev, n_neighbors=k, sample_size=256, verbose=False,
-                                    seed=4, initial_positions=pos0, use_cuda_graph=False, use_symmetric_memory=False)
+                                    seed=4, initial_positions=pos0, use_cuda_graph=False, use_symmetric_memory=False,
+                                    ownership="contiguous")
         for it in range(3 + 4):
             emb2.update_positions()
         emb.run_layout_device(4)
