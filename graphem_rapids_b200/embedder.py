@@ -122,7 +122,8 @@ class GraphEmbedderPyTorch:
         self._col = torch.from_numpy(L.col).to(self.device)
         self._up_ptr = torch.from_numpy(L.up_ptr).to(self.device)
         self._hubs = torch.from_numpy(L.hubs[self._rank]).to(self.device)
-        self._pad_index = None if L.n_pad == self.n else torch.from_numpy(L.pad_of).to(self.device)
+        identity = L.n_pad == self.n and bool(np.array_equal(L.pad_of, np.arange(self.n)))
+        self._pad_index = None if identity else torch.from_numpy(L.pad_of).to(self.device)
 
         self._has_pykeops = False                               # the PyKeOps branch (:247-258) is removed
         if self.batch_size is None:
