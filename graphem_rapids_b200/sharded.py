@@ -1,18 +1,21 @@
-"""Multi-GPU layout iteration: one process per GPU, vertex-range sharding.
+"""Multi-GPU layout iteration: one process per GPU, vertex sharding.
 
-Every rank holds the replicated positions and graph arrays and OWNS a contiguous vertex range
-(partition.py).  Because the spring stage is vertex-parallel ("pull" over the CSR), a rank
-produces the COMPLETE force of each vertex it owns -- there is no per-vertex force reduction
+Every rank holds the replicated positions and graph arrays and OWNS the vertices v with
+v mod G == rank (partition.py).  Because the spring stage is vertex-parallel ("pull" over the CSR), a
+rank produces the COMPLETE force of each vertex it owns -- there is no per-vertex force reduction
 across ranks -- and the midpoints of the edges whose first endpoint it owns, which are its share
 of the KNN candidates.  Per iteration the ranks exchange only
 
-    1. all-gather of the per-rank partial top-(k+1) lists   (S*(k+1)*12 bytes per rank)
-    2. all-reduce of the 2*ld column sums of the update      (tiny)
-    3. all-gather of the updated position blocks             (4*ld*N bytes in total, in place)
+    1. the per-rank partial top-(k+1) lists        (S*(k+1)*12 bytes per rank)
+    2. the 2*ld column sums of the update          (64 bytes per rank)
+    3. the updated position rows                   (4*ld*N bytes in total)
 
-The orchestration (`ShardedLayoutEngine`) is device-agnostic: it calls a `stages` object for the
-compute and torch.distributed for the exchanges.  The product binds it to the CUDA C ABI
-(`CudaStages`); the CPU tests bind it to the oracle under gloo to check the sharding logic.
+With CUDA stages each exchange is a store phase of the producing kernel into every rank's buffer over
+peer-mapped symmetric memory (NVLink P2P) plus one device-side barrier -- exchange 3 is fused into the
+normalisation kernel; NCCL all-gather / all-reduce is the fallback (and what the CPU tests use under
+gloo).  The orchestration (`ShardedLayoutEngine`) is device-agnostic: it calls a `stages` object for
+the compute.  The product binds it to the CUDA C ABI (`CudaStages`); the CPU tests bind it to the
+oracle to check the sharding logic.
 """
 from __future__ import annotations
 
