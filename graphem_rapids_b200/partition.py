@@ -1,17 +1,23 @@
-"""Host-side graph layout for the CUDA path (numpy only; no torch, no CUDA -- unit-tested on CPU).
+"""Host-side graph layout for the CUDA path (numpy / scipy only; no torch, no CUDA -- unit-tested on CPU).
 
-The device works on a *padded vertex numbering*: with G ranks, rank r owns a contiguous range of
-original vertex ids [v_lo[r], v_hi[r]) and stores it at rows [r*slice, r*slice + len_r) of every
-per-vertex array, `slice` = the longest range.  Rows r*slice + len_r .. (r+1)*slice - 1 are dummies
-(degree 0, position 0, never referenced).  This makes every rank's block the same size, so the
-position all-gather of the multi-GPU iteration is one in-place equal-chunk collective and needs
-no unpacking.  With G = 1 the mapping is the identity and there are no dummies.
+The device works on a *padded vertex numbering*: with G ranks, rank r stores the vertices it owns at
+rows [r*slice, r*slice + count_r) of every per-vertex array, `slice` = the largest count.  Rows
+r*slice + count_r .. (r+1)*slice - 1 are dummies (degree 0, position 0, never referenced).  Every
+rank's block has the same size, so the position exchange of the multi-GPU iteration is one
+equal-chunk store per peer and needs no unpacking.  Two ownership rules (`build_layout`):
+'strided' (default for G > 1; vertex v -> rank v mod G, balanced for any vertex order) and
+'contiguous' (cost-balanced ranges of original ids, monotonic numbering).  With G = 1 the mapping is
+the identity and there are no dummies.
 
-Edge ids are NOT renumbered: the edge list stays in the reference's order
-(embedder_pytorch.py:220-245, nonzero() order of the upper triangle), because edge ids are what
-the sampler draws and what the KNN returns.  The mapping is monotonic, so an (i,j)-sorted edge list
-stays sorted, and rank r's vertices are the first endpoints of the contiguous edge range
-[up_ptr[v_lo[r]], up_ptr[v_hi[r]]).
+Edge ids are NOT renumbered in the public sense: the edge list stays in the reference's order
+(embedder_pytorch.py:220-245, nonzero() order of the upper triangle), because edge ids are what the
+sampler draws and what the KNN returns; `edges32` is indexed by original edge id.  What differs per
+ownership is the order in which a rank's spring kernel PRODUCES the midpoints of the edges it owns
+(rows in padded order, each row its owned edges in edge-list order).  Under contiguous ownership
+that order is the edge-list order itself (rank r owns the contiguous edge range
+[up_ptr[row_begin], up_ptr[row_end])); under strided ownership it is a permutation, recorded in
+`edge_orig` (local-order number -> original edge id) and undone on the device by
+`gem_remap_indices` before ties are broken.
 """
 from __future__ import annotations
 
