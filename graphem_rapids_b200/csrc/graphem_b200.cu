@@ -1750,6 +1750,141 @@ __global__ void __launch_bounds__(kThreads) spmv_norm_adj_kernel(const int64_t *
     }
 }
 
+// ==========================================================================================
+// SURVEY 8(f).2 -- graph arrays on the device: _validate_adjacency + _extract_edges_from_adjacency
+// (embedder_pytorch.py:182-245) take a scipy CSR to the upper-triangular (E,2) edge list in nonzero() order on
+// the host; here a canonical (rows strictly ascending), pattern-symmetric CSR goes to
+//   edges  (E,2) int32  the entries with col > row, in storage order  == the reference's edge list
+//   col    (2E)  int32  the adjacency minus its diagonal             == the symmetric CSR of the pull kernels
+//   row_ptr, up_ptr (n+1) int64  offsets of both
+// in two passes (count + offsets, fill).  `flags` reports what the shortcut "symmetric CSR = adjacency minus
+// diagonal" needs and the input does not satisfy (the host then builds the arrays its general way).
+// ==========================================================================================
+constexpr int kScanItems = 4;
+constexpr int kScanTile = kThreads * kScanItems;
+
+__device__ __forceinline__ int64_t block_scan_inclusive(int64_t v, int64_t *s_warp, int64_t &total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int64_t u = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += u;
+    }
+    if (lane == 31) s_warp[w] = v;
+    __syncthreads();
+    int64_t add = 0, tot = 0;
+#pragma unroll
+    for (int i = 0; i < kWarps; ++i) {
+        const int64_t x = s_warp[i];
+        if (i < w) add += x;
+        tot += x;
+    }
+    __syncthreads();                                       // s_warp may be reused by the caller
+    total = tot;
+    return v + add;
+}
+
+// one thread per row: off-diagonal entries -> row_cnt, entries above the diagonal -> up_cnt; checks
+__global__ void __launch_bounds__(kThreads) graph_count_kernel(const int64_t *__restrict__ indptr,
+                                                               const int32_t *__restrict__ indices, int64_t n,
+                                                               int64_t *__restrict__ row_cnt, int64_t *__restrict__ up_cnt,
+                                                               int32_t *__restrict__ flags) {
+    const int64_t v = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (v >= n) return;
+    const int64_t b = indptr[v], e = indptr[v + 1];
+    int64_t deg = 0, up = 0;
+    int32_t bad = 0;
+    int64_t prev = -1;
+    for (int64_t t = b; t < e; ++t) {
+        const int64_t c = indices[t];
+        if (c <= prev) bad |= GEM_GRAPH_NOT_CANONICAL;     // unsorted row or duplicate entry
+        prev = c;
+        if (c < 0 || c >= n) { bad |= GEM_GRAPH_NOT_CANONICAL; continue; }
+        if (c == v) continue;                              // self loop: rows < cols drops it (:233)
+        ++deg;
+        up += c > v;
+        int64_t lo = indptr[c], hi = indptr[c + 1];        // the mirror entry (c, v)
+        while (lo < hi) {
+            const int64_t m = (lo + hi) >> 1;
+            if (indices[m] < v) lo = m + 1; else hi = m;
+        }
+        if (lo >= indptr[c + 1] || indices[lo] != v) bad |= GEM_GRAPH_NOT_SYMMETRIC;
+    }
+    row_cnt[v] = deg;
+    up_cnt[v] = up;
+    if (bad) atomicOr(flags, bad);
+}
+
+// in-place inclusive scan of a[0..n) for two arrays at once (blockIdx.y), three launches:
+// tile sums -> exclusive scan of the tile sums (one CTA per array) -> scan inside the tiles
+__global__ void __launch_bounds__(kThreads) scan_tile_sums_kernel(const int64_t *__restrict__ a0, const int64_t *__restrict__ a1,
+                                                                  int64_t n, int64_t *__restrict__ tile_sums, int64_t ntiles) {
+    __shared__ int64_t s_warp[kWarps];
+    const int64_t *a = blockIdx.y == 0 ? a0 : a1;
+    const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+    int64_t sum = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i)
+        if (base + i < n) sum += a[base + i];
+    int64_t total;
+    block_scan_inclusive(sum, s_warp, total);
+    if (threadIdx.x == 0) tile_sums[(int64_t)blockIdx.y * ntiles + blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kThreads) scan_tile_offsets_kernel(int64_t *__restrict__ tile_sums, int64_t ntiles) {
+    __shared__ int64_t s_warp[kWarps];
+    int64_t *ts = tile_sums + (int64_t)blockIdx.x * ntiles;
+    int64_t carry = 0;
+    for (int64_t b0 = 0; b0 < ntiles; b0 += kThreads) {
+        const int64_t i = b0 + threadIdx.x;
+        const int64_t v = i < ntiles ? ts[i] : 0;
+        int64_t total;
+        const int64_t incl = block_scan_inclusive(v, s_warp, total);
+        if (i < ntiles) ts[i] = carry + incl - v;          // exclusive
+        carry += total;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) scan_apply_kernel(int64_t *__restrict__ a0, int64_t *__restrict__ a1, int64_t n,
+                                                              const int64_t *__restrict__ tile_sums, int64_t ntiles) {
+    __shared__ int64_t s_warp[kWarps];
+    int64_t *a = blockIdx.y == 0 ? a0 : a1;
+    const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+    int64_t x[kScanItems];
+    int64_t sum = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+        x[i] = base + i < n ? a[base + i] : 0;
+        sum += x[i];
+    }
+    int64_t total;
+    const int64_t incl = block_scan_inclusive(sum, s_warp, total);
+    int64_t run = tile_sums[(int64_t)blockIdx.y * ntiles + blockIdx.x] + incl - sum;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+        run += x[i];
+        if (base + i < n) a[base + i] = run;
+    }
+}
+
+// one thread per row: copy the off-diagonal entries to `col`, emit (row, c) for the entries above the diagonal
+__global__ void __launch_bounds__(kThreads) graph_fill_kernel(const int64_t *__restrict__ indptr,
+                                                              const int32_t *__restrict__ indices, int64_t n,
+                                                              const int64_t *__restrict__ row_ptr,
+                                                              const int64_t *__restrict__ up_ptr, int32_t *__restrict__ col,
+                                                              int2 *__restrict__ edges) {
+    const int64_t v = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (v >= n) return;
+    int64_t o = row_ptr[v], u = up_ptr[v];
+    const int64_t e = indptr[v + 1];
+    for (int64_t t = indptr[v]; t < e; ++t) {
+        const int32_t c = indices[t];
+        if (c == (int32_t)v) continue;
+        col[o++] = c;
+        if (c > (int32_t)v) edges[u++] = make_int2((int32_t)v, c);
+    }
+}
+
 // FP32 FMA peak probe: 8 independent chains per thread
 __global__ void __launch_bounds__(kThreads) fma_probe_kernel(float *out, int iters, float a, float b) {
     float r[8];
@@ -2562,6 +2697,46 @@ int gem_spmv_normalized_adjacency(const int64_t *row_ptr, const int32_t *col, co
     if (((uintptr_t)x & 15) || ((uintptr_t)y & 15) || (z && ((uintptr_t)z & 15))) return GEM_E_BADARG;
     const int grid = grid_for(n * kGrp, 8);
     spmv_norm_adj_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(row_ptr, col, dinv_sqrt, x, y, n, alpha, beta, z, gamma);
+    GEM_CHECK_LAUNCH();
+    return GEM_OK;
+}
+
+int gem_graph_workspace_bytes(int64_t n, size_t *bytes) {
+    if (!bytes || n <= 0) return GEM_E_BADARG;
+    const int64_t ntiles = (n + kScanTile - 1) / kScanTile;
+    *bytes = (size_t)(2 * ntiles) * sizeof(int64_t);
+    return GEM_OK;
+}
+
+int gem_graph_count(const int64_t *indptr, const int32_t *indices, int64_t n, int64_t *row_ptr, int64_t *up_ptr,
+                    int32_t *flags, void *ws, size_t ws_bytes, void *stream) {
+    if (!indptr || !indices || !row_ptr || !up_ptr || !flags || n <= 0 || n >= ((int64_t)1 << 31)) return GEM_E_BADARG;
+    const int64_t ntiles = (n + kScanTile - 1) / kScanTile;
+    if (!ws || ws_bytes < (size_t)(2 * ntiles) * sizeof(int64_t) || ((uintptr_t)ws & 7)) return GEM_E_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    GEM_CUDA(cudaMemsetAsync(flags, 0, sizeof(int32_t), st));
+    GEM_CUDA(cudaMemsetAsync(row_ptr, 0, sizeof(int64_t), st));
+    GEM_CUDA(cudaMemsetAsync(up_ptr, 0, sizeof(int64_t), st));
+    graph_count_kernel<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, st>>>(indptr, indices, n, row_ptr + 1,
+                                                                                       up_ptr + 1, flags);
+    GEM_CHECK_LAUNCH();
+    int64_t *ts = reinterpret_cast<int64_t *>(ws);
+    const dim3 grid((unsigned)ntiles, 2);
+    scan_tile_sums_kernel<<<grid, kThreads, 0, st>>>(row_ptr + 1, up_ptr + 1, n, ts, ntiles);
+    GEM_CHECK_LAUNCH();
+    scan_tile_offsets_kernel<<<2, kThreads, 0, st>>>(ts, ntiles);
+    GEM_CHECK_LAUNCH();
+    scan_apply_kernel<<<grid, kThreads, 0, st>>>(row_ptr + 1, up_ptr + 1, n, ts, ntiles);
+    GEM_CHECK_LAUNCH();
+    return GEM_OK;
+}
+
+int gem_graph_fill(const int64_t *indptr, const int32_t *indices, int64_t n, const int64_t *row_ptr, const int64_t *up_ptr,
+                   int32_t *col, int32_t *edges, void *stream) {
+    if (!indptr || !indices || !row_ptr || !up_ptr || !col || !edges || n <= 0) return GEM_E_BADARG;
+    if ((uintptr_t)edges & 7) return GEM_E_BADARG;
+    graph_fill_kernel<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        indptr, indices, n, row_ptr, up_ptr, col, reinterpret_cast<int2 *>(edges));
     GEM_CHECK_LAUNCH();
     return GEM_OK;
 }

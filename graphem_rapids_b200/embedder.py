@@ -12,7 +12,9 @@ Deliberate differences (DESIGN.md "Boundary"):
     torch.randperm(E)[:S]; `sampler='torch'` restores the reference's call and RNG stream.
   * extra keyword-only arguments: initial_positions, sampler, use_cuda_graph, init_method
     ('auto' | 'arpack' | 'device': the Laplacian initial embedding on the host like the reference, or by
-    a device subspace iteration -- default for graphs of 20 000+ vertices).
+    a device subspace iteration -- default for graphs of 20 000+ vertices), graph_build ('auto' | 'host' |
+    'device': edge list + symmetric CSR extracted from the adjacency by numpy/scipy on the host, or by the
+    library on the device -- default for canonical symmetric adjacencies of 20 000+ vertices).
 """
 from __future__ import annotations
 
@@ -26,7 +28,7 @@ import scipy.sparse as sp
 import torch
 
 from . import _cabi
-from .partition import build_layout
+from .partition import GraphLayout, build_layout
 
 logger = logging.getLogger(__name__)
 
@@ -43,7 +45,8 @@ class GraphEmbedderPyTorch:
     def __init__(self, adjacency, n_components=2, device=None, dtype=torch.float32, L_min=1.0,
                  k_attr=0.2, k_inter=0.5, n_neighbors=10, sample_size=256, batch_size=None,
                  memory_efficient=True, verbose=True, logger_instance=None, seed=None, *,
-                 initial_positions=None, sampler="device", use_cuda_graph=True, init_method="auto"):
+                 initial_positions=None, sampler="device", use_cuda_graph=True, init_method="auto",
+                 graph_build="auto"):
         # seeding contract (embedder_pytorch.py:106-111)
         if seed is not None:
             np.random.seed(seed)
@@ -97,6 +100,9 @@ class GraphEmbedderPyTorch:
         if init_method not in ("auto", "arpack", "device"):
             raise ValueError("init_method must be 'auto', 'arpack' or 'device'")
         self.init_method = init_method
+        if graph_build not in ("auto", "host", "device"):
+            raise ValueError("graph_build must be 'auto', 'host' or 'device'")
+        self.graph_build = graph_build
 
         _cabi.load()
         _cabi.init_device(self.device.index)
@@ -104,26 +110,34 @@ class GraphEmbedderPyTorch:
         self._ld = self._lib.gem_row_pitch(int(n_components))
         self._mld = self._lib.gem_mid_pitch(int(n_components))
 
-        edges = self._extract_edges_from_adjacency(adjacency)
-        self.n_edges = len(edges)
-        self.sample_size = min(sample_size, self.n_edges)       # :156
         if self.n >= 2 ** 31:
             raise ValueError("graphem_rapids_b200 stores edge endpoints as int32: n must be < 2^31")
-        self.edges = torch.tensor(edges, device=self.device, dtype=torch.long).reshape(-1, 2)   # :159
-        # device-side graph arrays (partition.py): padded vertex numbering (identity on one GPU),
-        # int32 edge endpoints, symmetric CSR + per-vertex upper-edge offsets for the pull kernels
+        # device-side graph arrays: padded vertex numbering (identity on one GPU), int32 edge endpoints,
+        # symmetric CSR + per-vertex upper-edge offsets for the pull kernels.  Built by the library on the
+        # device when the adjacency allows it, else by partition.py on the host.
         self._world, self._rank = self._world_and_rank()
-        self._layout = build_layout(np.asarray(edges, dtype=np.int64).reshape(-1, 2), self.n, self._world,
-                                    hub_degree=int(self._lib.gem_hub_degree()),
-                                    ownership=getattr(self, "_ownership", "strided"))
-        L = self._layout
-        self._edges32 = torch.from_numpy(L.edges32).to(self.device).contiguous()
-        self._row_ptr = torch.from_numpy(L.row_ptr).to(self.device)
-        self._col = torch.from_numpy(L.col).to(self.device)
-        self._up_ptr = torch.from_numpy(L.up_ptr).to(self.device)
-        self._hubs = torch.from_numpy(L.hubs[self._rank]).to(self.device)
-        identity = L.n_pad == self.n and bool(np.array_equal(L.pad_of, np.arange(self.n)))
-        self._pad_index = None if identity else torch.from_numpy(L.pad_of).to(self.device)
+        built = self._graph_arrays_device(adjacency)
+        if built is not None:
+            self._layout, self.edges, self._edges32, self._row_ptr, self._col, self._up_ptr, self._hubs = built
+            self.n_edges = int(self._edges32.shape[0])
+            self.sample_size = min(sample_size, self.n_edges)       # :156
+            self._pad_index = None
+        else:
+            edges = self._extract_edges_from_adjacency(adjacency)
+            self.n_edges = len(edges)
+            self.sample_size = min(sample_size, self.n_edges)       # :156
+            self.edges = torch.tensor(edges, device=self.device, dtype=torch.long).reshape(-1, 2)   # :159
+            self._layout = build_layout(np.asarray(edges, dtype=np.int64).reshape(-1, 2), self.n, self._world,
+                                        hub_degree=int(self._lib.gem_hub_degree()),
+                                        ownership=getattr(self, "_ownership", "strided"))
+            L = self._layout
+            self._edges32 = torch.from_numpy(L.edges32).to(self.device).contiguous()
+            self._row_ptr = torch.from_numpy(L.row_ptr).to(self.device)
+            self._col = torch.from_numpy(L.col).to(self.device)
+            self._up_ptr = torch.from_numpy(L.up_ptr).to(self.device)
+            self._hubs = torch.from_numpy(L.hubs[self._rank]).to(self.device)
+            identity = L.n_pad == self.n and bool(np.array_equal(L.pad_of, np.arange(self.n)))
+            self._pad_index = None if identity else torch.from_numpy(L.pad_of).to(self.device)
 
         self._has_pykeops = False                               # the PyKeOps branch (:247-258) is removed
         if self.batch_size is None:
@@ -168,6 +182,71 @@ class GraphEmbedderPyTorch:
         if self.verbose and len(edges) == 0:
             self.logger.warning("No edges found in adjacency matrix")
         return edges
+
+    _DEVICE_GRAPH_MIN_N = 20000
+
+    def _graph_arrays_device(self, adjacency):
+        """Edge list + symmetric CSR built on the device from the CSR adjacency (gem_graph_count /
+        gem_graph_fill; replaces the host work of embedder_pytorch.py:220-245 and partition.build_layout).
+        Returns None when the host path has to be used: several ranks, graph_build='host', a small graph under
+        'auto', or an adjacency that is not canonical (sorted rows, no duplicates, no stored zeros) with a
+        symmetric pattern -- the reference's nonzero() order is then not "entries above the diagonal in storage
+        order", or the symmetric CSR is not the adjacency minus its diagonal.  graph_build='device' raises
+        instead of falling back."""
+        mode = self.graph_build
+        forced = mode == "device"
+
+        def give_up(why):
+            if forced:
+                raise ValueError(f"graph_build='device' is not applicable: {why}")
+            return None
+
+        if mode == "host":
+            return None
+        if self._world != 1:
+            return give_up("the vertex partition of a multi-GPU run is built on the host")
+        if not forced and self.n < self._DEVICE_GRAPH_MIN_N:
+            return None
+        nnz = int(adjacency.nnz)
+        if nnz == 0:
+            return give_up("no stored entries")
+        if not adjacency.has_canonical_format:
+            return give_up("CSR rows are not sorted / contain duplicates")
+        if int(np.count_nonzero(adjacency.data)) != nnz:
+            return give_up("stored zeros (nonzero() drops them)")
+        lib, dev, n = self._lib, self.device, self.n
+        with torch.cuda.device(dev):
+            indptr = torch.from_numpy(np.ascontiguousarray(adjacency.indptr, dtype=np.int64)).to(dev)
+            indices = torch.from_numpy(np.ascontiguousarray(adjacency.indices, dtype=np.int32)).to(dev)
+            row_ptr = torch.empty((n + 1,), device=dev, dtype=torch.long)
+            up_ptr = torch.empty((n + 1,), device=dev, dtype=torch.long)
+            flags = torch.zeros((1,), device=dev, dtype=torch.int32)
+            nbytes = ctypes.c_size_t(0)
+            _cabi.check(lib.gem_graph_workspace_bytes(n, ctypes.byref(nbytes)), "gem_graph_workspace_bytes")
+            ws = torch.empty((nbytes.value // 8 + 1,), device=dev, dtype=torch.long)
+            st = self._stream()
+            _cabi.check(lib.gem_graph_count(_ptr(indptr), _ptr(indices), n, _ptr(row_ptr), _ptr(up_ptr), _ptr(flags),
+                                            _ptr(ws), nbytes.value, st), "gem_graph_count")
+            two_e, n_edges, bad = (int(x) for x in torch.stack([row_ptr[n], up_ptr[n], flags[0].to(torch.long)]).tolist())
+            if bad:
+                return give_up("adjacency pattern is not symmetric" if bad & 1 else "CSR rows are not strictly ascending")
+            if n_edges == 0:
+                return give_up("no edges")
+            if two_e != 2 * n_edges:
+                raise RuntimeError(f"gem_graph_count: inconsistent offsets ({two_e} entries for {n_edges} edges)")
+            col = torch.empty((two_e,), device=dev, dtype=torch.int32)
+            edges32 = torch.empty((n_edges, 2), device=dev, dtype=torch.int32)
+            _cabi.check(lib.gem_graph_fill(_ptr(indptr), _ptr(indices), n, _ptr(row_ptr), _ptr(up_ptr), _ptr(col),
+                                           _ptr(edges32), st), "gem_graph_fill")
+            deg = row_ptr[1:] - row_ptr[:-1]
+            hubs = torch.nonzero(deg > int(lib.gem_hub_degree())).reshape(-1).to(torch.int32)
+            edges64 = edges32.to(torch.long)                        # public attribute (:159)
+        layout = GraphLayout(n=n, n_edges=n_edges, world=1, slice=n, n_pad=n, rank_count=np.array([n], np.int64),
+                             e_lo=np.array([0], np.int64), e_hi=np.array([n_edges], np.int64), pad_of=None,
+                             edges32=None, row_ptr=None, col=None, up_ptr=None, edge_orig=None, hubs=[],
+                             sorted_edges=True, ownership="contiguous", v_lo=np.array([0], np.int64),
+                             v_hi=np.array([n], np.int64), on_device=True)
+        return layout, edges64, edges32, row_ptr, col, up_ptr, hubs
 
     def _check_pykeops_availability(self):
         return False

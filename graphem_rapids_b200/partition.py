@@ -60,6 +60,8 @@ class GraphLayout:
     ownership: str = "contiguous"
     v_lo: Optional[np.ndarray] = None        # contiguous ownership only: original id range per rank
     v_hi: Optional[np.ndarray] = None
+    on_device: bool = False     # single-GPU arrays built by the library on the device (embedder._graph_arrays_device):
+                                # pad_of / edges32 / row_ptr / col / up_ptr are then None here (identity numbering)
 
     def rank_rows(self, r: int):
         """[begin, end) of the rank's VALID rows in padded numbering."""
@@ -73,7 +75,7 @@ class GraphLayout:
 
     def pad_positions(self, pos: np.ndarray, ld: int) -> np.ndarray:
         out = np.zeros((self.n_pad, ld), dtype=np.float32)
-        out[self.pad_of, : pos.shape[1]] = pos
+        out[self.pad_of if self.pad_of is not None else slice(None), : pos.shape[1]] = pos
         return out
 
 

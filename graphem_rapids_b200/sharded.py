@@ -430,6 +430,7 @@ class ShardedGraphEmbedder(GraphEmbedderPyTorch):
             raise RuntimeError("ShardedGraphEmbedder needs an initialised torch.distributed process group")
         self._group = process_group
         self._ownership = ownership            # 'strided' (v mod G: balanced for any vertex order) | 'contiguous'
+        kwargs["graph_build"] = "host"        # the vertex partition (partition.build_layout) is host work
         super().__init__(adjacency, n_components, *args, **kwargs)
         if self.sampler != "device":
             raise NotImplementedError("the multi-GPU path uses the device sampler (identical ids on every rank)")

@@ -293,6 +293,25 @@ int gem_spmv_normalized_adjacency(const int64_t *row_ptr, const int32_t *col, co
                                   float *y, int64_t n, float alpha, float beta, const float *z, float gamma,
                                   void *stream);
 
+/* SURVEY 8(f).2, graph arrays on the device.  Replaces the host work of _validate_adjacency +
+ * _extract_edges_from_adjacency (embedder_pytorch.py:182-245: adjacency.nonzero(), rows < cols, column_stack,
+ * H2D of the int64 list) and the host build of the symmetric CSR of the pull kernels, for an adjacency whose CSR
+ * is canonical (every row strictly ascending: sorted, no duplicates), has no stored zeros (caller's check) and a
+ * symmetric pattern.  Then the reference's edge list is "the entries with col > row in storage order" and the
+ * symmetric CSR is the adjacency minus its diagonal.
+ *   gem_graph_count: row_ptr / up_ptr (n+1, int64) = offsets of the off-diagonal entries / of the entries above
+ *     the diagonal per row (row_ptr[n] = 2E, up_ptr[n] = E); *flags (device int32) = 0 or a combination of
+ *     GEM_GRAPH_* naming the precondition the input violates (the arrays are then not to be used);
+ *     ws: gem_graph_workspace_bytes(n) bytes, 8-byte aligned.
+ *   gem_graph_fill: col (2E int32) and edges (E x 2 int32, 8-byte aligned) from the offsets of gem_graph_count. */
+#define GEM_GRAPH_NOT_SYMMETRIC 1  /* an off-diagonal entry (r, c) has no mirror entry (c, r) */
+#define GEM_GRAPH_NOT_CANONICAL 2  /* a row is not strictly ascending, or a column index is out of range */
+int gem_graph_workspace_bytes(int64_t n, size_t *bytes);
+int gem_graph_count(const int64_t *indptr, const int32_t *indices, int64_t n, int64_t *row_ptr, int64_t *up_ptr,
+                    int32_t *flags, void *ws, size_t ws_bytes, void *stream);
+int gem_graph_fill(const int64_t *indptr, const int32_t *indices, int64_t n, const int64_t *row_ptr,
+                   const int64_t *up_ptr, int32_t *col, int32_t *edges, void *stream);
+
 /* Helpers behind the reference's private, unit-tested methods:
  * gem_pack_points: arbitrary (n,d) row-major points -> midpoint layout, for
  *   _compute_knn_chunked(query, reference, k) / _compute_knn_torch (:426-483, :543-593);

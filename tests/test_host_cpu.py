@@ -72,3 +72,113 @@ def test_fails_loudly_without_cuda():
         gr.create_graphem(adj, n_components=2, backend="cpu")
     with pytest.raises(RuntimeError):
         gr.GraphEmbedderPyTorch(adj, n_components=2, device="cpu", verbose=False)
+
+
+# ----------------------------------------------------------------------------- device graph build, specification
+def _model_graph_count(indptr, indices, n):
+    """numpy model of graph_count_kernel + the three scan launches (tile = 1024) of gem_graph_count."""
+    NOT_SYM, NOT_CANON = 1, 2
+    row_cnt = np.zeros(n, np.int64)
+    up_cnt = np.zeros(n, np.int64)
+    flags = 0
+    for v in range(n):
+        prev = -1
+        for t in range(indptr[v], indptr[v + 1]):
+            c = int(indices[t])
+            if c <= prev:
+                flags |= NOT_CANON
+            prev = c
+            if c < 0 or c >= n:
+                flags |= NOT_CANON
+                continue
+            if c == v:
+                continue
+            row_cnt[v] += 1
+            up_cnt[v] += c > v
+            lo, hi = int(indptr[c]), int(indptr[c + 1])
+            while lo < hi:
+                m = (lo + hi) >> 1
+                if indices[m] < v:
+                    lo = m + 1
+                else:
+                    hi = m
+            if lo >= indptr[c + 1] or indices[lo] != v:
+                flags |= NOT_SYM
+
+    def scan(a, tile=1024, threads=256):
+        nt = (n + tile - 1) // tile
+        sums = np.array([a[i * tile:(i + 1) * tile].sum() for i in range(nt)], np.int64)
+        offs = np.zeros(nt, np.int64)
+        carry = 0
+        for b0 in range(0, nt, threads):                   # scan_tile_offsets_kernel: chunks of 256 with a carry
+            chunk = sums[b0:b0 + threads]
+            incl = np.cumsum(chunk)
+            offs[b0:b0 + threads] = carry + incl - chunk
+            carry += chunk.sum()
+        out = np.empty(n + 1, np.int64)
+        out[0] = 0
+        for i in range(nt):
+            out[1 + i * tile:1 + min(n, (i + 1) * tile)] = offs[i] + np.cumsum(a[i * tile:(i + 1) * tile])
+        return out
+    return scan(row_cnt), scan(up_cnt), flags
+
+
+def _model_graph_fill(indptr, indices, n, row_ptr, up_ptr):
+    col = np.full(int(row_ptr[n]), -1, np.int32)
+    edges = np.full((int(up_ptr[n]), 2), -1, np.int32)
+    for v in range(n):
+        o, u = int(row_ptr[v]), int(up_ptr[v])
+        for t in range(indptr[v], indptr[v + 1]):
+            c = int(indices[t])
+            if c == v:
+                continue
+            col[o] = c
+            o += 1
+            if c > v:
+                edges[u] = (v, c)
+                u += 1
+    return col, edges
+
+
+@pytest.mark.parametrize("name", ["ba", "er_loops", "rr"])
+def test_device_graph_build_specification_equals_host_layout(name):
+    """The two-pass construction the library runs on the device (gem_graph_count / gem_graph_fill), modelled in
+    numpy, produces exactly partition.build_layout's arrays and the reference's edge list for a canonical
+    symmetric adjacency -- with self loops, isolated vertices and non-unit data."""
+    import scipy.sparse as sp
+    from graphem_rapids_b200.partition import build_layout
+    if name == "ba":
+        a = gr.generate_ba(2500, 3, seed=2).tocsr()
+    elif name == "rr":
+        a = gr.generate_random_regular(1025, 4, seed=3).tocsr()
+    else:
+        a = gr.erdos_renyi_graph(1500, 0.002, seed=4).tolil()          # isolated vertices
+        for v in (0, 7, 1499):
+            a[v, v] = 3                                                # self loops: dropped by rows < cols
+        a = a.tocsr().astype(np.float32)
+        a.data *= 2.5
+    a.sort_indices()
+    assert a.has_canonical_format
+    n = a.shape[0]
+    indptr, indices = a.indptr.astype(np.int64), a.indices.astype(np.int32)
+    row_ptr, up_ptr, flags = _model_graph_count(indptr, indices, n)
+    assert flags == 0
+    col, edges = _model_graph_fill(indptr, indices, n, row_ptr, up_ptr)
+    r, c = a.nonzero()
+    keep = r < c
+    ref_edges = np.column_stack([r[keep], c[keep]])
+    L = build_layout(ref_edges, n, 1)
+    assert np.array_equal(edges, ref_edges) and np.array_equal(edges, L.edges32)
+    assert np.array_equal(row_ptr, L.row_ptr) and np.array_equal(up_ptr, L.up_ptr) and np.array_equal(col, L.col)
+
+
+def test_device_graph_build_specification_flags():
+    import scipy.sparse as sp
+    a = sp.triu(gr.generate_random_regular(200, 4, seed=5)).tocsr()   # upper triangle only: pattern not symmetric
+    a.sort_indices()
+    assert _model_graph_count(a.indptr.astype(np.int64), a.indices, 200)[2] == 1
+    b = gr.generate_random_regular(200, 4, seed=5).tocsr()
+    b.sort_indices()
+    idx = b.indices.copy()
+    idx[b.indptr[3]:b.indptr[4]] = idx[b.indptr[3]:b.indptr[4]][::-1]   # one row descending
+    assert _model_graph_count(b.indptr.astype(np.int64), idx, 200)[2] & 2

@@ -513,3 +513,80 @@ def test_seed_selection_on_device_matches_reference_formula():
     assert isinstance(seeds, list) and len(seeds) == 25 and all(isinstance(v, int) for v in seeds)
     radial = np.linalg.norm(emb.positions, axis=1)
     assert seeds == np.argsort(-radial)[:25].tolist()
+
+
+# ----------------------------------------------------------------------------- graph arrays built on the device
+def _graph_case(name):
+    import scipy.sparse as sp
+    import graphem_rapids_b200 as gr
+    if name == "ba30k":                                     # hubs (degree > 128), n spans 30 scan tiles
+        a = gr.generate_ba(30000, 4, seed=11).tocsr()
+    elif name == "rr300k":                                  # > 256 scan tiles: the carry loop of the tile-offset pass
+        a = gr.generate_random_regular(300000, 3, seed=12).tocsr()
+    elif name == "er_loops":                                # isolated vertices, self loops, non-unit float data
+        a = gr.erdos_renyi_graph(5000, 0.0004, seed=13).tolil()
+        for v in (0, 17, 4999):
+            a[v, v] = 2
+        a = a.tocsr().astype(np.float32)
+        a.data *= 0.5
+    else:                                                   # tile-boundary sizes of the scan
+        n = int(name[1:])
+        a = gr.erdos_renyi_graph(n, min(1.0, 6.0 / n), seed=n).tocsr()
+    a.sort_indices()
+    return a
+
+
+@pytest.mark.parametrize("name", ["ba30k", "rr300k", "er_loops", "n2", "n255", "n1024", "n1025", "n4097"])
+def test_device_graph_build_equals_host_layout(name):
+    """gem_graph_count / gem_graph_fill produce exactly the arrays of the host path (the reference's
+    nonzero() edge list, partition.build_layout's symmetric CSR, offsets and hub list)."""
+    import graphem_rapids_b200 as gr
+    adj = _graph_case(name)
+    if adj.nnz == 0:
+        pytest.skip("empty graph drawn")
+    n = adj.shape[0]
+    pos0 = np.random.default_rng(3).standard_normal((n, 3)).astype(np.float32)
+    kw = dict(n_components=3, device="cuda:0", verbose=False, seed=2, initial_positions=pos0)
+    dev = gr.GraphEmbedderPyTorch(adj, graph_build="device", **kw)
+    host = gr.GraphEmbedderPyTorch(adj, graph_build="host", **kw)
+    assert dev._layout.on_device and not host._layout.on_device
+    r, c = adj.nonzero()
+    keep = r < c
+    assert np.array_equal(dev.edges.cpu().numpy(), np.column_stack([r[keep], c[keep]]))     # :220-245
+    assert dev.edges.dtype == torch.long and dev.n_edges == host.n_edges and dev.sample_size == host.sample_size
+    for attr in ("edges", "_edges32", "_row_ptr", "_col", "_up_ptr", "_hubs"):
+        a, b = getattr(dev, attr), getattr(host, attr)
+        assert a.dtype == b.dtype and a.shape == b.shape and torch.equal(a, b), attr
+    if dev.n_edges > 11:
+        dev.run_layout(3)
+        host.run_layout(3)
+        # same arrays, same sample; the intersection forces are accumulated with float atomics, so two runs agree
+        # to rounding, not bitwise
+        assert torch.equal(dev.last_sampled_indices, host.last_sampled_indices)
+        assert rel_inf(dev.positions, host.positions) <= TOL
+
+
+def test_device_graph_build_falls_back_when_not_applicable():
+    import scipy.sparse as sp
+    import graphem_rapids_b200 as gr
+    full = gr.generate_random_regular(25000, 4, seed=21).tocsr()
+    full.sort_indices()
+    pos0 = np.random.default_rng(4).standard_normal((25000, 2)).astype(np.float32)
+    kw = dict(n_components=2, device="cuda:0", verbose=False, seed=2, initial_positions=pos0)
+    upper = sp.triu(full).tocsr()                           # valid input for the reference (rows < cols), not symmetric
+    upper.sort_indices()
+    with pytest.raises(ValueError, match="symmetric"):
+        gr.GraphEmbedderPyTorch(upper, graph_build="device", **kw)
+    auto = gr.GraphEmbedderPyTorch(upper, **kw)             # 'auto': detected on the device, built on the host
+    ref = gr.GraphEmbedderPyTorch(full, **kw)               # 'auto': built on the device
+    assert not auto._layout.on_device and ref._layout.on_device
+    assert torch.equal(auto.edges, ref.edges) and torch.equal(auto._col, ref._col) and torch.equal(auto._row_ptr, ref._row_ptr)
+    zeros = full.copy().astype(np.float32)
+    zeros.data[5] = 0.0                                     # a stored zero: nonzero() drops that entry
+    z = gr.GraphEmbedderPyTorch(zeros, **kw)
+    assert not z._layout.on_device and z.n_edges in (ref.n_edges, ref.n_edges - 1)
+    with pytest.raises(ValueError, match="stored zeros"):
+        gr.GraphEmbedderPyTorch(zeros, graph_build="device", **kw)
+    small = gr.GraphEmbedderPyTorch(gr.generate_random_regular(500, 4, seed=1), n_components=2, device="cuda:0",
+                                    verbose=False, seed=2)
+    assert not small._layout.on_device                      # 'auto' keeps small graphs on the host path
