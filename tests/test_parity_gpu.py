@@ -465,6 +465,25 @@ def test_paths_outside_the_fast_path_limits(S, k):
     assert np.all(np.isfinite(p))
 
 
+def test_full_knn_regime_sample_size_equals_E():
+    """sample_size >= E makes every edge a query (arange(E), embedder_pytorch.py:412): 24 batches of
+    1024 queries through the filter + re-check scan, S*k = 240 K candidate pairs in the intersection stage."""
+    import graphem_rapids_b200 as gr
+    n = 6000
+    adj = gr.generate_random_regular(n, 8, seed=8)
+    pos0 = np.random.default_rng(8).standard_normal((n, 2)).astype(np.float32)
+    emb = gr.GraphEmbedderPyTorch(adj, n_components=2, device="cuda:0", n_neighbors=10, sample_size=10 ** 9,
+                                  verbose=False, seed=2, initial_positions=pos0)
+    E = emb.n_edges
+    assert emb.sample_size == E                                        # :156
+    emb.update_positions()
+    assert torch.equal(emb.last_sampled_indices.cpu(), torch.arange(E))
+    ref = oracle.layout_step(torch.from_numpy(pos0), emb.edges.cpu(), torch.arange(E), n_neighbors=10, strict=True)
+    assert torch.equal(emb._bufs["knn_idx"].cpu(), ref["knn_full"])
+    assert torch.equal(emb._bufs["knn_dist"].cpu(), ref["knn_dist"])
+    assert rel_inf(emb.positions, ref["new_pos"].numpy()) <= TOL
+
+
 # ----------------------------------------------------------------------------- SURVEY 8(f).1: device initial embedding
 def test_device_laplacian_embedding_matches_arpack_subspace():
     """Chebyshev-filtered subspace iteration with the library's SpMV vs ARPACK on a graph with a clear
