@@ -13,12 +13,13 @@ device the embedder raises.
 """
 from .embedder import GraphEmbedderPyTorch, create_graphem
 from .influence import graphem_seed_selection
+from .correlation import radial_correlations
 from . import generators
 from .generators import (erdos_renyi_graph, generate_ba, generate_random_regular, generate_sbm)
 
 __version__ = "0.1.0"
 
 __all__ = [
-    "GraphEmbedderPyTorch", "create_graphem", "graphem_seed_selection", "generators",
+    "GraphEmbedderPyTorch", "create_graphem", "graphem_seed_selection", "radial_correlations", "generators",
     "erdos_renyi_graph", "generate_ba", "generate_random_regular", "generate_sbm",
 ]

@@ -182,3 +182,38 @@ def test_device_graph_build_specification_flags():
     idx = b.indices.copy()
     idx[b.indptr[3]:b.indptr[4]] = idx[b.indptr[3]:b.indptr[4]][::-1]   # one row descending
     assert _model_graph_count(b.indptr.astype(np.int64), idx, 200)[2] & 2
+
+
+# ----------------------------------------------------------------------------- correlation harness (torch part)
+def test_rank_average_and_spearman_match_scipy():
+    from scipy.stats import rankdata, spearmanr
+    from graphem_rapids_b200.correlation import rank_average, spearman
+    rng = np.random.default_rng(0)
+    for n, levels in ((1, 1), (7, 3), (1000, 12), (5000, 100000)):
+        a = rng.integers(0, levels, n).astype(np.float32)                  # heavy ties (degree-like)
+        b = (a + rng.standard_normal(n) * 2).astype(np.float32)
+        assert np.array_equal(rank_average(torch.from_numpy(a)).numpy(), rankdata(a, method="average"))
+        if n > 1 and levels > 1:
+            assert abs(spearman(torch.from_numpy(a), torch.from_numpy(b)) - spearmanr(a, b).correlation) < 1e-12
+    assert np.isnan(spearman(torch.zeros(5), torch.arange(5.0)))
+    assert rank_average(torch.empty(0)).numel() == 0
+
+
+def test_pagerank_power_iteration_matches_networkx():
+    """The iteration pagerank_device runs (with the normalised-adjacency operator supplied by scipy here, by the
+    CUDA library on the device) reproduces networkx.pagerank, dangling (isolated) vertices included."""
+    import networkx as nx
+    import scipy.sparse as sp
+    from graphem_rapids_b200.correlation import _pagerank_power_iteration
+    a = gr.generate_ba(800, 3, seed=3).tolil()
+    a.resize((803, 803))                                                    # three isolated vertices
+    a = a.tocsr().astype(np.float64)
+    deg = np.asarray(a.sum(1)).ravel()
+    dinv = np.where(deg > 0, 1.0 / np.sqrt(np.maximum(deg, 1)), 0.0)
+    m = sp.diags(dinv) @ a @ sp.diags(dinv)
+    pr = _pagerank_power_iteration(torch.from_numpy(deg), lambda z: torch.from_numpy((m @ z.numpy().astype(np.float64))
+                                                                                     .astype(np.float32)),
+                                   0.85, 1e-8, 200).numpy()
+    ref = nx.pagerank(nx.from_scipy_sparse_array(a), alpha=0.85, tol=1e-10, max_iter=500)
+    ref = np.array([ref[i] for i in range(803)])
+    assert abs(pr.sum() - 1) < 1e-5 and np.abs(pr - ref).max() / ref.max() < 1e-4

@@ -609,3 +609,27 @@ def test_device_graph_build_falls_back_when_not_applicable():
     small = gr.GraphEmbedderPyTorch(gr.generate_random_regular(500, 4, seed=1), n_components=2, device="cuda:0",
                                     verbose=False, seed=2)
     assert not small._layout.on_device                      # 'auto' keeps small graphs on the host path
+
+
+# ----------------------------------------------------------------------------- radial correlations on the device
+def test_radial_correlations_on_device_match_scipy_and_networkx():
+    import networkx as nx
+    from scipy.stats import spearmanr
+    import graphem_rapids_b200 as gr
+    from graphem_rapids_b200.correlation import pagerank_device
+    n = 4000
+    adj = gr.generate_ba(n, 3, seed=5).tolil()
+    adj.resize((n + 2, n + 2))                              # two isolated (dangling) vertices
+    adj = adj.tocsr()
+    emb = gr.GraphEmbedderPyTorch(adj, n_components=3, device="cuda:0", verbose=False, seed=3)
+    emb.run_layout(20)
+    pr = pagerank_device(emb, tol=1e-8, max_iter=200).cpu().numpy()
+    ref = nx.pagerank(nx.from_scipy_sparse_array(adj), alpha=0.85, tol=1e-10, max_iter=500)
+    ref = np.array([ref[i] for i in range(n + 2)])
+    assert np.abs(pr - ref).max() / ref.max() < 1e-4
+    out = gr.radial_correlations(emb, measures={"pagerank_networkx": ref})
+    r = np.linalg.norm(emb.get_positions(), axis=1)
+    deg = np.asarray(adj.sum(1)).ravel()
+    assert abs(out["degree"] - spearmanr(r, deg).correlation) < 1e-6
+    assert abs(out["pagerank_networkx"] - spearmanr(r, ref).correlation) < 1e-6
+    assert abs(out["pagerank"] - out["pagerank_networkx"]) < 5e-3
