@@ -12,8 +12,11 @@ graph is edge-sharded across the ranks, so scaling is "strong").  Rank 0 prints 
 
 Timing: W >= 3 warm-up steps; every timed step is bracketed by its own pair of CUDA events on
 the launching stream and preceded by an (untimed) L2 flush (a 512 MiB buffer write); the K step
-durations are summed, max over ranks.  `e2e` times the public API with host buffers: pinned
-host->device upload of the positions, update_positions(), device->host read of the result.
+durations are summed, max over ranks.  `sustained` repeats the measurement as >= 2 s of back-to-back
+replays (clocks recorded).  `e2e` times the drop-in API with host buffers: `emb.positions = x`
+(pinned host tensor -> device), `emb.run_layout(1)`, which returns the result as a fresh ndarray; on
+N > 1 GPUs every rank moves its 1/N of the rows (load_positions_chunk / read_positions_chunk).
+N > 1 lines carry `parity` (sharded state vs a single-GPU embedder on rank 0) and `phase_us`.
 """
 import argparse
 import json
@@ -31,8 +34,19 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 METRIC = "layout iters/sec & edge-updates/s, 1M-vertex BA graph, 1/2/4/8 B200 vs host CPU"
-# DRAM traffic of one knn_scan_kernel launch from the committed ncu capture (profiles/), bytes
-SCAN_DRAM_BYTES_NCU = {"c3": 64070400 + 451072}
+
+
+def scan_traffic_from_profiles(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE knn_scan_kernel launch, from this round's `ncu --set full`
+    capture of the same build (profiles/r02_scan_traffic.json, written by scripts/ncu_summary.py); None when no
+    capture of this build/workload is committed -- a stale constant is worse than null."""
+    path = os.path.join(ROOT, "profiles", "r02_scan_traffic.json")
+    try:
+        with open(path) as f:
+            rec = json.load(f)
+        return rec.get(workload)
+    except Exception:
+        return None
 
 WORKLOADS = {
     # BASELINE.json configs[2] -- the headline
@@ -166,29 +180,94 @@ def measured_peaks():
 
 
 # ----------------------------------------------------------------------------------------------
+# graph cache: generate once per box (rank 0), every other rank loads the CSR arrays
+# ----------------------------------------------------------------------------------------------
+def load_graph(w, key, world, rank, barrier):
+    import scipy.sparse as sp
+    path = os.path.join(os.environ.get("GEM_GRAPH_CACHE", "/tmp"), f"gem_graph_{key}.npz")
+    if world == 1:
+        return make_graph(w)
+    if rank == 0:
+        adj = make_graph(w)
+        tmp = path + ".tmp.npz"
+        np.savez(tmp, indptr=adj.indptr, indices=adj.indices, n=np.int64(adj.shape[0]))
+        os.replace(tmp, path)
+    barrier()
+    if rank != 0:
+        with np.load(path) as z:
+            n = int(z["n"])
+            indices, indptr = z["indices"], z["indptr"]
+        adj = sp.csr_matrix((np.ones(len(indices), dtype=np.int64), indices, indptr), shape=(n, n))
+        adj.has_sorted_indices = True
+    barrier()
+    if rank == 0:
+        try:
+            os.remove(path)
+        except OSError:
+            pass
+    return adj
+
+
+def workload_config(w, n, E):
+    """The `config` object: identical in both arms (it names the workload, not the implementation)."""
+    return {"workload": w["desc"], "N": int(n), "E": int(E), "n_components": w["d"], "sample_size": int(min(w["S"], E)),
+            "n_neighbors": w["k"], "init": "randn*0.1 default_rng(0)",
+            "graph": "graphem_rapids_b200.generators (numpy, seed 0): same degree law as the reference's networkx generator, "
+                     "not its random stream (E differs slightly from the reference's own graph of that name)",
+            "l2": "GPU arm: flushed before every timed step (512 MiB write, untimed); CPU arm: not applicable"}
+
+
+# ----------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the oracle port (torch CPU restatement of the reference) timed on
 # the host cores.  The ONLY place besides tests/ and smoke() that executes oracle/.
 # ----------------------------------------------------------------------------------------------
-def cpu_reference_timing(adj, w, steps, warmup, chunk=32):
+def cpu_reference_timing(adj, w, steps, warmup, chunk=32, with_gc=False, budget_s=150.0):
+    """K timed iterations of the reference algorithm (oracle/oracle.py: the literal cdist + topk restatement) on all
+    host cores.  with_gc: additionally the 4 gc.collect() per iteration that the reference's MemoryManager /
+    cleanup_gpu_memory execute (utils/memory_management.py:117-128) -- the as-shipped-equivalent figure.
+    When K full iterations would not fit `budget_s`, every step runs the KNN on the first S' of the S queries and
+    its KNN time is scaled by S/S' (said in `sample`)."""
+    import gc
     from oracle import oracle
     torch.set_num_threads(os.cpu_count() or 1)
     edges = torch.from_numpy(oracle.extract_edges(adj).astype(np.int64))
     E = edges.shape[0]
+    S = min(w["S"], E)
     pos = torch.from_numpy(initial_positions(adj.shape[0], w["d"]))
     gen = torch.Generator().manual_seed(0)
-    times = []
-    for it in range(warmup + steps):
-        samp = oracle.draw_sample(E, w["S"], gen)
+
+    def one(pos, s_used):
+        samp = oracle.draw_sample(E, S, gen)[:s_used]
         t0 = time.perf_counter()
-        pos = oracle.layout_step(pos, edges, samp, n_neighbors=w["k"], strict=False, chunk_size=chunk)["new_pos"]
-        dt = time.perf_counter() - t0
-        if it >= warmup:
-            times.append(dt)
+        if with_gc:
+            gc.collect()                       # spring stage exit (:616 via MemoryManager)
+        out = oracle.layout_step(pos, edges, samp, n_neighbors=w["k"], strict=False, chunk_size=chunk)
+        if with_gc:
+            gc.collect(); gc.collect(); gc.collect()      # knn / intersection / update stage exits
+        return out["new_pos"], time.perf_counter() - t0
+
+    pos, t1 = one(pos, S)                      # first warm-up step doubles as the cost probe
+    s_used = S
+    if t1 * (steps + warmup) > budget_s and S > 8:
+        s_used = max(8, int(S * budget_s / (t1 * (steps + warmup))))
+    for _ in range(max(warmup - 1, 0)):
+        pos, _ = one(pos, s_used)
+    times = []
+    for _ in range(steps):
+        pos, dt = one(pos, s_used)
+        times.append(dt)
     sec = float(np.mean(times))
-    return dict(E=int(E), sec_per_step=sec, cores=torch.get_num_threads(),
-                sample=f"{steps} full iterations of the workload (E={E}) after {warmup} warm-up, literal cdist+topk "
-                       f"restatement (oracle/oracle.py, strict=False), query chunk {chunk}, gc.collect/MemoryManager "
-                       f"of the reference omitted")
+    sample = (f"{steps} full iterations of the workload (E={E}) after {warmup} warm-up")
+    if s_used < S:
+        # the KNN dominates: scale the step to the full query count (conservative for the CPU: the non-KNN part is
+        # scaled too)
+        sec = sec * S / s_used
+        sample = (f"{steps} iterations with the KNN on the first {s_used} of {S} queries, step time scaled by "
+                  f"{S}/{s_used} (a full iteration takes {t1:.1f} s), after {warmup} warm-up")
+    sample += (f"; literal cdist+topk restatement (oracle/oracle.py, strict=False), query chunk {chunk}; "
+               + ("with the reference's 4 gc.collect() per iteration (MemoryManager, utils/memory_management.py:117-128)"
+                  if with_gc else "gc.collect/MemoryManager of the reference omitted (the maths only)"))
+    return dict(E=int(E), sec_per_step=sec, cores=torch.get_num_threads(), sample=sample)
 
 
 def run_reference(args, w):
@@ -196,8 +275,7 @@ def run_reference(args, w):
     if rank != 0:
         return
     adj = make_graph(w)
-    steps = max(1, min(args.steps, 3))
-    warm = 1
+    steps, warm = max(1, args.steps), max(1, args.warmup)
     r = cpu_reference_timing(adj, w, steps, warm)
     val = r["E"] / r["sec_per_step"]
     line = {
@@ -205,7 +283,8 @@ def run_reference(args, w):
         "steps": steps, "warmup": warm, "ms_per_step": r["sec_per_step"] * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "iters_per_s": 1.0 / r["sec_per_step"],
-        "config": {"workload": w["desc"], "E": r["E"], "note": "reference algorithm on host CPU cores (oracle port)"},
+        "config": workload_config(w, adj.shape[0], r["E"]),
+        "details": {"note": "reference algorithm on host CPU cores (oracle port)"},
         "cpu_baseline": {"value": val, "unit": "edge-updates/s", "cores": r["cores"], "kind": "port",
                          "sample": r["sample"]},
         "e2e": {"value": val, "unit": "edge-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -216,6 +295,13 @@ def run_reference(args, w):
 # ----------------------------------------------------------------------------------------------
 # B200 arm
 # ----------------------------------------------------------------------------------------------
+def rel_inf(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    den = np.abs(b).max()
+    return float(np.abs(a - b).max() / (den if den > 0 else 1.0))
+
+
 def run_b200(args, w):
     import torch.distributed as dist
     import graphem_rapids_b200 as gr
@@ -228,16 +314,26 @@ def run_b200(args, w):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    adj = make_graph(w)
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    t_setup0 = time.perf_counter()
+    adj = load_graph(w, f"{args.workload}_{os.environ.get('MASTER_PORT', '0')}", world, rank, barrier)
+    t_graph = time.perf_counter() - t_setup0
     n, d = adj.shape[0], w["d"]
     pos0 = initial_positions(n, d)
+    kw = dict(n_components=d, device=dev, n_neighbors=w["k"], sample_size=w["S"], verbose=False, seed=0,
+              initial_positions=pos0, sampler=args.sampler)
+    t_c0 = time.perf_counter()
     if world > 1:
         from graphem_rapids_b200.sharded import ShardedGraphEmbedder
-        emb = ShardedGraphEmbedder(adj, n_components=d, device=dev, n_neighbors=w["k"], sample_size=w["S"],
-                                   verbose=False, seed=0, initial_positions=pos0)
+        emb = ShardedGraphEmbedder(adj, **kw)
     else:
-        emb = gr.GraphEmbedderPyTorch(adj, n_components=d, device=dev, n_neighbors=w["k"], sample_size=w["S"],
-                                      verbose=False, seed=0, initial_positions=pos0)
+        emb = gr.GraphEmbedderPyTorch(adj, **kw)
+    torch.cuda.synchronize(dev)
+    t_construct = time.perf_counter() - t_c0
     E = emb.n_edges
     # one-off graph set-up (untimed by the metric; reported): the object was built above with CUDA already
     # initialised, so a second construction measures the set-up itself -- device build vs host build
@@ -247,24 +343,19 @@ def run_b200(args, w):
         for mode in ("auto", "host"):
             torch.cuda.synchronize(dev)
             t0 = time.perf_counter()
-            tmp = gr.GraphEmbedderPyTorch(adj, n_components=d, device=dev, n_neighbors=w["k"], sample_size=w["S"],
-                                          verbose=False, seed=0, initial_positions=pos0, graph_build=mode)
+            tmp = gr.GraphEmbedderPyTorch(adj, graph_build=mode, **kw)
             torch.cuda.synchronize(dev)
             setup[f"{mode}_s"] = round(time.perf_counter() - t0, 4)
             setup[f"{mode}_on_device"] = bool(tmp._layout.on_device)
+            tmp.close()
             del tmp
 
     flush_buf = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
     K, W = args.steps, max(args.warmup, 3)
     # warm-up: W iterations through the production path (run_layout's CUDA-graph replay; the graph of one
-    # iteration -- both streams and, for N > 1, the NCCL collectives -- is captured here, untimed)
-    emb.run_layout_device(W)
+    # iteration -- both streams and, for N > 1, the peer stores and device barriers -- is captured here, untimed)
+    emb.run_layout_device(W + (W & 1))      # even count: both buffer parities of the sharded flow are captured
     barrier()
 
     def one_step():
@@ -290,40 +381,107 @@ def run_b200(args, w):
     total_ms = float(np.sum(step_ms))
     clk = clocks.stop() if rank == 0 else None
 
-    # ---- back-to-back (no flush between iterations), for context
+    # ---- sustained: >= 2 s of back-to-back replays (no flush: every array of the step is larger than it can keep
+    # in L2 across an iteration only at C4/C5; said in the line), clocks sampled over the whole region
+    sus_iters = int(min(max(2.2e3 / max(total_ms / K, 1e-3), K), 200000))
+    sus_iters += sus_iters & 1
+    clocks2 = ClockSampler(local_rank)
     barrier()
+    if rank == 0:
+        clocks2.start()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    emb.run_layout_device(K)
+    emb.run_layout_device(sus_iters)
     b.record()
     barrier()
-    b2b_ms = a.elapsed_time(b) / K
+    sus_ms = a.elapsed_time(b) / sus_iters
+    clk2 = clocks2.stop() if rank == 0 else None
 
     # ---- end to end through the public API with HOST buffers
-    host_in = torch.from_numpy(emb.positions).pin_memory()
-    host_out = torch.empty_like(host_in).pin_memory()
-    nbytes = host_in.numel() * 4
+    sharded_io = world > 1 and emb.exchange == "p2p"
     Ke = max(3, min(K, 10))
-    emb.load_positions(host_in)                # untimed: first-use allocations of the staging buffers
-    one_step()
-    emb.read_positions(host_out)
+    if sharded_io:
+        lo, hi = emb.chunk_rows()
+        cur = emb.positions
+        host_in = torch.from_numpy(np.ascontiguousarray(cur[lo:hi])).pin_memory()
+        host_out = torch.empty_like(host_in).pin_memory()
+        h2d = d2h = int(n * d * 4)             # whole job: the ranks' chunks add up to the full array
+
+        def e2e_step():
+            emb.load_positions_chunk(host_in)  # H2D of the rank's rows + NVLink fan-out (collective)
+            one_step()
+            emb.read_positions_chunk(host_out) # D2H of the rank's rows + stream sync
+        api = ("every rank: load_positions_chunk(pinned rows of its 1/N) -> run_layout_device(1) [replay of the captured "
+               "iteration] -> read_positions_chunk(pinned)")
+    else:
+        host_in = torch.from_numpy(emb.positions).pin_memory()
+        h2d = d2h = int(n * d * 4)
+        state = {"x": host_in}
+
+        def e2e_step():
+            emb.positions = state["x"]         # the reference's setter (embedder_pytorch.py:329-335), pinned source
+            out = emb.run_layout(1)            # the reference's driver (:808-833): returns a FRESH ndarray
+            state["out"] = out
+        api = ("emb.positions = pinned host tensor -> emb.run_layout(1) -> fresh ndarray (the reference's own setter / "
+               "driver / return convention)")
+    e2e_step()                                 # untimed: first-use allocations of the staging buffers
     barrier()
     ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_e0 = time.perf_counter()
     ea.record()
     for _ in range(Ke):
-        emb.load_positions(host_in)            # H2D from pinned memory (positions setter semantics)
-        one_step()
-        emb.read_positions(host_out)           # D2H of the step's result + stream sync
-        host_in, host_out = host_out, host_in
+        e2e_step()
     eb.record()
+    torch.cuda.synchronize(dev)
+    e2e_wall_ms = (time.perf_counter() - t_e0) * 1e3 / Ke
     barrier()
-    e2e_ms = ea.elapsed_time(eb) / Ke
+    e2e_ms = max(ea.elapsed_time(eb) / Ke, e2e_wall_ms)     # host-side copies after the last event count too
+
+    # ---- N > 1: parity of the sharded state against a single-GPU embedder on rank 0 (same seed, same device
+    # counter => same samples), from the current positions, over T more iterations
+    parity = None
+    phase_us = None
+    if world > 1:
+        T = 3
+        cur = emb.positions
+        if rank == 0:
+            ref_emb = gr.GraphEmbedderPyTorch(adj, **dict(kw, initial_positions=cur))
+            if args.sampler == "device":
+                ref_emb._buffers()["iter"].copy_(emb._engine.st._iter)
+        emb.run_layout_device(T + (T & 1))
+        torch.cuda.synchronize(dev)
+        mine = emb._pos.clone()
+        dist.broadcast(mine, src=0)
+        same = torch.tensor([1 if torch.equal(mine, emb._pos) else 0], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            if args.sampler == "device":
+                ref_emb.run_layout_device(T + (T & 1))
+                torch.cuda.synchronize(dev)
+                parity = {"iterations": T + (T & 1),
+                          "vs": "single-GPU GraphEmbedderPyTorch on rank 0 from the same positions, seed and iteration counter",
+                          "samples_equal": bool(torch.equal(ref_emb.last_sampled_indices, emb.last_sampled_indices)),
+                          "knn_lists_equal": bool(torch.equal(ref_emb._bufs["knn_idx"], emb._engine.knn_idx)),
+                          "pos_rel_inf": rel_inf(emb.positions, ref_emb.positions),
+                          "replicas_bit_identical": bool(int(same.item()))}
+                parity["ok"] = bool(parity["samples_equal"] and parity["knn_lists_equal"] and parity["replicas_bit_identical"]
+                                    and parity["pos_rel_inf"] <= 1e-5 * parity["iterations"])
+            else:
+                parity = {"replicas_bit_identical": bool(int(same.item())), "ok": bool(int(same.item())),
+                          "vs": "replica comparison only (sampler='torch' streams differ between two objects in one process)"}
+            ref_emb.close()
+        if emb.exchange == "p2p":
+            ph = emb.profile_phases(20)
+            t = torch.tensor([ph[k] for k in emb.PHASES], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            phase_us = {"end_of_phase_us_since_step_start_max_over_ranks": dict(zip(emb.PHASES, [round(float(x), 1) for x in t.tolist()])),
+                        "note": "external CUDA events inside the captured iteration; prep and colsum run on the side stream"}
 
     # max over ranks
     if world > 1:
-        t = torch.tensor([total_ms, b2b_ms, e2e_ms], device=dev, dtype=torch.float64)
+        t = torch.tensor([total_ms, sus_ms, e2e_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, b2b_ms, e2e_ms = [float(x) for x in t.tolist()]
+        total_ms, sus_ms, e2e_ms = [float(x) for x in t.tolist()]
 
     # ---- per-kernel roofline (rank 0, single GPU), measured live with CUDA events: gem_profile_step runs the
     # same launches in series on one stream with an event after every stage (in the timed steps above the
@@ -345,18 +503,21 @@ def run_b200(args, w):
         batched = S > 1024            # general path (KNN in batches of 1024 queries): no per-stage events inside the KNN
         scan_s = (total_ms / K if batched else stage["knn_scan"]) * 1e-3
         executed = 2.0 * d * S * E                           # what the filter executes: d FMA per pair
+        traffic = scan_traffic_from_profiles(args.workload)
         roof = {"kernel": "knn_scan_kernel" if not batched else
                 "knn_scan_kernel (batched full-KNN regime: the WHOLE iteration time is used as its duration -- a lower "
                 "bound of its rate)", "bound": "fp32", "achieved": flops / scan_s / 1e12,
                 "peak": fp32_peak / 1e12, "unit": "TFLOP/s", "frac": flops / scan_s / fp32_peak,
-                "traffic": SCAN_DRAM_BYTES_NCU.get(args.workload),
-                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
-                                  "(profiles/r01_knn_scan_v3_spring_csr_ncu.md); algorithmic bytes per launch = 16*E = "
-                                  f"{16.0 * E:.0f}",
+                "traffic": traffic,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full of THIS build "
+                                  "(profiles/r02_scan_traffic.json) or null when not captured; algorithmic bytes per launch "
+                                  f"= 16*E = {16.0 * E:.0f}",
                 "peak_source": "gem_fp32_peak_probe: dependent-chain-free FFMA loop measured in this run "
                                "(MEASURED_PEAKS.json has no FP32 figure); nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.5",
+                "frac_of_nominal_peak": flops / scan_s / 74.5e12,
                 "algorithmic_flops_per_launch": flops, "ms": scan_s * 1e3,
                 "executed_fma_tflops": executed / scan_s / 1e12,
+                "executed_frac_of_peak": executed / scan_s / fp32_peak,
                 "note": "algorithmic = SURVEY 8(d): 2(d+2)*S*E flop (the 5-term cdist chain per pair). The kernel "
                         "executes d FMA + a min/compare per pair as a conservative filter and re-checks the rare "
                         "passes with the exact chain, so `achieved` counts work it does not have to do: "
@@ -370,15 +531,14 @@ def run_b200(args, w):
                                   "frac": ka_bytes / (stage["spring_mid"] * 1e-3) / 1e9 / hbm,
                                   "algorithmic_bytes": ka_bytes, "ms": stage["spring_mid"],
                                   "note": "bound in practice by the L1 wavefront rate of 2E scattered 16-byte position "
-                                          "gathers (DESIGN.md section 4a), not by DRAM"},
-            "update (stats pass + normalise)": {
+                                          "gathers (DESIGN.md section 4a), not by DRAM; the stage includes the column-sum pass"},
+            "update (normalise)": {
                 "bound": "hbm", "achieved": kd_bytes / (stage["update"] * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                 "frac": kd_bytes / (stage["update"] * 1e-3) / 1e9 / hbm, "algorithmic_bytes": kd_bytes,
                 "ms": stage["update"],
                 "note": "the `update` stage is the normalisation pass only: the add of pass 1 is done by the spring kernel "
-                        "(it writes pos+F) and the column-sum pass is timed inside the spring stage; in the timed steps "
-                        "it runs on the side stream next to the scan. frac uses the full 20dN algorithmic bytes of the "
-                        "reference's update and is therefore an upper bound for this stage alone"},
+                        "(it writes pos+F) and the column-sum pass is timed inside the spring stage; frac uses the full "
+                        "20dN algorithmic bytes of the reference's update and is an upper bound for this stage alone"},
             "spring+update combined": {
                 "bound": "hbm", "algorithmic_bytes": ka_bytes + kd_bytes, "ms": stage["spring_mid"] + stage["update"],
                 "achieved": (ka_bytes + kd_bytes) / ((stage["spring_mid"] + stage["update"]) * 1e-3) / 1e9, "peak": hbm,
@@ -392,53 +552,62 @@ def run_b200(args, w):
         b_iter = 8.0 * E + 8.0 * d * E + 28.0 * d * N
         t_roof = b_iter / (hbm * 1e9) + flops / fp32_peak
         extra_roof["iteration"] = {"t_roof_ms": t_roof * 1e3, "achieved_ms": total_ms / K,
-                                   "frac": t_roof * 1e3 / (total_ms / K)}
+                                   "frac": t_roof * 1e3 / (total_ms / K),
+                                   "frac_sustained": t_roof * 1e3 / sus_ms}
 
+    exchange = emb.exchange if world > 1 else None
     if world > 1:
-        emb.close()            # captured graphs hold NCCL kernels: release them before the communicator
+        emb.close()            # captured graphs hold barrier / NCCL kernels: release them before the communicator
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- CPU baseline on this box's host cores (bounded sample)
+    # ---- CPU baseline on this box's host cores (bounded sample), N = 1 only
     cpu = None
-    if not args.no_cpu_baseline:
+    cpu_gc = None
+    if not args.no_cpu_baseline and world == 1:
         cb_steps = 2 if E > 1_000_000 else 3
-        r = cpu_reference_timing(adj, w, cb_steps, 1)
+        r = cpu_reference_timing(adj, w, cb_steps, 1, budget_s=25.0)
         cpu = {"value": r["E"] / r["sec_per_step"], "unit": "edge-updates/s", "cores": r["cores"], "kind": "port",
                "sample": r["sample"], "iters_per_s": 1.0 / r["sec_per_step"]}
+        r2 = cpu_reference_timing(adj, w, cb_steps, 1, with_gc=True, budget_s=25.0)
+        cpu_gc = {"value": r2["E"] / r2["sec_per_step"], "unit": "edge-updates/s", "cores": r2["cores"], "kind": "port",
+                  "sample": r2["sample"], "iters_per_s": 1.0 / r2["sec_per_step"]}
 
     ms_per_step = total_ms / K
     value = E / (ms_per_step * 1e-3)
-    # kernels of libgraphem_b200.so per iteration (memset / memcpy nodes and torch / NCCL kernels not counted):
-    # 1 GPU: linegraph_hint (+sample +query midpoints), knn_bound, knn_threshold, spring_csr, column sums, knn_scan,
-    # knn_select (+intersection), normalise; N > 1: the 12 stage kernels of sharded.CudaStages
-    launches_per_step = 8 if world == 1 else 12
+    # kernels of libgraphem_b200.so per iteration (memset / memcpy nodes and torch / barrier kernels not counted):
+    # 1 GPU: knn_prep (sample + query midpoints + bounds + thresholds), spring_csr, column sums, knn_scan,
+    # knn_select (+intersection), normalise; N > 1: knn_prep, spring_csr (push), column sums, knn_scan, knn_select
+    # (publishing the lists), topk_merge_intersect (+patch/stat publication), normalise_all
+    launches_per_step = 6 if world == 1 else (7 if exchange == "p2p" else 12)
     S_eff = min(w["S"], E)
     if world == 1 and S_eff > 1024:
-        # general path: sample, spring, query midpoints, hint, per batch of 1024 queries (bound, threshold, one scan per
-        # 256 queries, select), intersection, two update passes
+        # general path: sample, spring, query midpoints, hint, per batch of 1024 queries (prep, one scan per 256 queries,
+        # select), intersection, two update passes
         nb, rem = divmod(S_eff, 1024)
-        launches_per_step = 4 + nb * (3 + 4) + ((3 + (rem + 255) // 256) if rem else 0) + 3
+        launches_per_step = 4 + nb * (2 + 4) + ((2 + (rem + 255) // 256) if rem else 0) + 3
     line = {
         "metric": METRIC, "value": value, "unit": "edge-updates/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "iters_per_s": 1e3 / ms_per_step,
-        "config": {"workload": w["desc"], "N": n, "E": E, "sample_size": min(w["S"], E), "n_neighbors": w["k"],
-                   "parallelism": "single GPU" if world == 1 else
-                   (f"vertex-range sharded x{world}, exchanges = P2P stores over symmetric memory + device barriers"
-                    if getattr(emb._engine.st, "peer_ptrs", None) is not None
-                    else f"vertex-range sharded x{world}, NCCL all-gather / all-reduce"),
-                   "l2": "flushed before every timed step (512 MiB write, untimed)",
-                   "step": "one replay of the CUDA graph of one iteration (run_layout's production path)",
-                   "sampler": "device (gem_sample_edges)", "init": "randn*0.1 default_rng(0)"},
-        "ms_per_step_back_to_back": b2b_ms,
+        "config": workload_config(w, n, E),
+        "details": {"parallelism": "single GPU" if world == 1 else
+                    (f"vertex-sharded x{world} (v mod N): spring kernel pushes pos+F rows to every replica over NVLink, select "
+                     f"publishes the partial lists, 2 device barriers, every rank normalises all rows; no NCCL collective"
+                     if exchange == "p2p" else f"vertex-sharded x{world}, NCCL all-gather / all-reduce fallback flow"),
+                    "step": "one replay of the CUDA graph of one iteration (run_layout's production path)",
+                    "sampler": "device (keyed bijection, gem_knn_prep)" if args.sampler == "device" else
+                               "torch.randperm(E)[:S] from the seeded default generator (the reference's RNG stream), drawn one "
+                               "iteration ahead on a side stream inside the captured graph",
+                    "graph_generation_s": round(t_graph, 2), "constructor_s": round(t_construct, 2)},
+        "sustained": {"iterations": sus_iters, "ms_per_step": sus_ms, "seconds": sus_ms * sus_iters * 1e-3,
+                      "value": E / (sus_ms * 1e-3), "l2": "not flushed (back-to-back replays)", "clocks": clk2},
         "wall_s_timed_region": t_wall,
         "e2e": {"value": E / (e2e_ms * 1e-3), "unit": "edge-updates/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
-                "api": "load_positions(pinned host) -> run_layout_device(1) [replay of the captured iteration] -> read_positions(pinned host)"},
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "api": api},
         "gpu_launches": launches_per_step * K,
         "timed_steps_ms": {"min": float(np.min(step_ms)), "median": float(np.median(step_ms)), "max": float(np.max(step_ms))},
         "clocks": clk,
@@ -447,6 +616,12 @@ def run_b200(args, w):
         "stage_ms": stage,
         "cpu_baseline": cpu,
     }
+    if cpu_gc is not None:
+        line["cpu_baseline_as_shipped_equivalent"] = cpu_gc
+    if parity is not None:
+        line["parity"] = parity
+    if phase_us is not None:
+        line["phase_us"] = phase_us
     if setup is not None:
         line["graph_setup_s"] = setup          # constructor with given initial positions: device vs host graph build
     print(json.dumps(line), flush=True)
@@ -461,6 +636,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--sampler", default="device", choices=["device", "torch"],
+                    help="query-edge sampler: the library's keyed bijection, or the reference's torch.randperm stream")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sample-size", type=int, default=None,
                     help="override the workload's sample size S (>= E: the full-KNN regime, SURVEY 8(f).4)")

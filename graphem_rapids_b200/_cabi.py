@@ -13,7 +13,7 @@ from ctypes import (POINTER, Structure, c_char_p, c_double, c_float, c_int, c_in
 from . import build as _build
 
 _lib = None
-ABI_VERSION = 2
+ABI_VERSION = 3
 STAGE_NAMES = ["sample", "spring_mid", "query_mid", "knn_bound", "knn_threshold", "knn_scan", "knn_select",
                "knn_fallback", "intersect", "update"]
 _inited_devices = set()
@@ -33,13 +33,40 @@ class GemPlan(Structure):
         ("iter_counter", c_void_p),
         ("knn_ws", c_void_p), ("knn_ws_bytes", c_size_t),
         ("stats_ws", c_void_p),
-        ("external_sample", c_int32), ("mm_mode", c_int32),
+        ("external_sample", c_int32), ("mm_mode", c_int32), ("coef_slot", c_int32),
     ]
+
+
+class GemKnnPrepArgs(Structure):
+    """Mirror of `struct gem_knn_prep_args`."""
+    _fields_ = [
+        ("d", c_int32), ("kp1", c_int32), ("s", c_int64), ("e", c_int64),
+        ("pos", c_void_p), ("edges", c_void_p), ("e_total", c_int64), ("samp", c_void_p),
+        ("draw", c_int32), ("bump", c_int32), ("seed", c_uint64), ("iter_counter", c_void_p),
+        ("qmid_in", c_void_p), ("qmid_out", c_void_p),
+        ("row_ptr", c_void_p), ("col", c_void_p), ("tau_hint_in", c_void_p), ("tau_hint_out", c_void_p),
+        ("bound_mid", c_void_p), ("bound_edges", c_void_p), ("e_bound", c_int64), ("bound_samples", c_int64),
+        ("coef_slot", c_int32),
+        ("ws", c_void_p), ("ws_bytes", c_size_t),
+    ]
+
+
+class GemKnnPublish(Structure):
+    """Mirror of `struct gem_knn_publish`."""
+    _fields_ = [("remap", c_void_p), ("peer_base_host", POINTER(c_void_p)), ("world", c_int32),
+                ("idx_offset_bytes", c_size_t), ("dist_offset_bytes", c_size_t)]
+
+
+class GemMergePublish(Structure):
+    """Mirror of `struct gem_merge_publish`."""
+    _fields_ = [("peer_raw_host", POINTER(c_void_p)), ("peer_xchg_host", POINTER(c_void_p)), ("world", c_int32),
+                ("rank", c_int32), ("stats_offset_bytes", c_size_t), ("touched", c_void_p), ("counters", c_void_p)]
 
 
 # name -> (restype, argtypes); every symbol include/graphem_b200.h declares
 SIGNATURES = {
     "gem_abi_version": (c_int, []),
+    "gem_abi_struct_sizes": (c_int, [POINTER(c_size_t)]),
     "gem_init": (c_int, []),
     "gem_error_string": (c_char_p, [c_int]),
     "gem_row_pitch": (c_int, [c_int]),
@@ -51,20 +78,22 @@ SIGNATURES = {
                                          c_int, c_float, c_float, c_void_p, c_void_p, c_int64, c_void_p]),
     "gem_spring_update_csr": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64,
                                       c_int, c_float, c_float, c_void_p, c_void_p, c_int64, c_void_p]),
+    "gem_spring_update_csr_push": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64,
+                                           c_int, c_float, c_float, POINTER(c_void_p), c_int, c_void_p, c_int64, c_void_p]),
+    "gem_coef_slots": (c_int, []),
+    "gem_coef_slot_acquire": (c_int, [POINTER(c_int)]),
+    "gem_coef_slot_release": (c_int, [c_int]),
     "gem_sample_edges": (c_int, [c_uint64, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p]),
     "gem_query_midpoints": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "gem_knn_workspace_bytes": (c_int, [c_int64, c_int, c_int64, c_int, POINTER(c_size_t)]),
     "gem_knn_midpoints": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_int, c_int, c_void_p,
-                                  c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+                                  c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     "gem_knn_midpoints_shard": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_int64, c_int, c_int,
-                                        c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+                                        c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     "gem_knn_fast_path": (c_int, [c_int64, c_int64, c_int, c_int64, c_int]),
-    "gem_knn_prepare": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p,
-                                c_void_p, c_void_p, c_size_t, c_void_p]),
-    "gem_knn_query_prep": (c_int, [c_uint64, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
-                                   c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "gem_knn_prep": (c_int, [POINTER(GemKnnPrepArgs), c_void_p]),
     "gem_knn_scan": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_void_p,
-                             c_void_p, c_size_t, c_void_p]),
+                             c_void_p, c_size_t, c_int, POINTER(GemKnnPublish), c_void_p]),
     "gem_knn_linegraph_hint": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int,
                                        c_void_p, c_void_p]),
     "gem_knn_midpoints_exact": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_int, c_int,
@@ -76,7 +105,7 @@ SIGNATURES = {
                                        c_void_p, c_void_p]),
     "gem_topk_merge_intersect": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int, c_void_p, c_void_p,
                                          c_void_p, c_void_p, c_void_p, c_int, c_float, c_int64, c_int64, c_void_p,
-                                         c_void_p, c_void_p]),
+                                         c_void_p, POINTER(GemMergePublish), c_void_p]),
     "gem_intersection_forces": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64,
                                         c_int, c_float, c_void_p, c_void_p]),
     "gem_intersection_forces_range": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64,
@@ -86,8 +115,11 @@ SIGNATURES = {
                                      c_int, c_void_p]),
     "gem_update_normalise_push": (c_int, [POINTER(c_void_p), c_int, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p,
                                           c_void_p, c_void_p]),
+    "gem_update_normalise_all": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_int, c_void_p]),
     "gem_remap_indices": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "gem_push_bytes": (c_int, [POINTER(c_void_p), c_int, c_size_t, c_void_p, c_size_t, c_void_p]),
+    "gem_rows_scatter": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, POINTER(c_void_p), c_int, c_void_p]),
+    "gem_rows_gather": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "gem_layout_step": (c_int, [POINTER(GemPlan), c_void_p]),
     "gem_profile_step": (c_int, [POINTER(GemPlan), c_void_p, POINTER(c_float)]),
     "gem_spmv_cols": (c_int, []),
@@ -120,6 +152,11 @@ def load():
                 raise ImportError(
                     "graphem_rapids_b200: libgraphem_b200.so is missing and could not be built "
                     f"({exc}). Run `python -c 'import __graft_entry__ as g; g.build()'`.") from exc
+            # an older library exists, the sources are newer and the rebuild failed (e.g. no nvcc on this box):
+            # say so instead of silently running stale code; the ABI version check below still applies
+            import warnings
+            warnings.warn(f"graphem_rapids_b200: sources are newer than {_build.LIB} and the rebuild failed ({exc}); "
+                          "loading the existing library", RuntimeWarning)
     lib = ctypes.CDLL(_build.LIB)
     for name, (restype, argtypes) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError if the library lacks a declared symbol
@@ -127,6 +164,11 @@ def load():
         fn.argtypes = argtypes
     if lib.gem_abi_version() != ABI_VERSION:
         raise ImportError("graphem_rapids_b200: ABI version mismatch between header and library")
+    sizes = (c_size_t * 4)()
+    lib.gem_abi_struct_sizes(sizes)
+    mine = [ctypes.sizeof(t) for t in (GemPlan, GemKnnPrepArgs, GemKnnPublish, GemMergePublish)]
+    if list(sizes) != mine:
+        raise ImportError(f"graphem_rapids_b200: struct layouts differ between _cabi.py {mine} and the library {list(sizes)}")
     _lib = lib
     return lib
 

@@ -10,6 +10,7 @@
 #include <stdint.h>
 #include <math.h>
 #include <type_traits>
+#include <mutex>
 #include "graphem_b200.h"
 
 #define GEM_CHECK_LAUNCH()                                   \
@@ -43,6 +44,10 @@ int num_sms() {
     }
     return g_num_sms;
 }
+
+// peer-mapped replicas of one buffer (own rank included): NVLink P2P stores (multi-GPU exchanges)
+constexpr int kMaxPeers = 16;
+struct PeerPtrs { float *p[kMaxPeers]; };
 
 // optional per-stage CUDA events (gem_profile_step); nullptr on the product path
 struct StageTimer {
@@ -206,10 +211,18 @@ constexpr int kUpdBlocksMax = 1184;    // 148 * 8
 // intersection forces are added to those rows afterwards with an exact correction of the sums
 // (intersect_pair<D, true>), so only the normalisation pass is left on the critical path behind the
 // KNN.  (Accumulating the sums inside this kernel cost 8 registers = one resident CTA per SM, +16 us.)
+// world > 0 (multi-GPU, FUSE only): the new row pos + F_spring of vertex v goes to row v of EVERY rank's replica of
+// the raw (unnormalised) position buffer -- the rank's own and, through peer-mapped pointers (NVLink P2P stores),
+// the others'.  The exchange of the updated positions therefore starts with the first finished row and runs
+// underneath the KNN scan instead of after it; every rank normalises all rows locally once the column sums are known.
+struct SpringPeers { PeerPtrs peers; int world; };
 template <int D, bool FUSE>
-__device__ __forceinline__ void spring_emit(const Vec<D> &pv, const Vec<D> &acc, float *__restrict__ out, int64_t row) {
-    if (!FUSE) acc.store(out, row);
-    else (pv + acc).store(out, row);                                 // :799 (total force = spring part here)
+__device__ __forceinline__ void spring_emit(const Vec<D> &pv, const Vec<D> &acc, float *__restrict__ out, int64_t v,
+                                            int64_t v_begin, const SpringPeers &sp) {
+    if (!FUSE) { acc.store(out, v - v_begin); return; }
+    const Vec<D> nv = pv + acc;                                      // :799 (total force = spring part here)
+    if (sp.world == 0) { nv.store(out, v - v_begin); return; }
+    for (int r = 0; r < sp.world; ++r) nv.store(sp.peers.p[r], v);
 }
 
 template <int D, bool FUSE>
@@ -220,7 +233,8 @@ __global__ void __launch_bounds__(kThreads) spring_csr_kernel(const float *__res
                                                               int64_t v_end, const int32_t *__restrict__ hubs,
                                                               int n_hub_blocks, float neg_k_attr, float l_min,
                                                               float *__restrict__ force,
-                                                              typename MidT<D>::T *__restrict__ mid, int64_t mid_base) {
+                                                              typename MidT<D>::T *__restrict__ mid, int64_t mid_base,
+                                                              const SpringPeers sp) {
     if ((int)blockIdx.x < n_hub_blocks) {
         // ---- one CTA per hub row; scheduled first so the long rows overlap the bulk of the work
         const int64_t v = hubs[blockIdx.x];
@@ -244,7 +258,7 @@ __global__ void __launch_bounds__(kThreads) spring_csr_kernel(const float *__res
             float t[3] = {0.f, 0.f, 0.f};
             for (int w = 0; w < kWarps; ++w)
                 for (int j = 0; j < 3; ++j) t[j] += red[w][j];
-            spring_emit<D, FUSE>(pv, vec_from3<D>(t), force, v - v_begin);
+            spring_emit<D, FUSE>(pv, vec_from3<D>(t), force, v, v_begin, sp);
         }
         return;
     }
@@ -291,7 +305,7 @@ __global__ void __launch_bounds__(kThreads) spring_csr_kernel(const float *__res
         }
         acc = acc + shfl_xor_vec(acc, 1);
         acc = acc + shfl_xor_vec(acc, 2);
-        if (valid && !hub && g == 0) spring_emit<D, FUSE>(pv, acc, force, v - v_begin);   // isolated vertices too
+        if (valid && !hub && g == 0) spring_emit<D, FUSE>(pv, acc, force, v, v_begin, sp);   // isolated vertices too
     }
 }
 
@@ -573,71 +587,6 @@ __device__ __forceinline__ float filter_threshold(float ta, float qn) {
     return __fadd_ru(th, 1e-37f);
 }
 
-// Candidates come either from the midpoint array or -- `mid == nullptr` -- are recomputed from
-// (pos, edges) with the spring kernel's own expression (identical bits).  The second form depends on
-// the positions only, so gem_layout_step runs the whole bound/threshold preparation on a second
-// stream concurrently with the spring kernel that produces `mid`.
-template <int D>
-__global__ void __launch_bounds__(kThreads) knn_bound_kernel(const typename MidT<D>::T *__restrict__ mid,
-                                                             const float *__restrict__ pos,
-                                                             const int2 *__restrict__ edges, int64_t e,
-                                                             const float *__restrict__ qmid, int s,
-                                                             int tiles_per_cta, float *__restrict__ chunkmin) {
-    using CandT = typename MidT<D>::T;
-    __shared__ float red[kWarps][kQB];
-    __shared__ __align__(16) CandT tile[kBoundTile];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = gridDim.x;
-    for (int qb = 0; qb * kQB < s; ++qb) {
-        QueryPar qp[kQ];
-        float best[kQ];
-#pragma unroll
-        for (int i = 0; i < kQ; ++i) {
-            const int q = qb * kQB + i * 32 + lane;
-            qp[i] = load_query<D>(qmid, q < s ? q : 0);
-            best[i] = kInf;
-        }
-        // stratified sample: CTA b looks at (up to) tiles_per_cta*kBoundTile consecutive candidates from the
-        // start of ITS share [b*e/g, (b+1)*e/g) of the index range (NOT the scan's interleaving: its first
-        // blocks are the lowest-index edges, i.e. the hub edges of a preferential-attachment graph -- a
-        // hopelessly biased sample).  Every CTA has candidates as soon as e >= g, so small problems get a
-        // finite bound too (with tile-granular shares, e < g*kBoundTile left most chunk minima at +inf).
-        const int64_t lo = ((int64_t)blockIdx.x * e) / g, hi = ((int64_t)(blockIdx.x + 1) * e) / g;
-        for (int j = 0; j < tiles_per_cta; ++j) {
-            const int64_t base = lo + (int64_t)j * kBoundTile;
-            if (base >= hi) break;
-            const int cnt = (int)min((int64_t)kBoundTile, hi - base);
-            __syncthreads();
-            if (mid != nullptr) {
-                for (int c = threadIdx.x; c < cnt; c += kThreads) tile[c] = __ldg(mid + base + c);
-            } else {
-                for (int c = threadIdx.x; c < cnt; c += kThreads) {
-                    const int2 ed = __ldg(edges + base + c);
-                    tile[c] = make_mid(half_sum(Vec<D>::load(pos, ed.x), Vec<D>::load(pos, ed.y)));
-                }
-            }
-            __syncthreads();
-            for (int c = warp; c < cnt; c += kWarps) {
-                float x, y, z, n;
-                cand_xyzn(tile[c], x, y, z, n);
-#pragma unroll
-                for (int i = 0; i < kQ; ++i) best[i] = fminf(best[i], chain_mm(qp[i], x, y, z, n, D));
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < kQ; ++i) red[warp][i * 32 + lane] = best[i];
-        __syncthreads();
-        {
-            const int q = qb * kQB + threadIdx.x;
-            float v = red[0][threadIdx.x];
-#pragma unroll
-            for (int w = 1; w < kWarps; ++w) v = fminf(v, red[w][threadIdx.x]);
-            if (q < s) chunkmin[(int64_t)q * g + blockIdx.x] = v;
-        }
-        __syncthreads();
-    }
-}
-
 // Line-graph bound: the edges incident to the endpoints (u,v) of a query edge are distinct
 // candidates whose midpoints tend to be its nearest neighbours in a force-directed layout (and they
 // are clustered in index space, which the strided chunk sample cannot see).  hint_q = the (k+1)-th
@@ -645,34 +594,17 @@ __global__ void __launch_bounds__(kThreads) knn_bound_kernel(const typename MidT
 // within hint_q, so it is a valid upper bound of the (k+1)-th neighbour distance.  One warp per query.
 constexpr int kLgPerLane = 8;
 constexpr int kLgMax = 16 * kLgPerLane;              // neighbours examined per endpoint
+// whole warp; returns the bound (distance, not squared) on every lane
 template <int D>
-__global__ void __launch_bounds__(kThreads) knn_linegraph_hint_kernel(const float *__restrict__ pos,
-                                                                      const int64_t *__restrict__ row_ptr,
-                                                                      const int32_t *__restrict__ col,
-                                                                      const int2 *__restrict__ edges,
-                                                                      int64_t *samp, int s, int kp1,
-                                                                      float *__restrict__ hint, int draw, uint64_t seed,
-                                                                      const int64_t *__restrict__ iter_counter,
-                                                                      int64_t e, typename MidT<D>::T *__restrict__ qmid) {
-    // draw != 0: this kernel also draws the sample (gem_sample_edges) and, qmid != nullptr, writes the query
-    // midpoints (gem_query_midpoints): the three per-query preparation launches of the iteration in one
-    const int lane = threadIdx.x & 31;
-    const int q = blockIdx.x * kWarps + (threadIdx.x >> 5);
-    if (q >= s) return;
-    int64_t id;
-    if (draw) {
-        id = (s >= e) ? (int64_t)q : feistel_draw(feistel_key(seed, iter_counter ? *iter_counter : 0, e), e, q);
-        if (lane == 0) samp[q] = id;
-    } else {
-        id = samp[q];
-    }
+__device__ __forceinline__ float lg_hint(const float *__restrict__ pos, const int64_t *__restrict__ row_ptr,
+                                         const int32_t *__restrict__ col, const int2 *__restrict__ edges, int64_t id,
+                                         int kp1, int lane) {
     const int2 ed = edges[id];
     const Vec<D> mq = half_sum(Vec<D>::load(pos, ed.x), Vec<D>::load(pos, ed.y));
-    if (qmid != nullptr && lane == 0) qmid[q] = make_mid(mq);
+    float qx, qy, qz, qn;
+    cand_xyzn(make_mid(mq), qx, qy, qz, qn);
     QueryPar qp;
-    qp.a0 = -2.f * mq.x; qp.a1 = -2.f * mq.y;
-    if (D == 3) { const Vec<3> &m3 = reinterpret_cast<const Vec<3> &>(mq); qp.a2 = -2.f * m3.z; } else qp.a2 = 0.f;
-    qp.qn = (D == 3) ? sqsum(reinterpret_cast<const Vec<3> &>(mq)) : sqsum(reinterpret_cast<const Vec<2> &>(mq));
+    qp.a0 = -2.f * qx; qp.a1 = -2.f * qy; qp.a2 = -2.f * qz; qp.qn = qn;
     float v[kLgPerLane];
 #pragma unroll
     for (int j = 0; j < kLgPerLane; ++j) v[j] = kInf;
@@ -713,62 +645,193 @@ __global__ void __launch_bounds__(kThreads) knn_linegraph_hint_kernel(const floa
                 if (!done && v[j] == wm) { v[j] = kInf; done = true; }
         }
     }
-    if (lane == 0) hint[q] = (kth < kInf) ? __fsqrt_rn(fmaxf(kth, 0.f)) + 0.f : kInf;
+    return (kth < kInf) ? __fsqrt_rn(fmaxf(kth, 0.f)) + 0.f : kInf;
 }
 
-// one warp per query: (k+1)-th smallest of g <= 1024 chunk minima by repeated min extraction
 template <int D>
-__global__ void __launch_bounds__(kThreads) knn_threshold_kernel(const float *__restrict__ chunkmin, int g, int kp1,
-                                                                 const float *__restrict__ qmid, int s,
-                                                                 const float *__restrict__ hint,
-                                                                 float *__restrict__ theta, float *__restrict__ tau,
-                                                                 float *__restrict__ qcoef /* [3][kMaxBatchQ/2][2] */,
-                                                                 int64_t *bump_counter) {
-    // (the fused query-preparation kernel reads the iteration counter in every CTA, so the increment
-    //  happens here, one launch later in the same stream)
-    if (bump_counter != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *bump_counter += 1;
+__global__ void __launch_bounds__(kThreads) knn_linegraph_hint_kernel(const float *__restrict__ pos,
+                                                                      const int64_t *__restrict__ row_ptr,
+                                                                      const int32_t *__restrict__ col,
+                                                                      const int2 *__restrict__ edges,
+                                                                      const int64_t *__restrict__ samp, int s, int kp1,
+                                                                      float *__restrict__ hint) {
     const int lane = threadIdx.x & 31;
     const int q = blockIdx.x * kWarps + (threadIdx.x >> 5);
     if (q >= s) return;
-    float v[32];                                   // g <= 1024
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        const int u = j * 32 + lane;
-        const float x = (u < g) ? chunkmin[(int64_t)q * g + u] : kInf;
-        v[j] = (x == x) ? x : kInf;                // NaN -> +inf
-    }
-    float kth = kInf;
-    if (kp1 <= g) {
-        for (int r = 0; r < kp1; ++r) {
-            float m = v[0];
-#pragma unroll
-            for (int j = 1; j < 32; ++j) m = fminf(m, v[j]);
-            float wm = m;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) wm = fminf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
-            kth = wm;
-            // the first lane holding wm removes one copy of it
-            const unsigned holders = __ballot_sync(0xffffffffu, m == wm);
-            if (holders == 0) break;               // only +inf left
-            if (lane == __ffs(holders) - 1) {
-                bool done = false;
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (!done && v[j] == wm) { v[j] = kInf; done = true; }
+    const float h = lg_hint<D>(pos, row_ptr, col, edges, samp[q], kp1, lane);
+    if (lane == 0) hint[q] = h;
+}
+
+// ---- fused preparation of one query batch: ONE launch ---------------------------------------------
+// Everything the scan needs before it can start depends on the positions only:
+//   (0) the sample (keyed bijection, or ids given by the caller) and the query midpoints,
+//   (1) a stratified bound pass: CTA b < g evaluates the exact cdist chain of ALL queries against `per`
+//       consecutive candidates from the start of ITS share [b*e/g, (b+1)*e/g) of the candidate range and
+//       records the per-query minimum -> chunkmin[b][q],
+//   (2) the line-graph bound (CTAs >= g, one warp per query; lg_hint() above),
+//   (3) thresholds: the LAST CTA to finish (ticket) takes, per query, the (k+1)-th smallest of the g chunk
+//       minima -- k+1 DISTINCT candidates lie within it, so it bounds the (k+1)-th neighbour distance --
+//       min the line-graph / caller bound, derives the filter threshold, writes the coefficient pairs of
+//       the constant bank, zeroes the scan's survivor counters and bumps the iteration counter.
+// Round 1 ran this as hint -> bound -> threshold (three dependent launches, ~50 us at C3, and a bound pass
+// whose floor of one 768-candidate tile per CTA re-evaluated 45-57 % of a 400-500 K-edge problem); here
+// the sample is M ~ 48*sqrt(E) candidates (knn_layout: the size that balances the bound pass against the
+// scan's slow-path work, (k+1)*E/M expected filter passes per query).
+struct PrepArgs {
+    const float *pos; const int2 *edges; int64_t e_total;
+    int64_t *samp; int draw; uint64_t seed; int64_t *iter_counter; int bump;
+    const float *qmid_in; float *qmid_out;
+    const int64_t *row_ptr; const int32_t *col; const float *hint_in; float *hint_out;
+    const void *bound_mid; const int2 *bound_edges; int64_t e_bound;
+    int g, per, s, kp1;
+    float *chunkmin, *theta, *tau, *qcoef;
+    uint32_t *counts; int ncounts;
+    unsigned int *ticket;
+};
+
+template <int D>
+__global__ void __launch_bounds__(kThreads) knn_prep_kernel(const PrepArgs A) {
+    using CandT = typename MidT<D>::T;
+    extern __shared__ __align__(16) unsigned char prep_smem[];
+    float4 *s_q = reinterpret_cast<float4 *>(prep_smem);                      // (a0,a1,a2,qn) per query
+    float *s_list = reinterpret_cast<float *>(s_q + A.s);                     // last CTA: kp1 x kThreads sorted lists
+    __shared__ float red[kWarps][kQB];
+    __shared__ __align__(16) CandT tile[kBoundTile];
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t iter = (A.draw && A.iter_counter) ? *A.iter_counter : 0;
+    if ((int)blockIdx.x >= A.g) {
+        // ---- (2) line-graph bound, one warp per query
+        const int q = ((int)blockIdx.x - A.g) * kWarps + warp;
+        if (q < A.s) {
+            const int64_t id = A.draw ? ((int64_t)A.s >= A.e_total ? (int64_t)q
+                                                                  : feistel_draw(feistel_key(A.seed, iter, A.e_total), A.e_total, q))
+                                      : A.samp[q];
+            const float h = lg_hint<D>(A.pos, A.row_ptr, A.col, A.edges, id, A.kp1, lane);
+            if (lane == 0) A.hint_out[q] = h;
+        }
+    } else {
+        // ---- (0) query parameters of the whole batch (every bound CTA computes them: 2 gathers per query)
+        FeistelKey fk = {};
+        if (A.draw && (int64_t)A.s < A.e_total) fk = feistel_key(A.seed, iter, A.e_total);
+        for (int q = threadIdx.x; q < A.s; q += kThreads) {
+            QueryPar p;
+            if (A.qmid_in != nullptr) {
+                p = load_query<D>(A.qmid_in, q);
+            } else {
+                const int64_t id = A.draw ? ((int64_t)A.s >= A.e_total ? (int64_t)q : feistel_draw(fk, A.e_total, q)) : A.samp[q];
+                const int2 ed = A.edges[id];
+                const CandT m = make_mid(half_sum(Vec<D>::load(A.pos, ed.x), Vec<D>::load(A.pos, ed.y)));
+                float x, y, z, n;
+                cand_xyzn(m, x, y, z, n);
+                p.a0 = -2.f * x; p.a1 = -2.f * y; p.a2 = -2.f * z; p.qn = n;
+                if (blockIdx.x == 0) {
+                    if (A.draw) A.samp[q] = id;
+                    reinterpret_cast<CandT *>(A.qmid_out)[q] = m;
+                }
             }
+            s_q[q] = make_float4(p.a0, p.a1, p.a2, p.qn);
+        }
+        __syncthreads();
+        // ---- (1) bound pass over this CTA's stratified sample
+        const int64_t lo = ((int64_t)blockIdx.x * A.e_bound) / A.g, hi = ((int64_t)(blockIdx.x + 1) * A.e_bound) / A.g;
+        const int64_t take = min((int64_t)A.per, hi - lo);
+        const CandT *mid = reinterpret_cast<const CandT *>(A.bound_mid);
+        for (int qb = 0; qb * kQB < A.s; ++qb) {
+            QueryPar qp[kQ];
+            float best[kQ];
+#pragma unroll
+            for (int i = 0; i < kQ; ++i) {
+                const int q = qb * kQB + i * 32 + lane;
+                const float4 v = s_q[q < A.s ? q : 0];
+                qp[i].a0 = v.x; qp[i].a1 = v.y; qp[i].a2 = v.z; qp[i].qn = v.w;
+                best[i] = kInf;
+            }
+            for (int64_t t0 = 0; t0 < take; t0 += kBoundTile) {
+                const int cnt = (int)min((int64_t)kBoundTile, take - t0);
+                const int64_t base = lo + t0;
+                __syncthreads();
+                if (mid != nullptr) {
+                    for (int c = threadIdx.x; c < cnt; c += kThreads) tile[c] = __ldg(mid + base + c);
+                } else {
+                    for (int c = threadIdx.x; c < cnt; c += kThreads) {
+                        const int2 ed = __ldg(A.bound_edges + base + c);
+                        tile[c] = make_mid(half_sum(Vec<D>::load(A.pos, ed.x), Vec<D>::load(A.pos, ed.y)));
+                    }
+                }
+                __syncthreads();
+                for (int c = warp; c < cnt; c += kWarps) {
+                    float x, y, z, n;
+                    cand_xyzn(tile[c], x, y, z, n);
+#pragma unroll
+                    for (int i = 0; i < kQ; ++i) best[i] = fminf(best[i], chain_mm(qp[i], x, y, z, n, D));
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < kQ; ++i) red[warp][i * 32 + lane] = best[i];
+            __syncthreads();
+            {
+                const int q = qb * kQB + threadIdx.x;
+                float v = red[0][threadIdx.x];
+#pragma unroll
+                for (int w = 1; w < kWarps; ++w) v = fminf(v, red[w][threadIdx.x]);
+                if (q < A.s) A.chunkmin[(int64_t)blockIdx.x * A.s + q] = v;
+            }
+            __syncthreads();
         }
     }
-    if (lane == 0) {
+    // ---- (3) the last CTA derives the thresholds
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(A.ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const float *hint = A.hint_in != nullptr ? A.hint_in : (A.row_ptr != nullptr ? A.hint_out : nullptr);
+    for (int q = threadIdx.x; q < A.s; q += kThreads) {
+        // sorted list of the kp1 smallest chunk minima of query q (column threadIdx.x of s_list)
+        float *lst = s_list + threadIdx.x;
+        for (int r = 0; r < A.kp1; ++r) lst[r * kThreads] = kInf;
+        float worst = kInf;
+        for (int c0 = 0; c0 < A.g; c0 += 8) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = (c0 + u < A.g) ? __ldcg(A.chunkmin + (int64_t)(c0 + u) * A.s + q) : kInf;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const float x = v[u];
+                if (x < worst) {                                   // NaN compares false: ignored
+                    int r = A.kp1 - 1;
+                    while (r > 0 && lst[(r - 1) * kThreads] > x) { lst[r * kThreads] = lst[(r - 1) * kThreads]; --r; }
+                    lst[r * kThreads] = x;
+                    worst = lst[(A.kp1 - 1) * kThreads];
+                }
+            }
+        }
         float ta = kInf;
-        if (kth < kInf) ta = __fsqrt_rn(fmaxf(kth, 0.f)) + 0.f;
-        if (hint != nullptr) ta = fminf(ta, hint[q]);     // caller-provided bound (line-graph neighbours)
-        const QueryPar qp = load_query<D>(qmid, q);
-        theta[q] = filter_threshold(ta, qp.qn);
-        tau[q] = ta;
-        // staging copy of c_qcoef: pair m = q/2, component q&1
-        qcoef[(0 * (kMaxBatchQ / 2) + q / 2) * 2 + (q & 1)] = qp.a0;
-        qcoef[(1 * (kMaxBatchQ / 2) + q / 2) * 2 + (q & 1)] = qp.a1;
-        qcoef[(2 * (kMaxBatchQ / 2) + q / 2) * 2 + (q & 1)] = qp.a2;
+        if (worst < kInf) ta = __fsqrt_rn(fmaxf(worst, 0.f)) + 0.f;
+        if (hint != nullptr) ta = fminf(ta, __ldcg(hint + q));
+        const float4 qv = (A.qmid_in != nullptr || (int)blockIdx.x < A.g) ? s_q[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+        QueryPar qp;
+        if (A.qmid_in != nullptr || (int)blockIdx.x < A.g) {
+            qp.a0 = qv.x; qp.a1 = qv.y; qp.a2 = qv.z; qp.qn = qv.w;
+        } else {
+            // the last CTA is a line-graph CTA: it has no query table, CTA 0 has published the midpoints
+            float x, y, z, n;
+            cand_xyzn(__ldcg(reinterpret_cast<const CandT *>(A.qmid_out) + q), x, y, z, n);
+            qp.a0 = -2.f * x; qp.a1 = -2.f * y; qp.a2 = -2.f * z; qp.qn = n;
+        }
+        A.theta[q] = filter_threshold(ta, qp.qn);
+        A.tau[q] = ta;
+        // staging copy of the constant-bank table: pair m = q/2, component q&1
+        A.qcoef[(0 * (kMaxBatchQ / 2) + q / 2) * 2 + (q & 1)] = qp.a0;
+        A.qcoef[(1 * (kMaxBatchQ / 2) + q / 2) * 2 + (q & 1)] = qp.a1;
+        A.qcoef[(2 * (kMaxBatchQ / 2) + q / 2) * 2 + (q & 1)] = qp.a2;
+    }
+    for (int i = threadIdx.x; i < A.ncounts; i += kThreads) A.counts[i] = 0;   // the scan's survivor / tile counters
+    if (threadIdx.x == 0) {
+        *A.ticket = 0;
+        if (A.bump && A.iter_counter) *A.iter_counter = *A.iter_counter + 1;    // every CTA has read it (ticket)
     }
 }
 
@@ -897,7 +960,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 // c_qcoef[k][b*128 + m] = (a_k of query 2m, a_k of query 2m+1) of query block b; filled by a
 // device-to-device cudaMemcpyToSymbolAsync per batch (knn_fast), so one KNN per device may be in
 // flight at a time (the host class runs on one stream, like the reference).
-__constant__ float2 c_qcoef[3][kMaxBatchQ / 2];
+constexpr int kCoefSlots = 4;
+__constant__ float2 c_qcoef[kCoefSlots][3][kMaxBatchQ / 2];
 
 // Rare path, out of line, entered by the WHOLE warp when any lane has a hit.  A set bit c of a
 // lane's `hitmask` says: some (query of the pairs [c*kPairChunk, (c+1)*kPairChunk), candidate of that
@@ -954,8 +1018,8 @@ __global__ void __launch_bounds__(kScanThreads, 2) knn_scan_kernel(const typenam
                                                                    uint32_t *__restrict__ counts,
                                                                    uint64_t *__restrict__ keys, int cap,
                                                                    uint32_t *__restrict__ tile_counter,
-                                                                   unsigned long long *__restrict__ stats, int qb) {
-    // qb (query block) is a kernel PARAMETER, not blockIdx.y: ptxas keeps parameter-derived values in
+                                                                   unsigned long long *__restrict__ stats, int qb, int slot) {
+    // qb (query block) and slot (coefficient bank) are kernel PARAMETERS, not blockIdx.y: ptxas keeps parameter-derived values in
     // uniform registers, which the constant-bank coefficient addressing below depends on
     using CandT = typename MidT<D>::T;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1060,9 +1124,9 @@ __global__ void __launch_bounds__(kScanThreads, 2) knn_scan_kernel(const typenam
 #pragma unroll
                 for (int u = 0; u < kPairChunk; ++u) {                // per pair of queries: 3*kC FFMA2, min, 2 compares
                     const int m = qb * (kQB / 2) + mc + u;               // direct constant-bank indexing -> LDCU
-                    const unsigned long long a0 = *reinterpret_cast<const unsigned long long *>(&c_qcoef[0][m]);
-                    const unsigned long long a1 = *reinterpret_cast<const unsigned long long *>(&c_qcoef[1][m]);
-                    const unsigned long long a2 = *reinterpret_cast<const unsigned long long *>(&c_qcoef[2][m]);
+                    const unsigned long long a0 = *reinterpret_cast<const unsigned long long *>(&c_qcoef[slot][0][m]);
+                    const unsigned long long a1 = *reinterpret_cast<const unsigned long long *>(&c_qcoef[slot][1][m]);
+                    const unsigned long long a2 = *reinterpret_cast<const unsigned long long *>(&c_qcoef[slot][2][m]);
                     float lo[kC], hi[kC];
 #pragma unroll
                     for (int j = 0; j < kC; ++j) {
@@ -1140,11 +1204,16 @@ __device__ __forceinline__ float orient2d(float ax, float ay, float bx, float by
     return __fsub_rn(__fmul_rn(__fsub_rn(bx, ax), __fsub_rn(cy, ay)), __fmul_rn(__fsub_rn(by, ay), __fsub_rn(cx, ax)));
 }
 
+// rows of `force` that received a repulsion term (CORR form, multi-GPU): the owner re-publishes exactly these rows
+// to its peers after the bulk push of pos + F_spring (duplicates allowed; capacity 4 * s * k by construction)
+struct TouchList { int *rows; unsigned int *count; };
+
 // one candidate pair (edge i = sampled query edge, edge j = one of its neighbours)
 template <int D, bool CORR>
 __device__ __forceinline__ void intersect_pair_core(const float *__restrict__ pos, const int2 *__restrict__ edges, int64_t i,
                                                     int64_t j, int2 ei, Vec<D> p1, Vec<D> p2, float k_inter, int v_begin,
-                                                    int v_end, float *__restrict__ force, double *dsum, double *dsq);
+                                                    int v_end, float *__restrict__ force, double *dsum, double *dsq,
+                                                    TouchList tl = TouchList{nullptr, nullptr});
 
 // CORR = true: `force` holds unnormalised new positions whose fp64 column sums are already known
 // (fused spring+update form); the repulsion is added with an atomic that returns the old row, and
@@ -1164,7 +1233,8 @@ __device__ __forceinline__ void intersect_pair(const float *__restrict__ pos, co
 template <int D, bool CORR>
 __device__ __forceinline__ void intersect_pair_core(const float *__restrict__ pos, const int2 *__restrict__ edges, int64_t i,
                                                     int64_t j, int2 ei, Vec<D> p1, Vec<D> p2, float k_inter, int v_begin,
-                                                    int v_end, float *__restrict__ force, double *dsum, double *dsq) {
+                                                    int v_end, float *__restrict__ force, double *dsum, double *dsq,
+                                                    TouchList tl) {
     if (!(i < j)) return;                                        // :672
     const int2 ej = edges[j];                                    // :682
     if (ei.x == ej.x || ei.x == ej.y || ei.y == ej.x || ei.y == ej.y) return;   // :685-692
@@ -1188,6 +1258,7 @@ __device__ __forceinline__ void intersect_pair_core(const float *__restrict__ po
                 rep.red_add(force, vid[u] - v_begin);
             } else {
                 const Vec<D> old = rep.fetch_add(force, vid[u] - v_begin);
+                if (tl.rows != nullptr) tl.rows[atomicAdd(tl.count, 1u)] = vid[u];
                 float o[3], r[3];
                 vec_to3(old, o);
                 vec_to3(rep, r);
@@ -1267,6 +1338,7 @@ struct FusedIntersect {
     const float *pos; const int2 *edges; const int64_t *samp; float *force;
     float k_inter; int d, v_begin, v_end;
     double *sums;          // != nullptr: `force` holds new positions; correct these column sums (2*ld doubles)
+    TouchList touched;     // optional (multi-GPU): rows that received a term
 };
 // tail shared by the select and the merge kernel: thread c < k evaluates the candidate pair (query edge,
 // neighbour c) of the intersection stage; qi/qe/qa/qb4 = the query edge, its endpoints and their positions
@@ -1281,11 +1353,11 @@ __device__ __forceinline__ void fused_intersect_tail(const FusedIntersect &fx, i
             if (fx.d == 2) {
                 const Vec<2> p1 = {qa.x, qa.y}, p2 = {qb4.x, qb4.y};
                 if (fx.sums == nullptr) intersect_pair_core<2, false>(fx.pos, fx.edges, qi, j, qe, p1, p2, fx.k_inter, fx.v_begin, fx.v_end, fx.force, ds, dq);
-                else intersect_pair_core<2, true>(fx.pos, fx.edges, qi, j, qe, p1, p2, fx.k_inter, fx.v_begin, fx.v_end, fx.force, ds, dq);
+                else intersect_pair_core<2, true>(fx.pos, fx.edges, qi, j, qe, p1, p2, fx.k_inter, fx.v_begin, fx.v_end, fx.force, ds, dq, fx.touched);
             } else {
                 const Vec<3> p1 = {qa.x, qa.y, qa.z}, p2 = {qb4.x, qb4.y, qb4.z};
                 if (fx.sums == nullptr) intersect_pair_core<3, false>(fx.pos, fx.edges, qi, j, qe, p1, p2, fx.k_inter, fx.v_begin, fx.v_end, fx.force, ds, dq);
-                else intersect_pair_core<3, true>(fx.pos, fx.edges, qi, j, qe, p1, p2, fx.k_inter, fx.v_begin, fx.v_end, fx.force, ds, dq);
+                else intersect_pair_core<3, true>(fx.pos, fx.edges, qi, j, qe, p1, p2, fx.k_inter, fx.v_begin, fx.v_end, fx.force, ds, dq, fx.touched);
             }
         }
         if (fx.sums != nullptr) {                            // CTA-level reduction, then 2*d fp64 atomics per query
@@ -1310,11 +1382,31 @@ __device__ __forceinline__ void fused_intersect_tail(const FusedIntersect &fx, i
         }
 }
 
+// where the select kernel writes a query's list: the local (s, kp1) arrays and -- world > 0, multi-GPU -- the same
+// rows into every rank's exchange buffer (the rank's partial list is published by the kernel that produces it:
+// no separate remap / push launches).  remap: local candidate number -> global edge id (strided vertex
+// ownership numbers a rank's edges in the order its rows produce them; ties are broken by ORIGINAL id, and the
+// local order is the original order restricted to the rank's edges, so ranking by local number is the same).
+struct SelectOut {
+    int64_t *idx; float *dist;
+    int64_t idx_offset; const int64_t *remap;
+    PeerPtrs peers; int world;
+    size_t peer_idx_off, peer_dist_off;        // byte offsets of this rank's (s, kp1) blocks in the peers' buffers
+};
+__device__ __forceinline__ void select_emit(const SelectOut &so, int64_t pos, int64_t id, float dist) {
+    so.idx[pos] = id;
+    so.dist[pos] = dist;
+    for (int r = 0; r < so.world; ++r) {
+        char *base = reinterpret_cast<char *>(so.peers.p[r]);
+        reinterpret_cast<int64_t *>(base + so.peer_idx_off)[pos] = id;
+        reinterpret_cast<float *>(base + so.peer_dist_off)[pos] = dist;
+    }
+}
+
 // per query: exact top-kp1 among n = counts[q] <= cap published keys (unique)
 __global__ void __launch_bounds__(kThreads) knn_select_kernel(const uint32_t *__restrict__ counts,
                                                               const uint64_t *__restrict__ keys, int cap, int kp1,
-                                                              int64_t idx_offset, int64_t *__restrict__ out_idx,
-                                                              float *__restrict__ out_dist, FusedIntersect fx) {
+                                                              const SelectOut so, FusedIntersect fx) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *all = reinterpret_cast<uint64_t *>(smem_raw);        // cap
     __shared__ uint64_t sub[kThreads];
@@ -1345,7 +1437,7 @@ __global__ void __launch_bounds__(kThreads) knn_select_kernel(const uint32_t *__
     if (t < n) all[t] = spec;
     for (int i = t + kThreads; i < n; i += kThreads) all[i] = keys[(int64_t)q * cap + i];
     // a hinted (shard-local) search may find fewer than kp1 candidates: pad with (+inf, -1)
-    for (int r = n + t; r < kp1; r += kThreads) { out_idx[(int64_t)q * kp1 + r] = -1; out_dist[(int64_t)q * kp1 + r] = kInf; }
+    for (int r = n + t; r < kp1; r += kThreads) select_emit(so, (int64_t)q * kp1 + r, -1, kInf);
     __syncthreads();
     // shrink by strided-subsample thresholds until direct rank counting is cheap
     while (n > kSurvMax || (n > 2 * kThreads && n > 8 * kp1)) {
@@ -1382,14 +1474,22 @@ __global__ void __launch_bounds__(kThreads) knn_select_kernel(const uint32_t *__
         int r = 0;
         for (int u = 0; u < n; ++u) r += all[u] < k;
         if (r < kp1) {
-            const int64_t id = idx_offset + (int64_t)(uint32_t)k;
-            out_idx[(int64_t)q * kp1 + r] = id;
-            out_dist[(int64_t)q * kp1 + r] = key_dist(k);
+            const int64_t id = so.remap ? so.remap[(uint32_t)k] : so.idx_offset + (int64_t)(uint32_t)k;
+            select_emit(so, (int64_t)q * kp1 + r, id, key_dist(k));
             if (r < kMaxFastKp1) s_nb[r] = id;
         }
     }
     if (fx.force != nullptr) fused_intersect_tail(fx, q, t, kp1, n < kp1 ? n : kp1, s_nb, qi, qe, qa, qb4);
 }
+
+// multi-GPU publication stage of the merge kernel (world == 0: none)
+struct MergePublish {
+    PeerPtrs raw;            // every rank's raw (unnormalised) position buffer of this iteration
+    PeerPtrs xchg;           // every rank's exchange buffer
+    size_t stats_off;        // byte offset of the statistics area (world slots of 2*ld doubles) inside it
+    unsigned int *ticket;
+    int world, rank;
+};
 
 // merge of the per-rank partial lists (gem_topk_merge_strided) with the same fused tail as the select kernel:
 // on the multi-GPU path the CTA that has just merged query q's list evaluates its k candidate pairs
@@ -1397,7 +1497,8 @@ __global__ void __launch_bounds__(kThreads) topk_merge_intersect_kernel(const fl
                                                                         const int64_t *__restrict__ idxs,
                                                                         int64_t dist_stride, int64_t idx_stride, int parts,
                                                                         int64_t s, int kp1, int64_t *__restrict__ out_idx,
-                                                                        float *__restrict__ out_dist, FusedIntersect fx) {
+                                                                        float *__restrict__ out_dist, FusedIntersect fx,
+                                                                        const MergePublish mp) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ int64_t s_nb[kMaxFastKp1];
     const int total = parts * kp1;
@@ -1441,6 +1542,41 @@ __global__ void __launch_bounds__(kThreads) topk_merge_intersect_kernel(const fl
     }
     // globally there are >= kp1 real candidates (k+1 <= E), so ranks 0..kp1-1 are all real and all written
     if (fx.force != nullptr) fused_intersect_tail(fx, q, t, kp1, kp1, s_nb, qi, qe, qa, qb4);
+    if (mp.world == 0) return;
+    // ---- multi-GPU publication, by the LAST CTA to finish: (1) the rows of this rank that received a repulsion term
+    // go to every peer's raw buffer again (they were pushed as pos + F_spring by the spring kernel); (2) the rank's
+    // corrected column sums go to slot `rank` of every rank's statistics area.  One barrier later every rank can
+    // normalise ALL rows locally.
+    __threadfence();
+    __syncthreads();
+    __shared__ bool s_last;
+    if (t == 0) s_last = (atomicAdd(mp.ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const unsigned int nt = fx.touched.count ? __ldcg(fx.touched.count) : 0u;
+    const int ld = fx.d == 3 ? 4 : fx.d;
+    for (unsigned int i = t; i < nt; i += kThreads) {
+        const int64_t row = __ldcg(fx.touched.rows + i);               // padded vertex id (row of the raw buffer)
+        if (ld == 4) {
+            const float4 v = __ldcg(reinterpret_cast<const float4 *>(mp.raw.p[mp.rank]) + row);
+            for (int r = 0; r < mp.world; ++r)
+                if (r != mp.rank) reinterpret_cast<float4 *>(mp.raw.p[r])[row] = v;
+        } else {
+            const float2 v = __ldcg(reinterpret_cast<const float2 *>(mp.raw.p[mp.rank]) + row);
+            for (int r = 0; r < mp.world; ++r)
+                if (r != mp.rank) reinterpret_cast<float2 *>(mp.raw.p[r])[row] = v;
+        }
+    }
+    if (t < 2 * ld) {
+        const double v = __ldcg(fx.sums + t);
+        for (int r = 0; r < mp.world; ++r)
+            reinterpret_cast<double *>(reinterpret_cast<char *>(mp.xchg.p[r]) + mp.stats_off)[mp.rank * 2 * ld + t] = v;
+    }
+    if (t == 0) {
+        *mp.ticket = 0;
+        if (fx.touched.count) *fx.touched.count = 0;
+    }
 }
 
 // ==========================================================================================
@@ -1572,13 +1708,11 @@ __global__ void __launch_bounds__(kThreads) update_pass2_kernel(float *pos, cons
 // stores each result row into EVERY rank's replica of the position buffer -- its own and, through
 // peer-mapped pointers (NVLink / NVSwitch P2P stores), the others' -- so the all-gather of the updated
 // positions is not a separate collective but the store phase of this kernel.
-constexpr int kMaxPeers = 16;
-struct PeerPtrs { float *p[kMaxPeers]; };
 template <int LD>
 __global__ void __launch_bounds__(kThreads) update_pass2_bcast_kernel(PeerPtrs peers, int world, const float *src,
                                                                       int64_t row_begin, int64_t n, int64_t n_total,
                                                                       int d, const void *__restrict__ ws,
-                                                                      const double *__restrict__ rank_sums) {
+                                                                      const double *__restrict__ rank_sums, int nslots) {
     using VT = typename std::conditional<LD == 2, float2, float4>::type;
     // rank_sums != nullptr: the column sums arrive as one (2*LD)-double slot per rank (pushed by the peers);
     // every rank adds them in rank order, so all ranks normalise with bit-identical statistics
@@ -1587,7 +1721,7 @@ __global__ void __launch_bounds__(kThreads) update_pass2_bcast_kernel(PeerPtrs p
         double a;
         if (rank_sums != nullptr) {
             a = 0.0;
-            for (int r = 0; r < world; ++r) a += rank_sums[r * 2 * LD + threadIdx.x];
+            for (int r = 0; r < nslots; ++r) a += rank_sums[r * 2 * LD + threadIdx.x];
         } else {
             a = reinterpret_cast<const double *>(ws)[threadIdx.x];
         }
@@ -1631,6 +1765,42 @@ __global__ void __launch_bounds__(kThreads) push_bytes_kernel(PeerPtrs peers, in
         const uint4 v = src[i];
         for (int r = 0; r < world; ++r)
             reinterpret_cast<uint4 *>(reinterpret_cast<char *>(peers.p[r]) + dst_offset)[i] = v;
+    }
+}
+
+// Positions cross the API as (n, d) row-major arrays in ORIGINAL vertex numbering; on the device they live as
+// (n_pad, ld) rows in padded numbering.  rows_scatter: rows [row0, row0+cnt) of the public array (already on the
+// device, contiguous) -> row pad_index[row0+i] (or row0+i) of EVERY replica in `peers`, pad lanes zeroed; the
+// multi-GPU upload lets each rank bring 1/world of the rows over ITS PCIe link and fan them out over NVLink.
+// rows_gather is the inverse for one replica.
+__global__ void __launch_bounds__(kThreads) rows_scatter_kernel(const float *__restrict__ src, int64_t row0, int64_t cnt,
+                                                                int d, int ld, const int64_t *__restrict__ pad_index,
+                                                                PeerPtrs peers, int world) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cnt) return;
+    const int64_t row = pad_index ? pad_index[row0 + i] : row0 + i;
+    if (ld == 4 && d == 3) {
+        const float4 v = make_float4(src[i * 3], src[i * 3 + 1], src[i * 3 + 2], 0.f);
+        for (int r = 0; r < world; ++r) reinterpret_cast<float4 *>(peers.p[r])[row] = v;
+    } else if (ld == 2 && d == 2) {
+        const float2 v = reinterpret_cast<const float2 *>(src)[i];
+        for (int r = 0; r < world; ++r) reinterpret_cast<float2 *>(peers.p[r])[row] = v;
+    } else {
+        for (int r = 0; r < world; ++r)
+            for (int j = 0; j < ld; ++j) peers.p[r][row * ld + j] = j < d ? src[i * d + j] : 0.f;
+    }
+}
+__global__ void __launch_bounds__(kThreads) rows_gather_kernel(const float *__restrict__ pos, int64_t row0, int64_t cnt, int d,
+                                                               int ld, const int64_t *__restrict__ pad_index,
+                                                               float *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cnt) return;
+    const int64_t row = pad_index ? pad_index[row0 + i] : row0 + i;
+    if (ld == 4 && d == 3) {
+        const float4 v = reinterpret_cast<const float4 *>(pos)[row];
+        out[i * 3] = v.x; out[i * 3 + 1] = v.y; out[i * 3 + 2] = v.z;
+    } else {
+        for (int j = 0; j < d; ++j) out[i * d + j] = pos[row * ld + j];
     }
 }
 
@@ -1958,74 +2128,98 @@ inline int grid_for(int64_t work, int per_sm) {
 
 // ---- KNN fast path plumbing -------------------------------------------------------------------
 struct KnnLayout {
-    int g;                  // scan CTAs over the candidate axis (= chunks of the bound pass)
+    int g;                  // scan CTAs over the candidate axis
+    int g_max;              // upper bound of g and of the bound pass's chunk count (sizes chunkmin / cap)
     int cap;                // published candidates kept per query  (>= g * kp1: cannot overflow)
-    int tiles_per_cta;      // bound-pass tiles per CTA
     int64_t sb;             // queries per batch
-    size_t off_chunkmin, off_theta, off_tau, off_counts, off_stats, off_qcoef, off_keys, total;
+    size_t off_chunkmin, off_theta, off_tau, off_counts, off_stats, off_qcoef, off_ticket, off_keys, total;
 };
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 KnnLayout knn_layout(int64_t e, int64_t s, int kp1) {
     KnnLayout L;
-    L.g = 2 * num_sms();
-    if (L.g > 1024) L.g = 1024;
-    const int64_t ntiles = (e + kBoundTile - 1) / kBoundTile;
-    // sample ~1/32 of the candidates (at least one tile per CTA, at most 16)
-    int64_t tps = ntiles / ((int64_t)32 * L.g);
-    if (tps < 1) tps = 1;
-    if (tps > 16) tps = 16;
-    L.tiles_per_cta = (int)tps;
-    int cap = (L.g * kp1 + 255) / 256 * 256;          // every CTA publishes at most kp1 keys per query
+    L.g_max = 2 * num_sms();
+    if (L.g_max > 1024) L.g_max = 1024;
+    // scan grid: every warp of a CTA is its own consumer of 192-candidate blocks, so a small problem gets only as
+    // many CTAs as it has blocks for (round 1 launched 2 x SMs CTAs for 27 blocks at E = 5 K)
+    const int64_t nblocks = (e + kCandBlock - 1) / kCandBlock;
+    int64_t g = (nblocks + kWarps - 1) / kWarps;
+    if (g < 1) g = 1;
+    if (g > L.g_max) g = L.g_max;
+    L.g = (int)g;
+    int cap = (L.g_max * kp1 + 255) / 256 * 256;      // every CTA publishes at most kp1 keys per query
     if (cap < 1024) cap = 1024;
     L.cap = cap;
-    L.sb = s < kMaxBatchQ ? s : kMaxBatchQ;              // <= 4 query blocks per batch (<= 64 tile counters)
+    L.sb = s < kMaxBatchQ ? s : kMaxBatchQ;              // <= 4 query blocks per batch
     if (L.sb < 1) L.sb = 1;
     size_t o = 0;
-    L.off_chunkmin = o; o = align_up(o + (size_t)L.sb * L.g * sizeof(float), 256);
+    L.off_chunkmin = o; o = align_up(o + (size_t)L.sb * L.g_max * sizeof(float), 256);
     L.off_theta = o;    o = align_up(o + (size_t)L.sb * sizeof(float), 256);
     L.off_tau = o;      o = align_up(o + (size_t)L.sb * sizeof(float), 256);
-    L.off_counts = o;   o = align_up(o + ((size_t)L.sb + 64) * sizeof(uint32_t), 256);   // + tile counters (one per query block)
+    L.off_counts = o;   o = align_up(o + ((size_t)L.sb + 64) * sizeof(uint32_t), 256);
     L.off_stats = o;    o = align_up(o + 8 * sizeof(unsigned long long), 256);
     L.off_qcoef = o;    o = align_up(o + sizeof(float2) * 3 * (kMaxBatchQ / 2), 256);
+    L.off_ticket = o;   o = align_up(o + sizeof(unsigned int), 256);
     L.off_keys = o;     o = align_up(o + (size_t)L.sb * L.cap * sizeof(uint64_t), 256);
     L.total = o;
     return L;
 }
 
-// Phase A of the fast path (one query batch): bound -> threshold (+ coefficient pairs) -> constant
-// bank.  Reads the candidates from `mid`, or recomputes the sampled ones from (pos, edges) when
-// mid == nullptr, in which case nothing here depends on the spring kernel's output.
+// Size of the bound pass's candidate sample.  Expected filter passes of the scan: (k+1) * E / M per query, each a
+// ~50-instruction warp-level slow-path event; the bound pass costs ~56 warp instructions per sampled candidate (256
+// queries): the sum is minimal at M = sqrt(228 * (k+1) * E) ~ 15 * sqrt((k+1) * E).  `scale` > 1 buys a tighter bound
+// where the preparation is hidden behind other work (single GPU: it runs next to the spring kernel).
+inline int64_t bound_sample_size(int64_t e_bound, int kp1, float scale) {
+    double m = 15.0 * sqrt((double)kp1 * (double)e_bound) * (scale > 0.f ? scale : 1.f);
+    if (m < 8192.0) m = 8192.0;
+    if (m > (double)e_bound) m = (double)e_bound;
+    return (int64_t)m;
+}
+
+// Phase A of the fast path (one query batch): ONE fused launch (sample / query midpoints / line-graph bound /
+// stratified bound pass / thresholds / coefficient pairs, knn_prep_kernel) + the copy of the coefficient pairs into
+// constant-bank slot `slot`.  `ws_e` = the candidate count the scan that follows will see (it fixes the workspace
+// layout); the bound pass itself runs over A.e_bound candidates, which may be another (larger) set: the multi-GPU
+// path bounds with the WHOLE edge list, so every rank filters its shard with the same global thresholds.
 template <int D>
-int knn_prepare(const KnnLayout &L, char *w, const float *mid, const float *pos, const int2 *edges, int64_t e,
-                const float *qm, int sb, int kp1, const float *tau_hint, cudaStream_t st,
-                int64_t *bump_counter = nullptr) {
-    using CandT = typename MidT<D>::T;
-    float *chunkmin = reinterpret_cast<float *>(w + L.off_chunkmin);
-    float *theta = reinterpret_cast<float *>(w + L.off_theta);
-    float *tau = reinterpret_cast<float *>(w + L.off_tau);
-    uint32_t *counts = reinterpret_cast<uint32_t *>(w + L.off_counts);
-    float *qcoef = reinterpret_cast<float *>(w + L.off_qcoef);
-    GEM_CUDA(cudaMemsetAsync(counts, 0, ((size_t)L.sb + 64) * sizeof(uint32_t), st));
-    knn_bound_kernel<D><<<L.g, kThreads, 0, st>>>(reinterpret_cast<const CandT *>(mid), pos, edges, e, qm, sb,
-                                                  L.tiles_per_cta, chunkmin);
+int knn_prepare(const KnnLayout &L, char *w, PrepArgs A, int64_t bound_samples, int slot, cudaStream_t st) {
+    if (slot < 0 || slot >= kCoefSlots) return GEM_E_BADARG;
+    A.chunkmin = reinterpret_cast<float *>(w + L.off_chunkmin);
+    A.theta = reinterpret_cast<float *>(w + L.off_theta);
+    A.tau = reinterpret_cast<float *>(w + L.off_tau);
+    A.counts = reinterpret_cast<uint32_t *>(w + L.off_counts);
+    A.ncounts = (int)L.sb + 64;
+    A.qcoef = reinterpret_cast<float *>(w + L.off_qcoef);
+    A.ticket = reinterpret_cast<unsigned int *>(w + L.off_ticket);
+    int64_t m = bound_samples > 0 ? bound_samples : bound_sample_size(A.e_bound, A.kp1, 1.f);
+    if (m > A.e_bound) m = A.e_bound;
+    int64_t g = m / 64;
+    if (g < 64) g = 64;
+    if (g > L.g_max) g = L.g_max;
+    if (g > A.e_bound) g = A.e_bound;
+    A.g = (int)g;
+    A.per = (int)((m + g - 1) / g);
+    const bool lg = A.row_ptr != nullptr && A.col != nullptr && A.qmid_in == nullptr && A.hint_out != nullptr;
+    if (!lg) { A.row_ptr = nullptr; A.col = nullptr; }
+    const int grid = A.g + (lg ? (A.s + kWarps - 1) / kWarps : 0);
+    const size_t smem = (size_t)A.s * sizeof(float4) + (size_t)A.kp1 * kThreads * sizeof(float);
+    knn_prep_kernel<D><<<grid, kThreads, smem, st>>>(A);
     GEM_CHECK_LAUNCH();
-    stage_mark();                                                   // GEM_STAGE_KNN_BOUND
-    knn_threshold_kernel<D><<<(sb + kWarps - 1) / kWarps, kThreads, 0, st>>>(chunkmin, L.g, kp1, qm, sb, tau_hint, theta,
-                                                                             tau, qcoef, bump_counter);
-    GEM_CHECK_LAUNCH();
+    stage_mark();                                                   // GEM_STAGE_KNN_BOUND (the fused preparation)
     // query coefficients of this batch -> constant bank (uniform operands of the scan's packed FMAs)
-    GEM_CUDA(cudaMemcpyToSymbolAsync(c_qcoef, qcoef, sizeof(float2) * 3 * (kMaxBatchQ / 2), 0, cudaMemcpyDeviceToDevice, st));
-    stage_mark();                                                   // GEM_STAGE_KNN_THRESHOLD
+    GEM_CUDA(cudaMemcpyToSymbolAsync(c_qcoef, A.qcoef, sizeof(float2) * 3 * (kMaxBatchQ / 2),
+                                     (size_t)slot * sizeof(float2) * 3 * (kMaxBatchQ / 2), cudaMemcpyDeviceToDevice, st));
+    stage_mark();                                                   // GEM_STAGE_KNN_THRESHOLD (the copy)
     return GEM_OK;
 }
 
 // Phase B: scan (one launch per block of 256 queries) -> select (+ optional fused intersection forces)
 template <int D>
-int knn_scan_select(const KnnLayout &L, char *w, const float *mid, int64_t e, int64_t idx_offset, const float *qm, int sb,
-                    int kp1, int64_t *out_idx, float *out_dist, const FusedIntersect &fx, cudaStream_t st,
+int knn_scan_select(const KnnLayout &L, char *w, const float *mid, int64_t e, const float *qm, int sb, int kp1,
+                    const SelectOut &so, const FusedIntersect &fx, int slot, cudaStream_t st,
                     cudaEvent_t before_select = nullptr) {
     using CandT = typename MidT<D>::T;
+    if (slot < 0 || slot >= kCoefSlots) return GEM_E_BADARG;
     float *theta = reinterpret_cast<float *>(w + L.off_theta);
     float *tau = reinterpret_cast<float *>(w + L.off_tau);
     uint32_t *counts = reinterpret_cast<uint32_t *>(w + L.off_counts);
@@ -2035,12 +2229,12 @@ int knn_scan_select(const KnnLayout &L, char *w, const float *mid, int64_t e, in
     for (int qb = 0; qb * kQB < sb; ++qb) {        // S = 256: one launch
         knn_scan_kernel<D><<<L.g, kScanThreads, scan_smem, st>>>(
             reinterpret_cast<const CandT *>(mid), e, qm, sb, kp1, theta, tau, counts, keys, L.cap, counts + L.sb,
-            g_knn_stats ? reinterpret_cast<unsigned long long *>(w + L.off_stats) : nullptr, qb);
+            g_knn_stats ? reinterpret_cast<unsigned long long *>(w + L.off_stats) : nullptr, qb, slot);
         GEM_CHECK_LAUNCH();
     }
     stage_mark();                                                   // GEM_STAGE_KNN_SCAN
     if (before_select) GEM_CUDA(cudaStreamWaitEvent(st, before_select, 0));
-    knn_select_kernel<<<sb, kThreads, sel_smem, st>>>(counts, keys, L.cap, kp1, idx_offset, out_idx, out_dist, fx);
+    knn_select_kernel<<<sb, kThreads, sel_smem, st>>>(counts, keys, L.cap, kp1, so, fx);
     GEM_CHECK_LAUNCH();
     stage_mark();                                                   // GEM_STAGE_KNN_SELECT
     stage_mark();                                                   // GEM_STAGE_KNN_FALLBACK (none needed)
@@ -2053,7 +2247,8 @@ bool knn_fast_applicable(int mm, int d, int64_t e, int kp1) {
 
 template <int D>
 int knn_fast(const float *mid, int64_t e, int64_t idx_offset, const float *qmid, int64_t s, int kp1,
-             const float *tau_hint, int64_t *out_idx, float *out_dist, void *ws, size_t ws_bytes, cudaStream_t st) {
+             const float *tau_hint, int64_t *out_idx, float *out_dist, void *ws, size_t ws_bytes, int slot,
+             cudaStream_t st) {
     const KnnLayout L = knn_layout(e, s, kp1);
     if (ws == nullptr || ws_bytes < L.total || ((uintptr_t)ws & 255)) return GEM_E_WORKSPACE;
     if (((uintptr_t)mid & 15) || ((uintptr_t)qmid & 15)) return GEM_E_BADARG;
@@ -2063,9 +2258,14 @@ int knn_fast(const float *mid, int64_t e, int64_t idx_offset, const float *qmid,
     for (int64_t q0 = 0; q0 < s; q0 += L.sb) {
         const int sb = (int)((s - q0) < L.sb ? (s - q0) : L.sb);
         const float *qm = qmid + q0 * mld;
-        int rc = knn_prepare<D>(L, w, mid, nullptr, nullptr, e, qm, sb, kp1, tau_hint ? tau_hint + q0 : nullptr, st);
+        PrepArgs A = {};
+        A.qmid_in = qm; A.hint_in = tau_hint ? tau_hint + q0 : nullptr;
+        A.bound_mid = mid; A.e_bound = e; A.s = sb; A.kp1 = kp1;
+        int rc = knn_prepare<D>(L, w, A, 0, slot, st);
         if (rc) return rc;
-        rc = knn_scan_select<D>(L, w, mid, e, idx_offset, qm, sb, kp1, out_idx + q0 * kp1, out_dist + q0 * kp1, none, st);
+        SelectOut so = {};
+        so.idx = out_idx + q0 * kp1; so.dist = out_dist + q0 * kp1; so.idx_offset = idx_offset;
+        rc = knn_scan_select<D>(L, w, mid, e, qm, sb, kp1, so, none, slot, st);
         if (rc) return rc;
     }
     return GEM_OK;
@@ -2075,6 +2275,11 @@ int knn_fast(const float *mid, int64_t e, int64_t idx_offset, const float *qmid,
 constexpr int kMaxDevices = 64;
 struct AuxStream { cudaStream_t st = nullptr; cudaEvent_t fork = nullptr, join = nullptr, spring = nullptr, stats = nullptr; };
 AuxStream g_aux[kMaxDevices];
+// gem_layout_step enqueues on two streams with library-owned events: one enqueue at a time per process
+std::mutex g_step_mutex;
+// owners of the constant-bank coefficient slots, per device (gem_coef_slot_acquire / _release)
+bool g_slot_used[kMaxDevices][kCoefSlots];
+std::mutex g_slot_mutex;
 
 int resolve_mm_mode(int mm_mode, int64_t s, int64_t e) {
     if (mm_mode < 0) return (s > 25 || e > 25) ? 1 : 0;      // torch.cdist default compute_mode
@@ -2093,7 +2298,9 @@ int gem_abi_version(void) { return GEM_ABI_VERSION; }
 int gem_init(void) {
     int dev = 0, major = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return GEM_E_NODEVICE;
-    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess || major < 10)
+    // the library holds sm_100a code only: compute capability 10.x exactly (sm_12x parts would fail later with
+    // "no kernel image")
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess || major != 10)
         return GEM_E_NODEVICE;
     g_num_sms = 0;
     (void)num_sms();
@@ -2102,6 +2309,9 @@ int gem_init(void) {
     GEM_CUDA(cudaFuncSetAttribute(knn_scan_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)scan_smem_bytes(16, kMaxFastKp1)));
     GEM_CUDA(cudaFuncSetAttribute(knn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    const int prep_smem = kMaxBatchQ * (int)sizeof(float4) + kMaxFastKp1 * kThreads * (int)sizeof(float);
+    GEM_CUDA(cudaFuncSetAttribute(knn_prep_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, prep_smem));
+    GEM_CUDA(cudaFuncSetAttribute(knn_prep_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, prep_smem));
     if (dev >= 0 && dev < kMaxDevices && g_aux[dev].st == nullptr) {
         // the one exception to "the library owns nothing": a non-blocking side stream and two events, so
         // that gem_layout_step can run the KNN preparation concurrently with the spring kernel
@@ -2114,6 +2324,34 @@ int gem_init(void) {
     return GEM_OK;
 }
 
+int gem_abi_struct_sizes(size_t *out4) {
+    if (!out4) return GEM_E_BADARG;
+    out4[0] = sizeof(gem_plan); out4[1] = sizeof(gem_knn_prep_args); out4[2] = sizeof(gem_knn_publish);
+    out4[3] = sizeof(gem_merge_publish);
+    return GEM_OK;
+}
+
+int gem_coef_slots(void) { return kCoefSlots; }
+
+int gem_coef_slot_acquire(int *slot) {
+    if (!slot) return GEM_E_BADARG;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return GEM_E_NODEVICE;
+    std::lock_guard<std::mutex> lock(g_slot_mutex);
+    for (int i = 0; i < kCoefSlots; ++i)
+        if (!g_slot_used[dev][i]) { g_slot_used[dev][i] = true; *slot = i; return GEM_OK; }
+    return GEM_E_BUSY;
+}
+
+int gem_coef_slot_release(int slot) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return GEM_E_NODEVICE;
+    if (slot < 0 || slot >= kCoefSlots) return GEM_E_BADARG;
+    std::lock_guard<std::mutex> lock(g_slot_mutex);
+    g_slot_used[dev][slot] = false;
+    return GEM_OK;
+}
+
 const char *gem_error_string(int code) {
     switch (code) {
         case GEM_OK: return "ok";
@@ -2121,6 +2359,7 @@ const char *gem_error_string(int code) {
         case GEM_E_WORKSPACE: return "workspace too small or not 256-byte aligned";
         case GEM_E_KRANGE: return "selected index k out of range";
         case GEM_E_NODEVICE: return "no usable sm_100 CUDA device";
+        case GEM_E_BUSY: return "all constant-bank coefficient slots of this device are in use (close() an embedder)";
         default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown graphem_b200 error";
     }
 }
@@ -2147,7 +2386,12 @@ int gem_hub_degree(void) { return kHubDeg; }
 
 static int spring_csr_launch(const float *pos, const int64_t *row_ptr, const int32_t *col, const int64_t *up_ptr,
                              int64_t v_begin, int64_t v_end, const int32_t *hubs, int64_t n_hubs, int d, float k_attr,
-                             float l_min, float *force, float *mid, int64_t mid_base, bool fuse, void *stream) {
+                             float l_min, float *force, float *mid, int64_t mid_base, bool fuse, void *stream,
+                             const SpringPeers *peers = nullptr) {
+    SpringPeers sp = {};
+    if (peers) sp = *peers;
+    if (sp.world > 0 && !fuse) return GEM_E_BADARG;
+    if (sp.world > 0 && !force) force = sp.peers.p[0];
     if (!pos || !row_ptr || !col || !up_ptr || !force || v_begin < 0 || v_end < v_begin || n_hubs < 0 ||
         (n_hubs > 0 && !hubs) || (d != 2 && d != 3))
         return GEM_E_BADARG;
@@ -2169,7 +2413,7 @@ static int spring_csr_launch(const float *pos, const int64_t *row_ptr, const int
 #define GEM_SPRING_LAUNCH(DD, FF)                                                                                  \
     spring_csr_kernel<DD, FF><<<grid, kThreads, 0, st>>>(pos, row_ptr, col, up_ptr, v_begin, v_end, hubs, (int)n_hubs, \
                                                          -k_attr, l_min, force,                                       \
-                                                         reinterpret_cast<typename MidT<DD>::T *>(mid), mid_base)
+                                                         reinterpret_cast<typename MidT<DD>::T *>(mid), mid_base, sp)
     if (d == 2 && !f) GEM_SPRING_LAUNCH(2, false);
     if (d == 3 && !f) GEM_SPRING_LAUNCH(3, false);
     if (d == 2 && f) GEM_SPRING_LAUNCH(2, true);
@@ -2191,6 +2435,21 @@ int gem_spring_update_csr(const float *pos, const int64_t *row_ptr, const int32_
                           float l_min, float *newpos, float *mid, int64_t mid_base, void *stream) {
     return spring_csr_launch(pos, row_ptr, col, up_ptr, v_begin, v_end, hubs, n_hubs, d, k_attr, l_min, newpos, mid, mid_base,
                              true, stream);
+}
+
+int gem_spring_update_csr_push(const float *pos, const int64_t *row_ptr, const int32_t *col, const int64_t *up_ptr,
+                               int64_t v_begin, int64_t v_end, const int32_t *hubs, int64_t n_hubs, int d, float k_attr,
+                               float l_min, float *const *peer_raw_host, int world, float *mid, int64_t mid_base,
+                               void *stream) {
+    if (!peer_raw_host || world < 1 || world > kMaxPeers) return GEM_E_BADARG;
+    SpringPeers sp = {};
+    sp.world = world;
+    for (int r = 0; r < world; ++r) {
+        if (!peer_raw_host[r]) return GEM_E_BADARG;
+        sp.peers.p[r] = peer_raw_host[r];
+    }
+    return spring_csr_launch(pos, row_ptr, col, up_ptr, v_begin, v_end, hubs, n_hubs, d, k_attr, l_min, nullptr, mid, mid_base,
+                             true, stream, &sp);
 }
 
 int gem_sample_edges(uint64_t seed, int64_t *iter_counter, int bump_counter, int64_t e, int64_t s, int64_t *samp,
@@ -2255,37 +2514,17 @@ int gem_knn_linegraph_hint(const float *pos, const int64_t *row_ptr, const int32
     cudaStream_t st = (cudaStream_t)stream;
     const int2 *ed = reinterpret_cast<const int2 *>(edges);
     const int grid = (int)((s + kWarps - 1) / kWarps);
-    int64_t *sm = const_cast<int64_t *>(samp);            // draw == 0: only read
-    if (d == 2) knn_linegraph_hint_kernel<2><<<grid, kThreads, 0, st>>>(pos, row_ptr, col, ed, sm, (int)s, kp1, tau_hint, 0, 0, nullptr, 0, nullptr);
-    else knn_linegraph_hint_kernel<3><<<grid, kThreads, 0, st>>>(pos, row_ptr, col, ed, sm, (int)s, kp1, tau_hint, 0, 0, nullptr, 0, nullptr);
-    GEM_CHECK_LAUNCH();
-    return GEM_OK;
-}
-
-int gem_knn_query_prep(uint64_t seed, int64_t *iter_counter, int draw, const float *pos, const int64_t *row_ptr,
-                       const int32_t *col, const int32_t *edges, int64_t e, int64_t *samp, int64_t s, int d, int kp1,
-                       float *qmid, float *tau_hint, void *stream) {
-    if (!pos || !row_ptr || !col || !edges || !samp || !qmid || !tau_hint || s <= 0 || e <= 0 || kp1 <= 0 ||
-        (d != 2 && d != 3))
-        return GEM_E_BADARG;
-    cudaStream_t st = (cudaStream_t)stream;
-    const int2 *ed = reinterpret_cast<const int2 *>(edges);
-    const int grid = (int)((s + kWarps - 1) / kWarps);
-    if (d == 2)
-        knn_linegraph_hint_kernel<2><<<grid, kThreads, 0, st>>>(pos, row_ptr, col, ed, samp, (int)s, kp1, tau_hint, draw ? 1 : 0,
-                                                               seed, iter_counter, e, reinterpret_cast<float2 *>(qmid));
-    else
-        knn_linegraph_hint_kernel<3><<<grid, kThreads, 0, st>>>(pos, row_ptr, col, ed, samp, (int)s, kp1, tau_hint, draw ? 1 : 0,
-                                                               seed, iter_counter, e, reinterpret_cast<float4 *>(qmid));
+    if (d == 2) knn_linegraph_hint_kernel<2><<<grid, kThreads, 0, st>>>(pos, row_ptr, col, ed, samp, (int)s, kp1, tau_hint);
+    else knn_linegraph_hint_kernel<3><<<grid, kThreads, 0, st>>>(pos, row_ptr, col, ed, samp, (int)s, kp1, tau_hint);
     GEM_CHECK_LAUNCH();
     return GEM_OK;
 }
 
 int gem_knn_midpoints(const float *mid, int64_t e, int64_t idx_offset, int d, const float *qmid, int64_t s, int kp1,
                       int mm_mode, const float *tau_hint, int64_t *out_idx, float *out_dist, void *ws, size_t ws_bytes,
-                      void *stream) {
+                      int coef_slot, void *stream) {
     return gem_knn_midpoints_shard(mid, e, e, idx_offset, d, qmid, s, kp1, mm_mode, tau_hint, out_idx, out_dist, ws,
-                                   ws_bytes, stream);
+                                   ws_bytes, coef_slot, stream);
 }
 
 __global__ void knn_fill_empty_kernel(int64_t *__restrict__ out_idx, float *__restrict__ out_dist, int64_t total) {
@@ -2295,7 +2534,7 @@ __global__ void knn_fill_empty_kernel(int64_t *__restrict__ out_idx, float *__re
 
 int gem_knn_midpoints_shard(const float *mid, int64_t e, int64_t e_total, int64_t idx_offset, int d, const float *qmid,
                             int64_t s, int kp1, int mm_mode, const float *tau_hint, int64_t *out_idx, float *out_dist,
-                            void *ws, size_t ws_bytes, void *stream) {
+                            void *ws, size_t ws_bytes, int coef_slot, void *stream) {
     if (!qmid || !out_idx || !out_dist || e < 0 || e_total < e || s <= 0 || d <= 0 || kp1 <= 0) return GEM_E_BADARG;
     if (kp1 > e_total) return GEM_E_KRANGE;            // the reference's torch.topk error (:583) is about ALL candidates
     const int mm = resolve_mm_mode(mm_mode, s, e_total);
@@ -2320,8 +2559,8 @@ int gem_knn_midpoints_shard(const float *mid, int64_t e, int64_t e_total, int64_
     }
     if (e >= ((int64_t)1 << 32)) return GEM_E_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
-    return d == 2 ? knn_fast<2>(mid, e, idx_offset, qmid, s, kp1, tau_hint, out_idx, out_dist, ws, ws_bytes, st)
-                  : knn_fast<3>(mid, e, idx_offset, qmid, s, kp1, tau_hint, out_idx, out_dist, ws, ws_bytes, st);
+    return d == 2 ? knn_fast<2>(mid, e, idx_offset, qmid, s, kp1, tau_hint, out_idx, out_dist, ws, ws_bytes, coef_slot, st)
+                  : knn_fast<3>(mid, e, idx_offset, qmid, s, kp1, tau_hint, out_idx, out_dist, ws, ws_bytes, coef_slot, st);
 }
 
 int gem_knn_fast_path(int64_t e, int64_t e_total, int d, int64_t s, int kp1) {
@@ -2329,22 +2568,37 @@ int gem_knn_fast_path(int64_t e, int64_t e_total, int d, int64_t s, int kp1) {
     return (knn_fast_applicable(mm, d, e, kp1) && s <= kMaxBatchQ && kp1 <= e_total) ? 1 : 0;
 }
 
-int gem_knn_prepare(const float *mid, const float *pos, const int32_t *edges, int64_t e, int d, const float *qmid,
-                    int64_t s, int kp1, const float *tau_hint, int64_t *bump_counter, void *ws, size_t ws_bytes,
-                    void *stream) {
-    if (!qmid || e <= 0 || s <= 0 || kp1 <= 0 || (!mid && (!pos || !edges))) return GEM_E_BADARG;
-    if (!gem_knn_fast_path(e, e, d, s, kp1)) return GEM_E_BADARG;
-    const KnnLayout L = knn_layout(e, s, kp1);
-    if (ws == nullptr || ws_bytes < L.total || ((uintptr_t)ws & 255)) return GEM_E_WORKSPACE;
-    char *w = reinterpret_cast<char *>(ws);
-    const int2 *ed = reinterpret_cast<const int2 *>(edges);
+static PrepArgs prep_args_from(const gem_knn_prep_args *a) {
+    PrepArgs A = {};
+    A.pos = a->pos; A.edges = reinterpret_cast<const int2 *>(a->edges); A.e_total = a->e_total;
+    A.samp = a->samp; A.draw = a->draw ? 1 : 0; A.seed = a->seed; A.iter_counter = a->iter_counter; A.bump = a->bump ? 1 : 0;
+    A.qmid_in = a->qmid_in; A.qmid_out = a->qmid_out;
+    A.row_ptr = a->row_ptr; A.col = a->col; A.hint_in = a->tau_hint_in; A.hint_out = a->tau_hint_out;
+    A.bound_mid = a->bound_mid; A.bound_edges = reinterpret_cast<const int2 *>(a->bound_edges); A.e_bound = a->e_bound;
+    A.s = (int)a->s; A.kp1 = a->kp1;
+    return A;
+}
+
+int gem_knn_prep(const gem_knn_prep_args *a, void *stream) {
+    if (!a || a->e <= 0 || a->s <= 0 || a->kp1 <= 0 || a->e_bound <= 0) return GEM_E_BADARG;
+    if (a->qmid_in == nullptr && (!a->pos || !a->edges || !a->samp || !a->qmid_out || a->e_total <= 0)) return GEM_E_BADARG;
+    if (a->bound_mid == nullptr && (!a->pos || !a->bound_edges)) return GEM_E_BADARG;
+    if (a->draw && (a->qmid_in != nullptr)) return GEM_E_BADARG;
+    if (a->row_ptr != nullptr && a->qmid_in == nullptr && (!a->col || !a->tau_hint_out)) return GEM_E_BADARG;
+    if (!gem_knn_fast_path(a->e, a->e, a->d, a->s, a->kp1) || a->kp1 > a->e_bound) return GEM_E_BADARG;
+    const KnnLayout L = knn_layout(a->e, a->s, a->kp1);
+    if (a->ws == nullptr || a->ws_bytes < L.total || ((uintptr_t)a->ws & 255)) return GEM_E_WORKSPACE;
+    if (a->qmid_in && ((uintptr_t)a->qmid_in & 15)) return GEM_E_BADARG;
+    char *w = reinterpret_cast<char *>(a->ws);
     cudaStream_t st = (cudaStream_t)stream;
-    return d == 2 ? knn_prepare<2>(L, w, mid, pos, ed, e, qmid, (int)s, kp1, tau_hint, st, bump_counter)
-                  : knn_prepare<3>(L, w, mid, pos, ed, e, qmid, (int)s, kp1, tau_hint, st, bump_counter);
+    const PrepArgs A = prep_args_from(a);
+    return a->d == 2 ? knn_prepare<2>(L, w, A, a->bound_samples, a->coef_slot, st)
+                     : knn_prepare<3>(L, w, A, a->bound_samples, a->coef_slot, st);
 }
 
 int gem_knn_scan(const float *mid, int64_t e, int64_t idx_offset, int d, const float *qmid, int64_t s, int kp1,
-                 int64_t *out_idx, float *out_dist, void *ws, size_t ws_bytes, void *stream) {
+                 int64_t *out_idx, float *out_dist, void *ws, size_t ws_bytes, int coef_slot, const gem_knn_publish *pub,
+                 void *stream) {
     if (!mid || !qmid || !out_idx || !out_dist || e <= 0 || s <= 0 || kp1 <= 0) return GEM_E_BADARG;
     if (!gem_knn_fast_path(e, e, d, s, kp1)) return GEM_E_BADARG;
     const KnnLayout L = knn_layout(e, s, kp1);
@@ -2352,9 +2606,22 @@ int gem_knn_scan(const float *mid, int64_t e, int64_t idx_offset, int d, const f
     if (((uintptr_t)mid & 15) || ((uintptr_t)qmid & 15)) return GEM_E_BADARG;
     char *w = reinterpret_cast<char *>(ws);
     FusedIntersect none = {};
+    SelectOut so = {};
+    so.idx = out_idx; so.dist = out_dist; so.idx_offset = idx_offset;
+    if (pub) {
+        so.remap = pub->remap;
+        if (pub->world < 0 || pub->world > kMaxPeers || (pub->world > 0 && !pub->peer_base_host)) return GEM_E_BADARG;
+        if ((pub->idx_offset_bytes & 7) || (pub->dist_offset_bytes & 3)) return GEM_E_BADARG;
+        so.world = pub->world;
+        for (int r = 0; r < pub->world; ++r) {
+            if (!pub->peer_base_host[r]) return GEM_E_BADARG;
+            so.peers.p[r] = reinterpret_cast<float *>(pub->peer_base_host[r]);
+        }
+        so.peer_idx_off = pub->idx_offset_bytes; so.peer_dist_off = pub->dist_offset_bytes;
+    }
     cudaStream_t st = (cudaStream_t)stream;
-    return d == 2 ? knn_scan_select<2>(L, w, mid, e, idx_offset, qmid, (int)s, kp1, out_idx, out_dist, none, st)
-                  : knn_scan_select<3>(L, w, mid, e, idx_offset, qmid, (int)s, kp1, out_idx, out_dist, none, st);
+    return d == 2 ? knn_scan_select<2>(L, w, mid, e, qmid, (int)s, kp1, so, none, coef_slot, st)
+                  : knn_scan_select<3>(L, w, mid, e, qmid, (int)s, kp1, so, none, coef_slot, st);
 }
 
 int gem_topk_merge(const float *dists, const int64_t *idxs, int parts, int64_t s, int kp1, int64_t *out_idx,
@@ -2378,7 +2645,7 @@ int gem_topk_merge_strided(const float *dists, const int64_t *idxs, int64_t dist
 int gem_topk_merge_intersect(const float *dists, const int64_t *idxs, int64_t dist_stride, int64_t idx_stride, int parts,
                              int64_t s, int kp1, int64_t *out_idx, float *out_dist, const float *pos, const int32_t *edges,
                              const int64_t *samp, int d, float k_inter, int64_t v_begin, int64_t v_end, float *newpos,
-                             double *sums, void *stream) {
+                             double *sums, const gem_merge_publish *pub, void *stream) {
     if (!dists || !idxs || !out_idx || !out_dist || parts <= 0 || s <= 0 || kp1 <= 0 || kp1 > kMaxFastKp1) return GEM_E_BADARG;
     if (!pos || !edges || !samp || !newpos || !sums || (d != 2 && d != 3) || v_begin < 0 || v_end < v_begin) return GEM_E_BADARG;
     const int total = parts * kp1;
@@ -2389,8 +2656,28 @@ int gem_topk_merge_intersect(const float *dists, const int64_t *idxs, int64_t di
         fx.pos = pos; fx.edges = reinterpret_cast<const int2 *>(edges); fx.samp = samp; fx.force = newpos;
         fx.k_inter = k_inter; fx.d = d; fx.v_begin = (int)v_begin; fx.v_end = (int)v_end; fx.sums = sums;
     }
+    MergePublish mp = {};
+    if (pub && pub->world > 0) {
+        if (pub->world > kMaxPeers || pub->rank < 0 || pub->rank >= pub->world || !pub->peer_raw_host || !pub->peer_xchg_host ||
+            !pub->touched || !pub->counters || (pub->stats_offset_bytes & 7))
+            return GEM_E_BADARG;
+        mp.world = pub->world; mp.rank = pub->rank; mp.stats_off = pub->stats_offset_bytes;
+        for (int r = 0; r < pub->world; ++r) {
+            if (!pub->peer_raw_host[r] || !pub->peer_xchg_host[r]) return GEM_E_BADARG;
+            mp.raw.p[r] = pub->peer_raw_host[r];
+            mp.xchg.p[r] = reinterpret_cast<float *>(pub->peer_xchg_host[r]);
+        }
+        mp.ticket = pub->counters;                      // [0] ticket, [1] number of touched rows (both left at zero)
+        fx.touched.rows = pub->touched;
+        fx.touched.count = pub->counters + 1;
+        // the kernel indexes the raw buffers by padded vertex id; `newpos` is row v_begin of the rank's own one
+        if (v_end > v_begin && newpos != pub->peer_raw_host[pub->rank] + v_begin * row_pitch(d)) return GEM_E_BADARG;
+        if (fx.force == nullptr) {                      // a rank without rows / k = 0 still publishes its (zero) sums
+            fx.d = d; fx.sums = sums;
+        }
+    }
     topk_merge_intersect_kernel<<<(unsigned)s, kThreads, smem, (cudaStream_t)stream>>>(dists, idxs, dist_stride, idx_stride, parts,
-                                                                                       s, kp1, out_idx, out_dist, fx);
+                                                                                       s, kp1, out_idx, out_dist, fx, mp);
     GEM_CHECK_LAUNCH();
     return GEM_OK;
 }
@@ -2434,7 +2721,8 @@ int gem_update_positions(float *pos, const float *f_spring, const float *f_inter
     if ((uintptr_t)stats_ws & 255) return GEM_E_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     if (n_total <= 0) n_total = n;
-    const int grid = grid_for(n, 8);
+    int grid = grid_for(n, 8);
+    if (grid > kUpdBlocksMax) grid = kUpdBlocksMax;      // the fp64 partials area holds kUpdBlocksMax slots
     if (d == 2 || d == 3) {
         if (phase == 3) {                           // column sums of `pos` only (f_spring == NULL: nothing added or written)
             if (d == 2) update_pass1_kernel<2><<<grid, kThreads, 0, st>>>(pos, nullptr, nullptr, n, stats_ws);
@@ -2516,8 +2804,47 @@ int gem_update_normalise_push(float *const *peer_pos_host, int world, const floa
         if (!pp.p[r]) return GEM_E_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = grid_for(n, 8);
-    if (d == 2) update_pass2_bcast_kernel<2><<<grid, kThreads, 0, st>>>(pp, world, src, row_begin, n, n_total, d, stats_ws, rank_sums);
-    else update_pass2_bcast_kernel<4><<<grid, kThreads, 0, st>>>(pp, world, src, row_begin, n, n_total, d, stats_ws, rank_sums);
+    if (d == 2) update_pass2_bcast_kernel<2><<<grid, kThreads, 0, st>>>(pp, world, src, row_begin, n, n_total, d, stats_ws, rank_sums, world);
+    else update_pass2_bcast_kernel<4><<<grid, kThreads, 0, st>>>(pp, world, src, row_begin, n, n_total, d, stats_ws, rank_sums, world);
+    GEM_CHECK_LAUNCH();
+    return GEM_OK;
+}
+
+int gem_update_normalise_all(float *pos, const float *raw, int64_t n_rows, int64_t n_total, int d, const double *rank_sums,
+                             int slots, void *stream) {
+    if (!pos || !raw || n_rows <= 0 || n_total <= 0 || (d != 2 && d != 3) || !rank_sums || slots < 1 || slots > kMaxPeers)
+        return GEM_E_BADARG;
+    PeerPtrs pp = {};
+    pp.p[0] = pos;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = grid_for(n_rows, 8);
+    if (d == 2) update_pass2_bcast_kernel<2><<<grid, kThreads, 0, st>>>(pp, 1, raw, 0, n_rows, n_total, d, nullptr, rank_sums, slots);
+    else update_pass2_bcast_kernel<4><<<grid, kThreads, 0, st>>>(pp, 1, raw, 0, n_rows, n_total, d, nullptr, rank_sums, slots);
+    GEM_CHECK_LAUNCH();
+    return GEM_OK;
+}
+
+int gem_rows_scatter(const float *src, int64_t row0, int64_t cnt, int d, const int64_t *pad_index, float *const *peer_pos_host,
+                     int world, void *stream) {
+    if (!src || row0 < 0 || cnt < 0 || d <= 0 || !peer_pos_host || world < 1 || world > kMaxPeers) return GEM_E_BADARG;
+    if (cnt == 0) return GEM_OK;
+    PeerPtrs pp = {};
+    for (int r = 0; r < world; ++r) {
+        if (!peer_pos_host[r]) return GEM_E_BADARG;
+        pp.p[r] = peer_pos_host[r];
+    }
+    if (d == 2 && ((uintptr_t)src & 7)) return GEM_E_BADARG;
+    rows_scatter_kernel<<<(unsigned)((cnt + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        src, row0, cnt, d, row_pitch(d), pad_index, pp, world);
+    GEM_CHECK_LAUNCH();
+    return GEM_OK;
+}
+
+int gem_rows_gather(const float *pos, int64_t row0, int64_t cnt, int d, const int64_t *pad_index, float *out, void *stream) {
+    if (!pos || !out || row0 < 0 || cnt < 0 || d <= 0) return GEM_E_BADARG;
+    if (cnt == 0) return GEM_OK;
+    rows_gather_kernel<<<(unsigned)((cnt + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        pos, row0, cnt, d, row_pitch(d), pad_index, out);
     GEM_CHECK_LAUNCH();
     return GEM_OK;
 }
@@ -2533,16 +2860,21 @@ int gem_layout_step(const gem_plan *p, void *stream) {
     const int mm = resolve_mm_mode(p->mm_mode, p->s, p->e);
     const bool fast = knn_fast_applicable(mm, p->d, p->e, p->kp1) && p->s <= kMaxBatchQ;
     if (fast) {
-        // ---- fast path: [sample -> query midpoints -> line-graph hint -> bound -> threshold -> constant bank]
-        // depends on the positions only, so it runs on the side stream while the spring kernel streams the
-        // graph on the main one; the scan joins both.  The profiling variant runs the same launches in
-        // series on one stream so that the per-stage events mean something.
+        // ---- fast path: the whole KNN preparation (sample, query midpoints, line-graph bound, stratified bound pass,
+        // thresholds, coefficient pairs: ONE launch + the copy into the constant bank) depends on the positions only,
+        // so it runs on the side stream while the spring kernel streams the graph on the main one; the scan joins
+        // both.  The profiling variant runs the same launches in series on one stream so that the per-stage events
+        // mean something.
         const KnnLayout L = knn_layout(p->e, p->s, p->kp1);
         if (p->knn_ws == nullptr || p->knn_ws_bytes < L.total || ((uintptr_t)p->knn_ws & 255)) return GEM_E_WORKSPACE;
+        if (p->coef_slot < 0 || p->coef_slot >= kCoefSlots) return GEM_E_BADARG;
         char *w = reinterpret_cast<char *>(p->knn_ws);
         int dev = 0;
         GEM_CUDA(cudaGetDevice(&dev));
         const bool overlap = g_timer == nullptr && dev >= 0 && dev < kMaxDevices && g_aux[dev].st != nullptr;
+        // the side stream and its events are shared by every caller on this device: one enqueue at a time
+        std::unique_lock<std::mutex> lock(g_step_mutex, std::defer_lock);
+        if (overlap) lock.lock();
         cudaStream_t side = overlap ? g_aux[dev].st : main_st;
         const int2 *ed = reinterpret_cast<const int2 *>(p->edges);
         stage_mark();                                                   // start
@@ -2550,18 +2882,10 @@ int gem_layout_step(const gem_plan *p, void *stream) {
             GEM_CUDA(cudaEventRecord(g_aux[dev].fork, main_st));
             GEM_CUDA(cudaStreamWaitEvent(side, g_aux[dev].fork, 0));
         }
-        // sample + query midpoints + line-graph hint in ONE launch when the CSR is there (the counter is then
-        // bumped by the threshold kernel); separate launches otherwise
-        const bool fused_prep = have_hint && g_timer == nullptr;
-        int64_t *bump_later = nullptr;
-        if (!fused_prep && !p->external_sample) {
-            rc = gem_sample_edges(p->seed, p->iter_counter, 1, p->e, p->s, p->samp, side);
-            if (rc) return rc;
-        }
-        stage_mark();                                                   // GEM_STAGE_SAMPLE
-        // with the CSR arrays present the spring kernel also does update pass 1 (p->force := pos + F_spring, fp64
-        // column sums); the intersection forces are then added with a correction of the sums, and only the
-        // normalisation pass is left behind the KNN
+        stage_mark();                                                   // GEM_STAGE_SAMPLE (inside the fused preparation)
+        // with the CSR arrays present the spring kernel also does update pass 1 (p->force := pos + F_spring); the
+        // intersection forces are then added with a correction of the column sums, and only the normalisation
+        // pass is left behind the KNN
         const bool fuse = layout_can_fuse(p) && (((uintptr_t)p->stats_ws & 255) == 0);
         if (!overlap) {
             rc = layout_spring(p, main_st, fuse);
@@ -2572,31 +2896,19 @@ int gem_layout_step(const gem_plan *p, void *stream) {
             }
         }
         stage_mark();                                                   // GEM_STAGE_SPRING
-        if (fused_prep) {
-            const int grid = (int)((p->s + kWarps - 1) / kWarps);
-            const int draw = p->external_sample ? 0 : 1;
-            if (draw) bump_later = p->iter_counter;
-            if (p->d == 2)
-                knn_linegraph_hint_kernel<2><<<grid, kThreads, 0, side>>>(p->pos, p->row_ptr, p->col, ed, p->samp, (int)p->s, p->kp1,
-                                                                       p->tau_hint, draw, p->seed, p->iter_counter, p->e,
-                                                                       reinterpret_cast<float2 *>(p->qmid));
-            else
-                knn_linegraph_hint_kernel<3><<<grid, kThreads, 0, side>>>(p->pos, p->row_ptr, p->col, ed, p->samp, (int)p->s, p->kp1,
-                                                                       p->tau_hint, draw, p->seed, p->iter_counter, p->e,
-                                                                       reinterpret_cast<float4 *>(p->qmid));
-            GEM_CHECK_LAUNCH();
-        } else {
-            rc = gem_query_midpoints(p->pos, p->edges, p->samp, p->s, p->d, p->qmid, side);
-            if (rc) return rc;
-        }
-        stage_mark();                                                   // GEM_STAGE_QUERY_MID
-        if (have_hint && !fused_prep) {
-            rc = gem_knn_linegraph_hint(p->pos, p->row_ptr, p->col, p->edges, p->samp, p->s, p->d, p->kp1, p->tau_hint, side);
-            if (rc) return rc;
-        }
-        const float *hint = have_hint ? p->tau_hint : nullptr;
-        rc = p->d == 2 ? knn_prepare<2>(L, w, nullptr, p->pos, ed, p->e, p->qmid, (int)p->s, p->kp1, hint, side, bump_later)
-                       : knn_prepare<3>(L, w, nullptr, p->pos, ed, p->e, p->qmid, (int)p->s, p->kp1, hint, side, bump_later);
+        stage_mark();                                                   // GEM_STAGE_QUERY_MID (inside the fused preparation)
+        PrepArgs A = {};
+        A.pos = p->pos; A.edges = ed; A.e_total = p->e;
+        A.samp = p->samp; A.draw = p->external_sample ? 0 : 1; A.seed = p->seed; A.iter_counter = p->iter_counter;
+        A.bump = A.draw;
+        A.qmid_out = p->qmid;
+        if (have_hint) { A.row_ptr = p->row_ptr; A.col = p->col; A.hint_out = p->tau_hint; }
+        A.bound_edges = ed; A.e_bound = p->e;                           // midpoints recomputed from (pos, edges): no wait for `mid`
+        A.s = (int)p->s; A.kp1 = p->kp1;
+        // the preparation is hidden behind the spring kernel here: a 4x larger sample than the balanced size buys a
+        // tighter bound (fewer slow-path events inside the scan, which IS on the critical path)
+        const int64_t samples = bound_sample_size(p->e, p->kp1, overlap ? 4.f : 1.f);
+        rc = p->d == 2 ? knn_prepare<2>(L, w, A, samples, p->coef_slot, side) : knn_prepare<3>(L, w, A, samples, p->coef_slot, side);
         if (rc) return rc;
         if (overlap) {
             GEM_CUDA(cudaEventRecord(g_aux[dev].join, side));
@@ -2621,8 +2933,10 @@ int gem_layout_step(const gem_plan *p, void *stream) {
             fx.sums = fuse ? reinterpret_cast<double *>(p->stats_ws) : nullptr;
         }
         cudaEvent_t before_select = (fuse && overlap) ? g_aux[dev].stats : nullptr;
-        rc = p->d == 2 ? knn_scan_select<2>(L, w, p->mid, p->e, 0, p->qmid, (int)p->s, p->kp1, p->knn_idx, p->knn_dist, fx, main_st, before_select)
-                       : knn_scan_select<3>(L, w, p->mid, p->e, 0, p->qmid, (int)p->s, p->kp1, p->knn_idx, p->knn_dist, fx, main_st, before_select);
+        SelectOut so = {};
+        so.idx = p->knn_idx; so.dist = p->knn_dist;
+        rc = p->d == 2 ? knn_scan_select<2>(L, w, p->mid, p->e, p->qmid, (int)p->s, p->kp1, so, fx, p->coef_slot, main_st, before_select)
+                       : knn_scan_select<3>(L, w, p->mid, p->e, p->qmid, (int)p->s, p->kp1, so, fx, p->coef_slot, main_st, before_select);
         if (rc) return rc;
         stage_mark();                                                   // GEM_STAGE_INTERSECT (fused into the select kernel)
         if (fuse) {                                                     // normalise p->force (new positions) into p->pos
@@ -2657,7 +2971,7 @@ int gem_layout_step(const gem_plan *p, void *stream) {
         hint = p->tau_hint;
     }
     rc = gem_knn_midpoints(p->mid, p->e, 0, p->d, p->qmid, p->s, p->kp1, p->mm_mode, hint, p->knn_idx, p->knn_dist,
-                           p->knn_ws, p->knn_ws_bytes, stream);
+                           p->knn_ws, p->knn_ws_bytes, p->coef_slot, stream);
     if (rc) return rc;
     if (p->kp1 > 1) {
         // accumulate the repulsion straight into the spring accumulator: total = spring + inter (:796)

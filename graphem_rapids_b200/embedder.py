@@ -20,6 +20,7 @@ from __future__ import annotations
 
 import ctypes
 import logging
+import weakref
 from typing import Optional
 
 import numpy as np
@@ -36,6 +37,28 @@ _SUPPORTED_BACKENDS = (None, "auto", "pytorch", "cuda", "cuvs", "b200")
 
 def _ptr(t: Optional[torch.Tensor]):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _acquire_coef_slot(lib, device_index: int) -> int:
+    slot = ctypes.c_int(-1)
+    with torch.cuda.device(device_index):
+        rc = lib.gem_coef_slot_acquire(ctypes.byref(slot))
+        if rc != 0:                     # slots of unreachable embedders are released by their finalizers
+            import gc
+            gc.collect()
+            rc = lib.gem_coef_slot_acquire(ctypes.byref(slot))
+    if rc != 0:
+        raise RuntimeError(f"graphem_rapids_b200: {_cabi.error_string(rc)} -- at most {lib.gem_coef_slots()} embedders "
+                           f"can be alive per GPU; call close() on (or delete) the ones no longer needed")
+    return int(slot.value)
+
+
+def _release_coef_slot(lib, device_index: int, slot: int) -> None:
+    try:
+        with torch.cuda.device(device_index):
+            lib.gem_coef_slot_release(int(slot))
+    except Exception:  # interpreter shutdown  # pylint: disable=broad-exception-caught
+        pass
 
 
 class GraphEmbedderPyTorch:
@@ -108,6 +131,10 @@ class GraphEmbedderPyTorch:
         self._lib = _cabi.load()
         self._ld = self._lib.gem_row_pitch(int(n_components))
         self._mld = self._lib.gem_mid_pitch(int(n_components))
+        # constant-bank coefficient slot of this object's KNN scans (include/graphem_b200.h "Coefficient slots"):
+        # owned for the object's lifetime, so embedders on different streams of one GPU never share filter state
+        self._coef_slot = _acquire_coef_slot(self._lib, self.device.index)
+        self._slot_finalizer = weakref.finalize(self, _release_coef_slot, self._lib, self.device.index, self._coef_slot)
 
         if self.n >= 2 ** 31:
             raise ValueError("graphem_rapids_b200 stores edge endpoints as int32: n must be < 2^31")
@@ -145,6 +172,7 @@ class GraphEmbedderPyTorch:
         self._bufs = {}
         self._graph = None
         self._graph_key = None
+        self._torch_sample_ready = False
         self.last_sampled_indices = None
         self.last_knn_indices = None
 
@@ -263,37 +291,86 @@ class GraphEmbedderPyTorch:
     @property
     def _positions(self):
         """(n, d) positions on the device (reference attribute `_positions`): a view of the padded
-        buffer on one GPU, a gather of the valid rows when the vertex numbering is padded."""
+        buffer on one GPU with ld == d, a gather of the valid rows otherwise."""
+        if self._pad_index is None and self._ld == self.n_components:
+            return self._pos
         if self._pad_index is None:
             return self._pos[:, : self.n_components]
-        return self._pos[self._pad_index][:, : self.n_components]
+        return self._rows_to_public()
 
     @_positions.setter
     def _positions(self, value):
-        value = torch.as_tensor(value).to(device=self.device, dtype=torch.float32)
-        if value.shape != (self.n, self.n_components):
+        value = torch.as_tensor(value)
+        if tuple(value.shape) != (self.n, self.n_components):
             raise ValueError(f"positions must have shape {(self.n, self.n_components)}, got {tuple(value.shape)}")
-        buf = torch.zeros((self._layout.n_pad, self._ld), device=self.device, dtype=torch.float32)
-        if self._pad_index is None:
-            buf[:, : self.n_components] = value
-        else:
-            buf[self._pad_index, : self.n_components] = value
-        if getattr(self, "_pos", None) is not None and self._pos.shape == buf.shape:
-            self._pos.copy_(buf)            # keep the address: captured CUDA graphs stay valid
-        else:
-            self._pos = buf
-            self._graph = None
+        self._public_to_rows(value)
+
+    def _io_stage(self, name="io_stage"):
+        """(n, d) fp32 device staging buffer of the positions setter / getter (allocated once)."""
+        st = getattr(self, "_io_bufs", None)
+        if st is None:
+            st = self._io_bufs = {}
+        if name not in st:
+            st[name] = torch.empty((self.n, self.n_components), device=self.device, dtype=torch.float32)
+        return st[name]
+
+    def _pinned_stage(self):
+        st = getattr(self, "_io_bufs", None)
+        if st is None:
+            st = self._io_bufs = {}
+        if "pinned" not in st:
+            st["pinned"] = torch.empty((self.n, self.n_components), dtype=torch.float32, pin_memory=True)
+        return st["pinned"]
+
+    def _replica_ptrs(self):
+        """Device pointers of every replica of the position buffer the setter must fill (one here)."""
+        return (ctypes.c_void_p * 1)(self._pos.data_ptr()), 1
+
+    def _public_to_rows(self, value: torch.Tensor, row0: int = 0):
+        """(cnt, d) rows [row0, row0+cnt) of the public array (host or device tensor) -> padded (n_pad, ld) rows of
+        the position buffer: one H2D copy (asynchronous when the source is pinned) + gem_rows_scatter."""
+        d = self.n_components
+        cnt = int(value.shape[0])
+        with torch.cuda.device(self.device):
+            if value.device.type == "cuda":
+                src = value.to(device=self.device, dtype=torch.float32).contiguous()
+            else:
+                v = value.to(torch.float32).contiguous()
+                if self._ld == d and self._pad_index is None and row0 == 0 and cnt == self.n:
+                    self._pos.copy_(v, non_blocking=True)            # layout already matches: straight into place
+                    return
+                src = self._io_stage()[row0: row0 + cnt]
+                src.copy_(v, non_blocking=True)
+            ptrs, world = self._replica_ptrs()
+            _cabi.check(self._lib.gem_rows_scatter(_ptr(src), row0, cnt, d, _ptr(self._pad_index), ptrs, world,
+                                                   self._stream()), "gem_rows_scatter")
+
+    def _rows_to_public(self, row0: int = 0, cnt: Optional[int] = None, out: Optional[torch.Tensor] = None):
+        """Rows [row0, row0+cnt) of the public (n, d) array as a device tensor (gem_rows_gather)."""
+        cnt = self.n - row0 if cnt is None else int(cnt)
+        if out is None:
+            out = torch.empty((cnt, self.n_components), device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.gem_rows_gather(_ptr(self._pos), row0, cnt, self.n_components, _ptr(self._pad_index),
+                                                  _ptr(out), self._stream()), "gem_rows_gather")
+        return out
 
     @property
     def positions(self):
-        """numpy copy (:324-327)."""
-        return self._positions.detach().cpu().numpy()
+        """numpy copy (:324-327): a fresh host array, like the reference's `.cpu().numpy()`."""
+        if self.n * self.n_components < 65536:
+            return self._positions.detach().cpu().numpy()
+        # large layouts: gather -> pinned staging (full-speed D2H) -> fresh pageable array filled by torch's
+        # multi-threaded host copy
+        pinned = self._pinned_stage()
+        self.read_positions(pinned)
+        return torch.empty_like(pinned, pin_memory=False).copy_(pinned).numpy()
 
     @positions.setter
     def positions(self, value):
         """ndarray or tensor -> device (:329-335)."""
         if isinstance(value, np.ndarray):
-            value = torch.tensor(value, dtype=torch.float32)
+            value = torch.from_numpy(np.ascontiguousarray(value, dtype=np.float32))
         self._positions = value
 
     def _compute_laplacian_embedding(self):
@@ -417,6 +494,7 @@ class GraphEmbedderPyTorch:
             qmid=torch.zeros((max(S, 1), self._mld), device=dev, dtype=f32),
             tau_hint=torch.zeros((max(S, 1),), device=dev, dtype=f32),
             samp=torch.zeros((max(S, 1),), device=dev, dtype=torch.long),
+            samp_next=torch.zeros((max(S, 1),), device=dev, dtype=torch.long),
             knn_idx=torch.zeros((max(S, 1), kp1), device=dev, dtype=torch.long),
             knn_dist=torch.zeros((max(S, 1), kp1), device=dev, dtype=f32),
             iter=self._bufs.get("iter", torch.zeros((1,), device=dev, dtype=torch.long)),
@@ -425,6 +503,7 @@ class GraphEmbedderPyTorch:
             knn_ws_bytes=ws_bytes.value,
         )
         self._graph = None
+        self._torch_sample_ready = False
         return self._bufs
 
     def _plan(self, external_sample: bool) -> _cabi.GemPlan:
@@ -455,9 +534,20 @@ class GraphEmbedderPyTorch:
         p.stats_ws = b["stats_ws"].data_ptr()
         p.external_sample = 1 if external_sample else 0
         p.mm_mode = -1
+        p.coef_slot = self._coef_slot
         return p
 
     # ------------------------------------------------------------------ the hot path
+    # torch.randperm offloads n < 30000 to the CPU generator + a synchronous copy (not capturable); graphs with the
+    # torch sampler are only built above this size
+    _TORCH_SAMPLER_GRAPH_MIN_E = 65536
+
+    def _draw_torch_sample(self, out: torch.Tensor):
+        """The reference's draw (embedder_pytorch.py:404-413): torch.randperm(E, device)[:S] from the seeded
+        default generator (or arange(E) when S == E) -> out."""
+        E, S = self.n_edges, out.numel()
+        out.copy_(torch.randperm(E, device=self.device)[:S] if S < E else torch.arange(E, device=self.device))
+
     def update_positions(self, sampled_indices=None):
         """One layout iteration (embedder_pytorch.py:776-806) = one gem_layout_step call.
 
@@ -474,9 +564,12 @@ class GraphEmbedderPyTorch:
                 raise ValueError(f"sampled_indices must have {b['S']} entries, got {s.numel()}")
             b["samp"].copy_(s)
         elif self.sampler == "torch":
-            E, S = self.n_edges, b["S"]
-            b["samp"].copy_(torch.randperm(E, device=self.device)[:S] if S < E
-                            else torch.arange(E, device=self.device))       # :408-413
+            with torch.cuda.device(self.device):
+                if self._torch_sample_ready:             # drawn ahead by the last graph replay: next in the RNG stream
+                    b["samp"].copy_(b["samp_next"])
+                    self._torch_sample_ready = False
+                else:
+                    self._draw_torch_sample(b["samp"])                       # :408-413
         plan = self._plan(external)
         with torch.cuda.device(self.device):
             _cabi.check(self._lib.gem_layout_step(ctypes.byref(plan), self._stream()), "gem_layout_step")
@@ -501,22 +594,53 @@ class GraphEmbedderPyTorch:
         self.fp32_peak_flops_packed = float(out2.value)
         return float(out.value)
 
+    def _graph_ok(self) -> bool:
+        """Can run_layout replay a captured iteration?  Always with the device sampler; with sampler='torch' when
+        torch.randperm itself is capturable (E large enough to stay on the device)."""
+        if not self.use_cuda_graph or self.n_neighbors + 1 > self.n_edges:
+            return False
+        if self.sampler == "device":
+            return True
+        return self.n_edges >= self._TORCH_SAMPLER_GRAPH_MIN_E and not getattr(self, "_torch_graph_failed", False)
+
     def _run_graph(self, num_iterations: int) -> bool:
-        """Replay one captured iteration `num_iterations` times (device sampler only)."""
+        """Replay one captured iteration `num_iterations` times.
+
+        sampler='torch': the sample of iteration t+1 depends on nothing in iteration t, so the captured graph draws it
+        (torch.randperm from the default generator, registered with the graph) on a side stream WHILE iteration t
+        runs and hands it over at the start of the next replay; the very first sample is drawn eagerly.  The samples
+        are the reference's RNG stream in order (`seed=s` reproduces embedder_pytorch.py:409); one sample is always
+        drawn ahead."""
         b = self._buffers()
-        key = (self._pos.data_ptr(), b["key"], float(self.k_attr), float(self.L_min), float(self.k_inter))
+        torch_samp = self.sampler == "torch"
+        key = (self._pos.data_ptr(), b["key"], float(self.k_attr), float(self.L_min), float(self.k_inter), self.sampler)
+        if torch_samp and not self._torch_sample_ready:      # first use, or an eager step consumed the one drawn ahead
+            self._draw_torch_sample(b["samp_next"])
+            self._torch_sample_ready = True
         if self._graph is None or self._graph_key != key:
-            plan = self._plan(False)
+            plan = self._plan(torch_samp)
             graph = torch.cuda.CUDAGraph()
             torch.cuda.synchronize(self.device)
             it0 = b["iter"].clone()
             pos0 = self._pos.clone()
+            next0 = b["samp_next"].clone()
+            torch.cuda.synchronize(self.device)
             with torch.cuda.graph(graph):
+                if torch_samp:
+                    cur = torch.cuda.current_stream(self.device)
+                    b["samp"].copy_(b["samp_next"])
+                    side = torch.cuda.Stream(device=self.device)
+                    side.wait_stream(cur)
+                    with torch.cuda.stream(side):
+                        self._draw_torch_sample(b["samp_next"])
                 rc = self._lib.gem_layout_step(ctypes.byref(plan), self._stream())
+                if torch_samp:
+                    cur.wait_stream(side)
             _cabi.check(rc, "gem_layout_step (capture)")
             # capture does not execute, but keep state exactly as it was in any case
             b["iter"].copy_(it0)
             self._pos.copy_(pos0)
+            b["samp_next"].copy_(next0)
             self._graph, self._graph_key = graph, key
         for _ in range(num_iterations):
             self._graph.replay()
@@ -531,9 +655,9 @@ class GraphEmbedderPyTorch:
         if self.n_edges == 0 and num_iterations > 0:
             raise RuntimeError("selected index k out of range")
         with torch.cuda.device(self.device):
-            if self.use_cuda_graph and self.sampler == "device" and num_iterations > 1:
-                if self.n_neighbors + 1 > self.n_edges:
-                    raise RuntimeError("selected index k out of range")
+            if self.n_neighbors + 1 > self.n_edges and num_iterations > 0:
+                raise RuntimeError("selected index k out of range")
+            if num_iterations > 1 and self._graph_ok():
                 self._run_graph(int(num_iterations))
             else:
                 for _ in range(int(num_iterations)):
@@ -546,42 +670,31 @@ class GraphEmbedderPyTorch:
         """embedder_pytorch.py:835-844."""
         return self.positions
 
-    # host-buffer fast paths of the positions setter / getter (extensions; bench.py e2e)
+    # host-buffer fast paths of the positions setter / getter (extensions)
     def load_positions(self, host_positions: torch.Tensor):
-        """Asynchronous H2D of an (n, d) fp32 host tensor (pinned for full speed) into the device state."""
+        """Asynchronous H2D of an (n, d) fp32 host tensor (pinned for full speed) into the device state
+        (what `emb.positions = tensor` does, minus the shape/dtype conversions)."""
         d = self.n_components
         if tuple(host_positions.shape) != (self.n, d) or host_positions.dtype != torch.float32:
             raise ValueError(f"expected an fp32 tensor of shape {(self.n, d)}")
-        if self._ld == d and self._pad_index is None:
-            self._pos.copy_(host_positions, non_blocking=True)
-            return
-        stage = self._bufs.get("h2d_stage")
-        if stage is None or stage.shape != host_positions.shape:
-            stage = torch.empty((self.n, d), device=self.device, dtype=torch.float32)
-            self._bufs["h2d_stage"] = stage
-        stage.copy_(host_positions, non_blocking=True)
-        if self._pad_index is None:
-            self._pos[:, :d].copy_(stage)
-        else:
-            self._pos[self._pad_index, :d] = stage
+        self._public_to_rows(host_positions)
 
     def read_positions(self, out: torch.Tensor):
-        """D2H of the current positions into an (n, d) fp32 host tensor, then stream sync."""
+        """D2H of the current positions into an (n, d) fp32 host tensor (pinned for full speed), then stream sync."""
         d = self.n_components
-        if self._ld == d and self._pad_index is None:
-            out.copy_(self._pos, non_blocking=True)
-        else:
-            stage = self._bufs.get("d2h_stage")
-            if stage is None or stage.shape != out.shape:
-                stage = torch.empty((self.n, d), device=self.device, dtype=torch.float32)
-                self._bufs["d2h_stage"] = stage
-            if self._pad_index is None:
-                stage.copy_(self._pos[:, :d])
+        with torch.cuda.device(self.device):
+            if self._ld == d and self._pad_index is None:
+                out.copy_(self._pos, non_blocking=True)
             else:
-                stage.copy_(self._pos[self._pad_index][:, :d])
-            out.copy_(stage, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
+                out.copy_(self._rows_to_public(out=self._io_stage("d2h_stage")), non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
         return out
+
+    def close(self):
+        """Release the object's coefficient slot and captured graph (also done when it is garbage collected)."""
+        self._graph = None
+        if getattr(self, "_slot_finalizer", None) is not None:
+            self._slot_finalizer()
 
     def run_layout_device(self, num_iterations=100):
         """run_layout without the final device->host copy (positions stay in HBM).  Replays the captured
@@ -589,7 +702,7 @@ class GraphEmbedderPyTorch:
         with torch.cuda.device(self.device):
             if self.n_edges == 0 or self.n_neighbors + 1 > self.n_edges:
                 raise RuntimeError("selected index k out of range")
-            if self.use_cuda_graph and self.sampler == "device" and (num_iterations > 1 or self._graph is not None):
+            if self._graph_ok() and (num_iterations > 1 or self._graph is not None):
                 self._run_graph(int(num_iterations))
             else:
                 for _ in range(int(num_iterations)):
@@ -606,8 +719,15 @@ class GraphEmbedderPyTorch:
         return buf
 
     def _edges_as_int32(self, edges: torch.Tensor) -> torch.Tensor:
+        """int32 copy of an edge tensor in the CALLER's vertex numbering.  `self._edges32` may only stand in for
+        `self.edges` when the device numbering is the identity: with several ranks it holds PADDED ids, while the
+        private stage methods take positions indexed by original ids."""
         if edges is self.edges:
-            return self._edges32
+            if self._pad_index is None:
+                return self._edges32
+            if getattr(self, "_edges32_public", None) is None:
+                self._edges32_public = self.edges.to(device=self.device, dtype=torch.int32).contiguous()
+            return self._edges32_public
         return edges.to(device=self.device, dtype=torch.int32).contiguous()
 
     def _spring_stage(self, positions, edges, want_mid):
@@ -667,7 +787,8 @@ class GraphEmbedderPyTorch:
                 _cabi.check(self._lib.gem_knn_workspace_bytes(nr, int(d), nq, int(k), ctypes.byref(nbytes)))
                 ws = torch.zeros((nbytes.value + 256,), device=self.device, dtype=torch.uint8)
                 _cabi.check(self._lib.gem_knn_midpoints(_ptr(rm), nr, 0, int(d), _ptr(qm), nq, int(k), -1, None, _ptr(idx),
-                                                        _ptr(dist), _ptr(ws), nbytes.value, st), "gem_knn_midpoints")
+                                                        _ptr(dist), _ptr(ws), nbytes.value, self._coef_slot, st),
+                            "gem_knn_midpoints")
         return (idx, dist) if return_distances else idx
 
     def _compute_knn_chunked(self, query_points, reference_points, k):

@@ -12,6 +12,24 @@ import numpy as np
 import scipy.sparse as sp
 
 
+def _sym_from_sorted_upper(lo, hi, n):
+    """Symmetric 0/1 CSR adjacency from the distinct pairs lo < hi, already sorted by (lo, hi): the upper triangle IS
+    a canonical CSR (indptr = offsets of lo, indices = hi); its transpose (scipy's O(E) counting sort in C) is the
+    lower triangle with sorted rows, and the canonical sum of both is the adjacency.  No Python-level sort."""
+    e = len(lo)
+    idx_t = np.int32 if n < 2 ** 31 and 2 * e < 2 ** 31 else np.int64
+    indptr = np.concatenate([[0], np.cumsum(np.bincount(lo, minlength=n))]).astype(idx_t)
+    upper = sp.csr_matrix((np.ones(e, dtype=np.int64), hi.astype(idx_t), indptr), shape=(n, n))
+    upper.has_sorted_indices = True
+    upper.has_canonical_format = True
+    lower = upper.T.tocsr()
+    lower.has_sorted_indices = True
+    lower.has_canonical_format = True
+    adj = (upper + lower).tocsr()
+    adj.sort_indices()
+    return adj
+
+
 def _to_adjacency(src, dst, n):
     """Undirected simple graph from endpoint arrays: drop loops, dedupe, symmetrise."""
     src = np.asarray(src, dtype=np.int64)
@@ -19,20 +37,47 @@ def _to_adjacency(src, dst, n):
     keep = src != dst
     lo = np.minimum(src[keep], dst[keep])
     hi = np.maximum(src[keep], dst[keep])
-    key = np.unique(lo * n + hi)
-    lo, hi = key // n, key % n
-    rows = np.concatenate([lo, hi])
-    cols = np.concatenate([hi, lo])
-    adj = sp.csr_matrix((np.ones(len(rows), dtype=np.int64), (rows, cols)), shape=(n, n))
-    adj.sort_indices()
-    return adj
+    key = np.unique(lo * n + hi)                      # sorted by (lo, hi)
+    return _sym_from_sorted_upper(key // n, key % n, n)
+
+
+_ER_SORTED_MIN_EDGES = 5_000_000
+
+
+def _er_sorted_pairs(n, m, rng):
+    """m (minus the rare collisions) distinct unordered pairs of [0, n), SORTED by (i, j), without a sort: the order
+    statistics of m uniforms are the normalised partial sums of m+1 exponentials; each value picks the pair with
+    that rank in the row-major enumeration of the upper triangle."""
+    total = n * (n - 1) // 2
+    c = np.cumsum(rng.exponential(size=m + 1))
+    r = np.floor(c[:-1] * (total / c[-1])).astype(np.int64)
+    r = np.minimum(r, total - 1)
+    r = r[np.concatenate([[True], r[1:] != r[:-1]])]              # collisions are consecutive
+    # rank -> (i, j): row i starts at off(i) = i*(2n-i-1)/2
+    t = 2.0 * n - 1.0
+    i = np.floor((t - np.sqrt(np.maximum(t * t - 8.0 * r.astype(np.float64), 0.0))) / 2.0).astype(np.int64)
+    i = np.clip(i, 0, n - 2)
+    for _ in range(3):                                             # float64 rounding: fix by +-1
+        off = i * (2 * n - i - 1) // 2
+        i = np.where(off > r, i - 1, i)
+        off_next = (i + 1) * (2 * n - i - 2) // 2
+        i = np.where(off_next <= r, i + 1, i)
+    off = i * (2 * n - i - 1) // 2
+    j = i + 1 + (r - off)
+    assert np.all((off <= r) & (j < n) & (j > i))
+    return i, j
 
 
 def erdos_renyi_graph(n, p, seed=0):
-    """G(n, p): draw m ~ Binomial(n(n-1)/2, p) distinct unordered pairs (generators.py:32-49)."""
+    """G(n, p): draw m ~ Binomial(n(n-1)/2, p) distinct unordered pairs (generators.py:32-49).  Small graphs
+    (fewer than 5 M edges) keep round 1's rejection sampler (same graphs as before); large ones take the sort-free
+    order-statistics sampler."""
     rng = np.random.default_rng(seed)
     total = n * (n - 1) // 2
     m = int(rng.binomial(total, p)) if total < 2 ** 62 else int(total * p)
+    if m >= _ER_SORTED_MIN_EDGES:
+        lo, hi = _er_sorted_pairs(n, m, rng)
+        return _sym_from_sorted_upper(lo, hi, n)
     got = np.empty(0, dtype=np.int64)
     while len(got) < m:
         need = int((m - len(got)) * 1.1) + 16

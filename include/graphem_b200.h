@@ -34,15 +34,19 @@
 extern "C" {
 #endif
 
-#define GEM_ABI_VERSION 2
+#define GEM_ABI_VERSION 3
 
 #define GEM_OK 0
 #define GEM_E_BADARG (-1)      /* null pointer, negative size, unsupported d */
 #define GEM_E_WORKSPACE (-2)   /* workspace too small / misaligned */
 #define GEM_E_KRANGE (-3)      /* k+1 > number of candidates (the reference's topk RuntimeError) */
 #define GEM_E_NODEVICE (-4)    /* no sm_100 device / kernel image not loadable */
+#define GEM_E_BUSY (-5)        /* gem_coef_slot_acquire: every coefficient slot of the device is owned */
 
 int gem_abi_version(void);
+/* sizeof of the four parameter structs below, in declaration order (gem_plan, gem_knn_prep_args, gem_knn_publish,
+ * gem_merge_publish): lets a foreign-language binding verify its mirror of the layouts at load time. */
+int gem_abi_struct_sizes(size_t *out4);
 /* Once per process and device, before the first launch (sets kernel attributes, creates the side
  * stream of gem_layout_step; not capturable). */
 int gem_init(void);
@@ -81,6 +85,19 @@ int gem_spring_midpoints_csr(const float *pos, const int64_t *row_ptr, const int
 int gem_spring_update_csr(const float *pos, const int64_t *row_ptr, const int32_t *col, const int64_t *up_ptr,
                           int64_t v_begin, int64_t v_end, const int32_t *hubs, int64_t n_hubs, int d,
                           float k_attr, float l_min, float *newpos, float *mid, int64_t mid_base, void *stream);
+/* Multi-GPU form of gem_spring_update_csr, fused with the exchange of the updated positions: the new row
+ * pos + F_spring of every vertex v in [v_begin, v_end) is stored at row v of EACH of the `world` raw
+ * (unnormalised) position buffers peer_raw_host[r] (host array of device pointers: the rank's own buffer and the
+ * peers' buffers mapped into this process, e.g. torch.distributed._symmetric_memory buffer_ptrs).  The stores to
+ * the peers travel over NVLink P2P while the rank goes on with its KNN scan: the all-gather of the positions is
+ * the store phase of the FIRST kernel of the iteration, not a collective behind the last one.  Rows that later
+ * receive intersection forces are re-published by gem_topk_merge_intersect; after one cross-rank barrier every rank
+ * normalises all rows locally (gem_update_normalise_push with world = 1).  The caller double-buffers the raw
+ * buffers by iteration parity (a fast rank may start iteration t+1 while a slow one still normalises t). */
+int gem_spring_update_csr_push(const float *pos, const int64_t *row_ptr, const int32_t *col, const int64_t *up_ptr,
+                               int64_t v_begin, int64_t v_end, const int32_t *hubs, int64_t n_hubs, int d,
+                               float k_attr, float l_min, float *const *peer_raw_host, int world, float *mid,
+                               int64_t mid_base, void *stream);
 
 /* Sampling of the query edges.  Replaces `torch.randperm(E, device)[:S]` / `arange(E)`
  * (_locate_knn_midpoints, :404-413) by a keyed bijection of [0,e) evaluated at 0..s-1
@@ -105,41 +122,79 @@ int gem_query_midpoints(const float *pos, const int32_t *edges, const int64_t *s
 int gem_knn_workspace_bytes(int64_t e, int d, int64_t s, int kp1, size_t *bytes);
 int gem_knn_midpoints(const float *mid, int64_t e, int64_t idx_offset, int d, const float *qmid,
                       int64_t s, int kp1, int mm_mode, const float *tau_hint, int64_t *out_idx,
-                      float *out_dist, void *ws, size_t ws_bytes, void *stream);
+                      float *out_dist, void *ws, size_t ws_bytes, int coef_slot, void *stream);
 /* Shard-local form for the multi-GPU path: `mid` holds e of the e_total candidates of the whole
  * problem (ids idx_offset .. idx_offset+e-1).  The k-range check and torch.cdist's mode choice use
  * e_total; rows with fewer than kp1 local candidates (or none: e == 0, mid may be NULL) are padded
  * with (distance +inf, index -1), which gem_topk_merge orders last. */
 int gem_knn_midpoints_shard(const float *mid, int64_t e, int64_t e_total, int64_t idx_offset, int d,
                             const float *qmid, int64_t s, int kp1, int mm_mode, const float *tau_hint,
-                            int64_t *out_idx, float *out_dist, void *ws, size_t ws_bytes, void *stream);
-/* The two phases of the fast path of gem_knn_midpoints[_shard] as separate calls, for callers that
- * overlap them with other work (gem_layout_step does so internally; the multi-GPU host does it with
- * its own side stream):
- *   gem_knn_prepare  bound pass -> thresholds -> query coefficients into the constant bank (and, when
- *                    bump_counter != NULL, *bump_counter += 1: see gem_knn_query_prep).  With
- *                    mid == NULL the sampled candidates are recomputed from (pos, edges) -- `edges`
- *                    points at the first of the e local edges -- so the call depends on the positions
- *                    only and can run while the spring kernel is still producing `mid`;
- *   gem_knn_scan     all-pairs scan + select -> (s, kp1) lists (short rows padded with +inf / -1).
+                            int64_t *out_idx, float *out_dist, void *ws, size_t ws_bytes, int coef_slot, void *stream);
+/* Coefficient slots.  The scan reads the query coefficients (-2q) as uniform-register operands from a __constant__
+ * table; the table has gem_coef_slots() independent slots per device, and every KNN entry point below takes the
+ * slot it may use (`coef_slot`).  An object that issues KNN work owns one slot for its lifetime
+ * (gem_coef_slot_acquire on the current device -> 0 .. slots-1, or GEM_E_BUSY; gem_coef_slot_release), so two
+ * embedders (or two captured CUDA graphs) on different streams of one GPU never share filter coefficients.
+ * (Round 1 had ONE table per device: concurrent KNNs silently filtered with each other's queries.) */
+int gem_coef_slots(void);
+int gem_coef_slot_acquire(int *slot);
+int gem_coef_slot_release(int slot);
+
+/* The two phases of the fast path of gem_knn_midpoints[_shard] as separate calls, for callers that overlap them
+ * with other work (gem_layout_step does so internally; the multi-GPU host does it with its own side stream).
+ *
+ * gem_knn_prep -- ONE kernel launch + one device-to-device copy: draws the sample (draw != 0: the keyed bijection of
+ *   gem_sample_edges from (seed, *iter_counter); bump != 0: *iter_counter += 1 at the end), computes the query
+ *   midpoints from (pos, edges, samp) (or takes them from qmid_in), the line-graph bound of every query (row_ptr /
+ *   col given: see gem_knn_linegraph_hint), a stratified bound pass over `bound_samples` of the e_bound bound
+ *   candidates (0: 15*sqrt((k+1)*e_bound), the size that balances the pass against the scan's slow path) -- taken
+ *   from bound_mid, or recomputed from (pos, bound_edges) so that the call depends on the positions only and can
+ *   run while the spring kernel is still producing the midpoints --, the filter thresholds and the coefficient
+ *   pairs of slot coef_slot, and zeroes the scan's counters.  The bound candidates need not be the scan's
+ *   candidates: any k+1 distinct candidates of the WHOLE problem bound the (k+1)-th neighbour distance, so the
+ *   multi-GPU path bounds with the full edge list on every rank (identical thresholds everywhere) and scans its
+ *   shard.  `e` = the candidate count of the gem_knn_scan that follows (it fixes the workspace layout).
+ * gem_knn_scan -- all-pairs scan + select -> (s, kp1) lists (short rows padded with +inf / -1).  pub (optional):
+ *   remap = table local candidate number -> global edge id (NULL: idx_offset + number); world > 0: every row is also
+ *   stored into each rank's exchange buffer (peer-mapped base pointers, the rank's own included) at
+ *   idx_offset_bytes (int64 rows) / dist_offset_bytes (fp32 rows): the rank's partial list is published by the
+ *   kernel that produces it.
  * Valid only when gem_knn_fast_path(e, e_total, d, s, kp1) returns 1 (matmul-mode cdist, d in {2,3},
- * e >= 2048, k+1 <= 64 and <= e, s <= 1024); otherwise use gem_knn_midpoints_shard.  The coefficient
- * table lives in one __constant__ array per device: at most one prepare/scan pair may be in flight
- * per device at a time. */
+ * e >= 2048, k+1 <= 64 and <= e, s <= 1024); otherwise use gem_knn_midpoints_shard. */
 int gem_knn_fast_path(int64_t e, int64_t e_total, int d, int64_t s, int kp1);
-int gem_knn_prepare(const float *mid, const float *pos, const int32_t *edges, int64_t e, int d, const float *qmid,
-                    int64_t s, int kp1, const float *tau_hint, int64_t *bump_counter, void *ws, size_t ws_bytes,
-                    void *stream);
-/* The three per-query preparation steps in ONE launch (what gem_layout_step uses): draw the sample
- * (draw != 0: like gem_sample_edges from (seed, *iter_counter), without incrementing the counter --
- * pass it as bump_counter to the gem_knn_prepare that follows in the same stream), the query
- * midpoints (gem_query_midpoints) and the line-graph bound (gem_knn_linegraph_hint).  d in {2,3};
- * `edges` is the full (e, 2) list. */
-int gem_knn_query_prep(uint64_t seed, int64_t *iter_counter, int draw, const float *pos, const int64_t *row_ptr,
-                       const int32_t *col, const int32_t *edges, int64_t e, int64_t *samp, int64_t s, int d,
-                       int kp1, float *qmid, float *tau_hint, void *stream);
+typedef struct gem_knn_prep_args {
+    int32_t d, kp1;
+    int64_t s;                  /* queries of this batch (<= 1024) */
+    int64_t e;                  /* candidates the following gem_knn_scan sees */
+    const float *pos;           /* (n, ld); may be NULL when qmid_in and bound_mid are given */
+    const int32_t *edges;       /* (e_total, 2): the edge list the query ids refer to */
+    int64_t e_total;
+    int64_t *samp;              /* (s) in (draw == 0) / out (draw != 0); unused with qmid_in */
+    int32_t draw, bump;
+    uint64_t seed;
+    int64_t *iter_counter;
+    const float *qmid_in;       /* (s, mld) precomputed query midpoints, or NULL */
+    float *qmid_out;            /* (s, mld) out, when qmid_in == NULL */
+    const int64_t *row_ptr;     /* symmetric CSR for the line-graph bound, or NULL */
+    const int32_t *col;
+    const float *tau_hint_in;   /* (s) caller-provided bound, or NULL */
+    float *tau_hint_out;        /* (s) scratch of the line-graph bound (required with row_ptr) */
+    const float *bound_mid;     /* (e_bound, mld) bound candidates, or NULL: recomputed from (pos, bound_edges) */
+    const int32_t *bound_edges; /* (e_bound, 2) */
+    int64_t e_bound;
+    int64_t bound_samples;      /* 0 = auto */
+    int32_t coef_slot;
+    void *ws; size_t ws_bytes;  /* gem_knn_workspace_bytes(e, d, s, kp1) */
+} gem_knn_prep_args;
+int gem_knn_prep(const gem_knn_prep_args *args_host, void *stream);
+typedef struct gem_knn_publish {
+    const int64_t *remap;
+    void *const *peer_base_host; int32_t world;
+    size_t idx_offset_bytes, dist_offset_bytes;
+} gem_knn_publish;
 int gem_knn_scan(const float *mid, int64_t e, int64_t idx_offset, int d, const float *qmid, int64_t s, int kp1,
-                 int64_t *out_idx, float *out_dist, void *ws, size_t ws_bytes, void *stream);
+                 int64_t *out_idx, float *out_dist, void *ws, size_t ws_bytes, int coef_slot,
+                 const gem_knn_publish *pub_host, void *stream);
 /* Optional search radius per query for gem_knn_midpoints (tau_hint, may be NULL): only
  * neighbours with distance <= tau_hint[q] are required.  gem_knn_linegraph_hint computes a valid
  * one: the (k+1)-th smallest exact distance among the edges incident to the endpoints of the query
@@ -175,11 +230,23 @@ int gem_topk_merge_strided(const float *dists, const int64_t *idxs, int64_t dist
  * select kernel does inside gem_layout_step): the CTA that merged query q's list evaluates its k
  * candidate pairs and adds the repulsion to the rows of `newpos` (fused spring+update form, row 0 =
  * vertex v_begin, only vertices in [v_begin, v_end)) with atomics that return the old row; the exact
- * change of the column sums is added to `sums` (2*ld doubles: sum | sum of squares). */
+ * change of the column sums is added to `sums` (2*ld doubles: sum | sum of squares).
+ * pub (optional, multi-GPU publication by the last CTA of the launch): the rows of this rank that received a
+ * repulsion term are stored again into every peer's raw buffer (row = padded vertex id; `newpos` must be row
+ * v_begin of peer_raw_host[rank]), and the rank's corrected column sums (2*ld doubles at `sums`) go to slot `rank`
+ * of the statistics area at stats_offset_bytes of every rank's exchange buffer.  touched: scratch of 4*s*(kp1-1)
+ * int32; counters: 2 x uint32, zero-initialised once by the caller (left at zero by the kernel). */
+typedef struct gem_merge_publish {
+    float *const *peer_raw_host; void *const *peer_xchg_host;
+    int32_t world, rank;
+    size_t stats_offset_bytes;
+    int32_t *touched; uint32_t *counters;
+} gem_merge_publish;
 int gem_topk_merge_intersect(const float *dists, const int64_t *idxs, int64_t dist_stride, int64_t idx_stride,
                              int parts, int64_t s, int kp1, int64_t *out_idx, float *out_dist, const float *pos,
                              const int32_t *edges, const int64_t *samp, int d, float k_inter, int64_t v_begin,
-                             int64_t v_end, float *newpos, double *sums, void *stream);
+                             int64_t v_end, float *newpos, double *sums, const gem_merge_publish *pub_host,
+                             void *stream);
 
 /* (c) intersection repulsion.  Replaces _compute_intersection_forces (:638-736) and
  * _check_line_intersections (:738-774).  knn_full is the (s, kp1) list INCLUDING column 0,
@@ -220,6 +287,11 @@ int gem_update_positions(float *pos, const float *f_spring, const float *f_inter
 int gem_update_normalise_push(float *const *peer_pos_host, int world, const float *src, int64_t row_begin,
                               int64_t n, int64_t n_total, int d, void *stats_ws, const double *rank_sums,
                               void *stream);
+/* Multi-GPU, early-push flow: every rank normalises ALL n_rows rows of its replica -- raw (unnormalised new
+ * positions: pushed by the owners' spring kernels, patched by their merge kernels) -> pos -- with the column sums
+ * that arrived as `slots` per-rank blocks of 2*ld doubles (added in rank order: bit-identical on every rank). */
+int gem_update_normalise_all(float *pos, const float *raw, int64_t n_rows, int64_t n_total, int d,
+                             const double *rank_sums, int slots, void *stream);
 /* idx[i] = table[idx[i]] for idx[i] >= 0 (the -1 padding of short lists is kept): a rank's KNN runs over
  * its own edges in the order its spring kernel produced their midpoints; with strided vertex ownership
  * that numbering is not the original one, and the partial lists are mapped back before the merge (which
@@ -231,8 +303,18 @@ int gem_remap_indices(int64_t *idx, int64_t n, const int64_t *table, void *strea
 int gem_push_bytes(void *const *peer_base_host, int world, size_t dst_offset, const void *src, size_t nbytes,
                    void *stream);
 
+/* Positions cross the public API as (n, d) row-major arrays in the caller's vertex numbering; on the device they are
+ * (n_pad, ld) rows in padded numbering.  gem_rows_scatter: rows [row0, row0+cnt) of the public array (`src`: cnt x d,
+ * already on the device) -> row pad_index[row0+i] (NULL: row0+i) of every buffer in peer_pos_host[0..world), pad
+ * lanes zeroed -- the positions setter; on several GPUs each rank uploads 1/world of the rows over its own PCIe link
+ * and this kernel fans them out over NVLink.  gem_rows_gather: the inverse for one buffer (the positions getter). */
+int gem_rows_scatter(const float *src, int64_t row0, int64_t cnt, int d, const int64_t *pad_index,
+                     float *const *peer_pos_host, int world, void *stream);
+int gem_rows_gather(const float *pos, int64_t row0, int64_t cnt, int d, const int64_t *pad_index, float *out,
+                    void *stream);
+
 /* One whole iteration (update_positions, :776-806) on one GPU:
- *   side stream : sample -> query midpoints -> line-graph hint -> KNN bound/threshold   (needs pos only)
+ *   side stream : KNN preparation (sample, query midpoints, line-graph + stratified bound, thresholds: one launch)
  *   `stream`    : spring forces + midpoints  ==join==>  KNN scan -> select + intersection forces -> update
  * The side stream and its two events belong to the library (created by gem_init, one set per
  * device); the fork/join is expressed with events, so the call stays CUDA-graph capturable.
@@ -261,6 +343,7 @@ typedef struct gem_plan {
     void *stats_ws;
     int32_t external_sample;  /* 1: samp was filled by the caller (torch.randperm parity mode) */
     int32_t mm_mode;          /* -1 auto */
+    int32_t coef_slot;        /* constant-bank coefficient slot owned by the caller (gem_coef_slot_acquire) */
 } gem_plan;
 
 int gem_layout_step(const gem_plan *plan_host, void *stream);
@@ -269,11 +352,11 @@ int gem_layout_step(const gem_plan *plan_host, void *stream);
  * stream, separate sample / query-midpoint / hint launches) with a CUDA event after every stage;
  * SYNCHRONISES the stream and writes the GEM_NUM_STAGES stage durations (ms) to ms_host.
  * Only valid when the KNN needs a single query batch (s <= 1024). */
-#define GEM_STAGE_SAMPLE 0
+#define GEM_STAGE_SAMPLE 0         /* fast path: empty (inside the fused preparation) */
 #define GEM_STAGE_SPRING 1         /* spring/midpoint kernel (writes pos+F in the fused form) + column-sum pass */
-#define GEM_STAGE_QUERY_MID 2
-#define GEM_STAGE_KNN_BOUND 3      /* line-graph hint + memset + bound kernel */
-#define GEM_STAGE_KNN_THRESHOLD 4  /* threshold kernel + coefficient copy to the constant bank */
+#define GEM_STAGE_QUERY_MID 2      /* fast path: empty (inside the fused preparation) */
+#define GEM_STAGE_KNN_BOUND 3      /* the fused KNN preparation kernel */
+#define GEM_STAGE_KNN_THRESHOLD 4  /* coefficient copy to the constant bank */
 #define GEM_STAGE_KNN_SCAN 5       /* the dominant kernel */
 #define GEM_STAGE_KNN_SELECT 6     /* select kernel (with the fused intersection forces in gem_layout_step) */
 #define GEM_STAGE_KNN_FALLBACK 7   /* exact kernel: the whole KNN for tiny / generic-d / k+1 > 64 inputs */

@@ -39,7 +39,7 @@ def test_committed_bench_line_matches_contract(name, line):
     e2e = line["e2e"]
     assert e2e["unit"] == line["unit"] and e2e["h2d_bytes_per_step"] > 0 and e2e["d2h_bytes_per_step"] > 0
     assert e2e["value"] < line["value"]                         # host copies are inside its timed region
-    assert line["gpu_launches"] >= 8 * line["steps"]
+    assert line["gpu_launches"] >= (8 if name.startswith("r01") else 6) * line["steps"]      # round 2: fused preparation
     clk = line["clocks"]
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(clk)
     assert not {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(clk["reasons"])

@@ -633,3 +633,168 @@ def test_radial_correlations_on_device_match_scipy_and_networkx():
     assert abs(out["degree"] - spearmanr(r, deg).correlation) < 1e-6
     assert abs(out["pagerank_networkx"] - spearmanr(r, ref).correlation) < 1e-6
     assert abs(out["pagerank"] - out["pagerank_networkx"]) < 5e-3
+
+
+# ----------------------------------------------------------------------------- round 2
+@pytest.mark.parametrize("workload", ["c2", "c3", "c4"])
+def test_full_size_one_iteration_vs_oracle(workload):
+    """One iteration at the BASELINE.json sizes (C2: 400 K edges d=2; C3: 4 M edges, the headline; C4: 10 M edges,
+    k=32) against the CPU ORACLE itself -- not an in-library cross-check: neighbour lists and distances bit-exact,
+    forces/positions within 1e-5 (||a-b||inf/||b||inf).  Second iteration through the captured CUDA graph."""
+    import bench
+    import graphem_rapids_b200 as gr
+    w = bench.WORKLOADS[workload]
+    adj = bench.make_graph(w)
+    n, d, k = adj.shape[0], w["d"], w["k"]
+    pos0 = bench.initial_positions(n, d)
+    emb = gr.GraphEmbedderPyTorch(adj, n_components=d, device="cuda:0", n_neighbors=k, sample_size=w["S"], verbose=False,
+                                  seed=0, initial_positions=pos0)
+    edges = emb.edges.cpu()
+    emb.update_positions()
+    samp = emb.last_sampled_indices.cpu()
+    ref = oracle.layout_step(torch.from_numpy(pos0), edges, samp, n_neighbors=k, strict=True)
+    assert torch.equal(emb._bufs["knn_idx"].cpu(), ref["knn_full"])
+    assert torch.equal(emb._bufs["knn_dist"].cpu(), ref["knn_dist"])
+    got = emb.positions
+    assert rel_inf(got, ref["new_pos"].numpy()) <= TOL
+    if workload == "c3":                                         # and the production path: graph replays from there
+        emb.run_layout_device(2)
+        samp2 = emb.last_sampled_indices.cpu()
+        # replay 1 ran from `got` with an unknown (device-drawn) sample; re-derive it: replays are deterministic in
+        # (seed, iteration), so a second embedder stepped eagerly gives the intermediate state
+        emb_b = gr.GraphEmbedderPyTorch(adj, n_components=d, device="cuda:0", n_neighbors=k, sample_size=w["S"],
+                                        verbose=False, seed=0, initial_positions=pos0)
+        emb_b.update_positions(); emb_b.update_positions()
+        before_last = emb_b.positions
+        emb_b.update_positions()
+        assert torch.equal(emb_b.last_sampled_indices.cpu(), samp2)
+        ref2 = oracle.layout_step(torch.from_numpy(before_last), edges, samp2, n_neighbors=k, strict=True)
+        assert torch.equal(emb_b._bufs["knn_idx"].cpu(), ref2["knn_full"])
+        assert rel_inf(emb_b.positions, ref2["new_pos"].numpy()) <= TOL
+        # replayed == eager (same kernels, same order of the deterministic parts; atomics may reorder the few
+        # intersection terms that hit one vertex)
+        assert torch.equal(emb._bufs["knn_idx"], emb_b._bufs["knn_idx"])
+        assert rel_inf(emb.positions, emb_b.positions) <= TOL
+
+
+@pytest.mark.parametrize("n,use_graph", [(30000, False), (30000, True), (4000, True)])
+def test_torch_sampler_reproduces_the_reference_rng_stream(n, use_graph):
+    """sampler='torch' draws torch.randperm(E, device)[:S] from the seeded default generator exactly like
+    embedder_pytorch.py:404-413: with seed=s the samples of iterations 0, 1, 2, ... are the reference's, whether the
+    iterations run eagerly or as replays of the captured graph (which draws sample t+1 on a side stream during
+    iteration t).  E = 120 K is above torch's CPU-offload threshold (graph path); E = 16 K is below (eager loop)."""
+    import graphem_rapids_b200 as gr
+    adj = gr.generate_ba(n, 4, seed=3)
+    pos0 = np.random.default_rng(3).standard_normal((n, 3)).astype(np.float32)
+    emb = gr.GraphEmbedderPyTorch(adj, n_components=3, device="cuda:0", n_neighbors=10, sample_size=256, verbose=False,
+                                  seed=11, initial_positions=pos0, sampler="torch", use_cuda_graph=use_graph)
+    E = emb.n_edges
+    T = 5
+    got = []
+    if use_graph:
+        # run_layout(t) for growing t on fresh objects would reseed; instead replay one iteration at a time
+        for t in range(T):
+            emb.run_layout_device(2 if t == 0 else 1)            # first call: 2 iterations (captures the graph)
+            got.append(emb.last_sampled_indices.clone().cpu())
+        T_total = T + 1
+    else:
+        for t in range(T):
+            emb.update_positions()
+            got.append(emb.last_sampled_indices.clone().cpu())
+        T_total = T
+    # the reference's stream: same global seeding calls as the constructor (:106-111), then one randperm per iteration
+    torch.manual_seed(11)
+    torch.cuda.manual_seed(11)
+    torch.cuda.manual_seed_all(11)
+    want = [torch.randperm(E, device="cuda:0")[:256].cpu() for _ in range(T_total)]
+    if use_graph:
+        want = want[1:]                                          # got[0] is iteration 1 (the first call ran two)
+    for t in range(T):
+        assert torch.equal(got[t], want[t]), f"iteration {t}: sample differs from torch.randperm's stream"
+    # and an iteration with that sample is the oracle's
+    emb2 = gr.GraphEmbedderPyTorch(adj, n_components=3, device="cuda:0", n_neighbors=10, sample_size=256, verbose=False,
+                                   seed=11, initial_positions=pos0, sampler="torch", use_cuda_graph=False)
+    emb2.update_positions()
+    ref = oracle.layout_step(torch.from_numpy(pos0), emb2.edges.cpu(), emb2.last_sampled_indices.cpu(), n_neighbors=10)
+    assert torch.equal(emb2._bufs["knn_idx"].cpu(), ref["knn_full"])
+    assert rel_inf(emb2.positions, ref["new_pos"].numpy()) <= TOL
+
+
+def test_two_embedders_on_two_streams_do_not_share_filter_state():
+    """Round 1 kept ONE __constant__ coefficient table per device: two embedders running on different streams filtered
+    with each other's queries (missing neighbours, silently).  Each object now owns a coefficient slot; interleaved
+    iterations on two streams give the same lists as running each object alone."""
+    import graphem_rapids_b200 as gr
+    from graphem_rapids_b200 import _cabi
+    lib = _cabi.load()
+    mk = []
+    for seed, n in ((1, 60000), (2, 50000)):
+        adj = gr.generate_ba(n, 4, seed=seed)
+        pos0 = np.random.default_rng(seed).standard_normal((n, 3)).astype(np.float32)
+        mk.append((adj, pos0))
+
+    def make(i, **kw):
+        adj, pos0 = mk[i]
+        return gr.GraphEmbedderPyTorch(adj, n_components=3, device="cuda:0", n_neighbors=10, sample_size=256,
+                                       verbose=False, seed=5 + i, initial_positions=pos0, **kw)
+    T = 3
+    solo = []
+    for i in range(2):
+        e = make(i)
+        lists = []
+        for it in range(T):
+            e.update_positions()
+            lists.append(e._bufs["knn_idx"].clone())
+        torch.cuda.synchronize()
+        solo.append((lists, e._positions.clone()))
+        e.close()
+    a, b = make(0), make(1)
+    assert a._coef_slot != b._coef_slot
+    sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+    la, lb = [], []
+    for it in range(T):                                          # eager steps, interleaved on two streams
+        with torch.cuda.stream(sa):
+            a.update_positions()
+            la.append(a._bufs["knn_idx"].clone())
+        with torch.cuda.stream(sb):
+            b.update_positions()
+            lb.append(b._bufs["knn_idx"].clone())
+    torch.cuda.synchronize()
+    for it in range(T):
+        assert torch.equal(la[it], solo[0][0][it]) and torch.equal(lb[it], solo[1][0][it]), f"iteration {it}"
+    assert rel_inf(a._positions.cpu().numpy(), solo[0][1].cpu().numpy()) <= TOL
+    assert rel_inf(b._positions.cpu().numpy(), solo[1][1].cpu().numpy()) <= TOL
+    # slots are released with the objects; a fifth live object is refused loudly, not silently shared
+    keep = [make(0) for _ in range(lib.gem_coef_slots() - 2)]
+    with pytest.raises(RuntimeError, match="coefficient slots"):
+        make(1)
+    del keep
+    import gc
+    gc.collect()
+    make(1).close()
+
+
+@pytest.mark.parametrize("n,d", [(500, 3), (300000, 3), (300000, 2)])
+def test_positions_setter_getter_round_trip(n, d):
+    """The drop-in state API (positions setter: ndarray or tensor, host or device, pinned or not; getter: a FRESH
+    ndarray) through gem_rows_scatter / gem_rows_gather and the pinned staging path."""
+    import graphem_rapids_b200 as gr
+    adj = gr.generate_random_regular(n, 4, seed=1)
+    rng = np.random.default_rng(0)
+    x0 = rng.standard_normal((n, d)).astype(np.float32)
+    emb = gr.GraphEmbedderPyTorch(adj, n_components=d, device="cuda:0", verbose=False, seed=0, initial_positions=x0)
+    assert np.array_equal(emb.positions, x0)
+    for make in (lambda x: x, lambda x: torch.from_numpy(x), lambda x: torch.from_numpy(x).pin_memory(),
+                 lambda x: torch.from_numpy(x).cuda(), lambda x: x.astype(np.float64)):
+        x = rng.standard_normal((n, d)).astype(np.float32)
+        emb.positions = make(x)
+        out1 = emb.get_positions()
+        out2 = emb.positions
+        assert out1 is not out2 and np.array_equal(out1, x) and np.array_equal(out2, x)
+        assert torch.equal(emb._positions.cpu(), torch.from_numpy(x))
+        out1[:] = 0                                              # a copy: the device state is untouched
+        assert np.array_equal(emb.positions, x)
+    if d == 3:
+        assert float(emb._pos[:, 3].abs().max()) == 0.0          # pad lane stays zero
+    with pytest.raises(ValueError):
+        emb.positions = x0[:-1]

@@ -1,10 +1,15 @@
 """GPU tests of the multi-GPU path.
 
-1. "Virtual ranks" on ONE GPU: R ShardedLayoutEngine objects bound to the CUDA stages are driven
-   phase by phase in one process, the three exchanges done by local copies.  This exercises every
+1. "Virtual ranks" on ONE GPU, fallback flow: R ShardedLayoutEngine objects bound to the CUDA stages are
+   driven phase by phase in one process, the three exchanges done by local copies.  This exercises every
    range-restricted kernel entry (CSR spring over a vertex range, shard-local KNN with global ids and
    short lists, strided merge, vertex-sliced intersection, two-phase update) against the oracle.
-2. Real ranks: 2 processes x 2 GPUs over NCCL (skipped when the box has one GPU).
+2. "Virtual ranks" on ONE GPU, PRODUCT flow (early raw-row push, published partial lists, touched-row
+   patches, local normalisation of all rows): the R engines' buffers are "peer-mapped" into each other by
+   plain device pointers (same GPU), the two barriers are stream synchronisations between the phases --
+   no kernel waits on another (B200_PROFILING.md forbids spinning ranks on one GPU).  Same kernels, same
+   pointers-to-replicas data flow as on R GPUs.
+3. Real ranks: N processes x N GPUs over NVLink (skipped when the box has fewer GPUs).
 """
 import os
 import socket
@@ -44,8 +49,11 @@ def test_virtual_ranks_one_gpu(kind, n, d, k, R, ownership):
     L = build_layout(e, n, R, hub_degree=_cabi.load().gem_hub_degree(), ownership=ownership)
     dev = torch.device("cuda:0")
     engines = []
+    slot = None
     for r in range(R):
-        st = CudaStages(L, r, dev, n_components=d, k_attr=0.2, L_min=1.0, k_inter=0.5, seed=9)
+        # the virtual ranks run one after the other on one stream: they share one coefficient slot (owned by rank 0's stages)
+        st = CudaStages(L, r, dev, n_components=d, k_attr=0.2, L_min=1.0, k_inter=0.5, seed=9, coef_slot=slot)
+        slot = st.coef_slot
         engines.append(ShardedLayoutEngine(L, r, st, n_components=d, n_neighbors=k, sample_size=128))
     pos0 = torch.from_numpy(np.random.default_rng(2).standard_normal((n, d)).astype(np.float32))
     for g in engines:
@@ -79,6 +87,62 @@ def test_virtual_ranks_one_gpu(kind, n, d, k, R, ownership):
         ref = got.clone()
 
 
+@pytest.mark.parametrize("kind,n,d,k,R,ownership", [
+    ("ba", 30000, 3, 10, 2, "strided"), ("rr", 40000, 2, 10, 4, "strided"), ("sbm", 40000, 3, 32, 3, "strided"),
+    ("ba", 60001, 3, 10, 8, "strided"), ("ba", 30000, 3, 10, 3, "contiguous")])
+def test_virtual_ranks_p2p_flow_one_gpu(kind, n, d, k, R, ownership):
+    from graphem_rapids_b200.partition import build_layout
+    from graphem_rapids_b200.sharded import CudaStages, ShardedLayoutEngine
+    from graphem_rapids_b200 import _cabi
+    lib = _cabi.load()
+    adj = _graph(kind, n)
+    e = oracle.extract_edges(adj).astype(np.int64)
+    L = build_layout(e, n, R, hub_degree=lib.gem_hub_degree(), ownership=ownership)
+    dev = torch.device("cuda:0")
+    S = 128
+    engines, stages, slot = [], [], None
+    for r in range(R):
+        # the virtual ranks run one after the other on one stream: they share one coefficient slot (owned by rank 0's stages)
+        st = CudaStages(L, r, dev, n_components=d, k_attr=0.2, L_min=1.0, k_inter=0.5, seed=9, coef_slot=slot)
+        slot = st.coef_slot
+        stages.append(st)
+        engines.append(ShardedLayoutEngine(L, r, st, n_components=d, n_neighbors=k, sample_size=S))
+    for g in engines:
+        assert lib.gem_knn_fast_path(g.e_hi - g.e_lo, L.n_edges, d, S, k + 1) == 1
+    ld = stages[0].ld
+    raws = [torch.zeros((2, L.n_pad, ld), device=dev) for _ in range(R)]
+    xb = CudaStages.exchange_bytes(R, engines[0]._nb, ld)
+    xchgs = [torch.zeros((xb,), device=dev, dtype=torch.uint8) for _ in range(R)]
+    for r, st in enumerate(stages):
+        st.attach_p2p([g.pos.data_ptr() for g in engines], [t.data_ptr() for t in raws], [t.data_ptr() for t in xchgs],
+                      raws[r], xchgs[r], engines[r]._nb, S, k + 1, barrier=lambda ch: None)
+    pos0 = torch.from_numpy(np.random.default_rng(2).standard_normal((n, d)).astype(np.float32))
+    for g in engines:
+        g.set_positions(pos0)
+    ref = pos0.clone()
+    edges = torch.from_numpy(e)
+    for it in range(4):                                    # both buffer parities, twice
+        for g in engines:
+            g.st.p2p_phase1(g)
+        torch.cuda.synchronize()                           # barrier A
+        for g in engines:
+            g.st.p2p_phase2(g)
+        torch.cuda.synchronize()                           # barrier B
+        for g in engines:
+            g.st.p2p_phase3(g)
+            g.iteration += 1
+        torch.cuda.synchronize()
+        samp = engines[0].samp.cpu()
+        assert all(torch.equal(g.samp.cpu(), samp) for g in engines)
+        o = oracle.layout_step(ref, edges, samp, n_neighbors=k, strict=True)
+        for g in engines:
+            assert torch.equal(g.knn_idx.cpu(), o["knn_full"]) and torch.equal(g.knn_dist.cpu(), o["knn_dist"])
+        got = engines[0].get_positions().cpu()
+        assert all(torch.equal(g.pos, engines[0].pos) for g in engines)      # replicas bit-identical
+        assert rel_inf(got.numpy(), o["new_pos"].numpy()) <= TOL
+        ref = got.clone()
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -94,14 +158,14 @@ def _nccl_worker(rank, world, port, out):
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
-        n, d, k = 40000, 3, 10
+        n, d, k = 40000 * max(1, world // 2), 3, 10
         adj = gr.generate_ba(n, 4, seed=1)
         pos0 = np.random.default_rng(2).standard_normal((n, d)).astype(np.float32)
         emb = ShardedGraphEmbedder(adj, n_components=d, device=dev, n_neighbors=k, sample_size=256, verbose=False,
                                    seed=4, initial_positions=pos0)
         ref = torch.from_numpy(pos0)
         ok, worst = True, 0.0
-        for it in range(3):
+        for it in range(3):                                                   # eager steps of the product flow vs the oracle
             emb.update_positions()
             samp = emb.last_sampled_indices.cpu()
             o = oracle.layout_step(ref, emb.edges.cpu(), samp, n_neighbors=k, strict=True)
@@ -109,48 +173,71 @@ def _nccl_worker(rank, world, port, out):
             got = emb.positions
             worst = max(worst, rel_inf(got, o["new_pos"].numpy()))
             ref = torch.from_numpy(got)
-        # CUDA-graph replay of the whole sharded step (kernels on both streams + the NCCL collectives)
-        # against eager launches of a second embedder with the same seed: same sample stream, same layout
-        # (emb: positions exchanged by P2P stores from the normalisation kernel over symmetric memory;
-        #  emb2: the NCCL all-gather fallback)
-        assert emb._engine.st.peer_ptrs is not None
-        print(f'[{rank}] exchange: symmetric memory, multicast={emb._engine.st.multicast} fused={emb._engine.st.fused}', flush=True)
-        assert emb._engine.st.fused
+        print(f'[{rank}] exchange: {emb.exchange}', flush=True)
+        assert emb.exchange == "p2p"
+        # CUDA-graph replay of the whole sharded step (kernels on both streams, peer stores, device barriers; one graph
+        # per buffer parity) against eager launches of a second embedder on the NCCL fallback flow with another
+        # ownership rule: same seed -> same sample stream -> same layout
         emb2 = ShardedGraphEmbedder(adj, n_components=d, device=dev, n_neighbors=k, sample_size=256, verbose=False,
                                     seed=4, initial_positions=pos0, use_cuda_graph=False, use_symmetric_memory=False,
                                     ownership="contiguous")
-        for it in range(3 + 4):
+        assert emb2.exchange == "nccl"
+        for it in range(3 + 5):
             emb2.update_positions()
-        emb.run_layout_device(4)
+        emb.run_layout_device(5)
         torch.cuda.synchronize()
         ok &= bool(torch.equal(emb.last_sampled_indices, emb2.last_sampled_indices))
         worst = max(worst, rel_inf(emb.positions, emb2.positions) * 1e-2)      # atomics reorder sums: 1e-3 allowed
         mine = emb._pos.clone()
         dist.broadcast(mine, src=0)
         same = bool(torch.equal(mine, emb._pos))
+        # host I/O split across the ranks: every rank uploads its chunk, all replicas end up with the whole array
+        lo, hi = emb.chunk_rows()
+        full = np.random.default_rng(5).standard_normal((n, d)).astype(np.float32)
+        emb.load_positions_chunk(torch.from_numpy(full[lo:hi]).pin_memory())
+        torch.cuda.synchronize()
+        same &= bool(np.array_equal(emb.positions, full))
+        back = torch.empty((hi - lo, d), dtype=torch.float32).pin_memory()
+        emb.read_positions_chunk(back)
+        same &= bool(np.array_equal(back.numpy(), full[lo:hi]))
         flag = torch.tensor([int(ok and same and worst <= TOL)], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if rank == 0:
             out.put((int(flag.item()), worst))
-        emb.close()                                  # release the captured graph before the communicator goes away
+        emb.close()                                  # release the captured graphs before the communicator goes away
+        emb2.close()
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_real_ranks_nccl():
+def _run_real_ranks(world):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     out = ctx.SimpleQueue()
     port = _free_port()
-    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, out)) for r in range(2)]
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, out)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
-        p.join(timeout=240)
+        p.join(timeout=300)
     hung = [p for p in procs if p.exitcode is None]
     for p in hung:
         p.kill()
     assert not hung and all(p.exitcode == 0 for p in procs)
     flag, worst = out.get()
     assert flag == 1, worst
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_real_ranks_nccl():
+    _run_real_ranks(2)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 4, reason="needs 4 GPUs")
+def test_four_real_ranks():
+    _run_real_ranks(4)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 8, reason="needs 8 GPUs")
+def test_eight_real_ranks():
+    _run_real_ranks(8)
