@@ -338,7 +338,7 @@ def run_b200(args, w):
     # one-off graph set-up (untimed by the metric; reported): the object was built above with CUDA already
     # initialised, so a second construction measures the set-up itself -- device build vs host build
     setup = None
-    if world == 1 and not args.no_cpu_baseline and E <= 12_000_000:
+    if world == 1 and not args.no_cpu_baseline and not args.profile_mode and E <= 12_000_000:
         setup = {}
         for mode in ("auto", "host"):
             torch.cuda.synchronize(dev)
@@ -384,6 +384,8 @@ def run_b200(args, w):
     # ---- sustained: >= 2 s of back-to-back replays (no flush: every array of the step is larger than it can keep
     # in L2 across an iteration only at C4/C5; said in the line), clocks sampled over the whole region
     sus_iters = int(min(max(2.2e3 / max(total_ms / K, 1e-3), K), 200000))
+    if args.profile_mode:
+        sus_iters = 2
     sus_iters += sus_iters & 1
     clocks2 = ClockSampler(local_rank)
     barrier()
@@ -566,7 +568,7 @@ def run_b200(args, w):
     # ---- CPU baseline on this box's host cores (bounded sample), N = 1 only
     cpu = None
     cpu_gc = None
-    if not args.no_cpu_baseline and world == 1:
+    if not args.no_cpu_baseline and not args.profile_mode and world == 1:
         cb_steps = 2 if E > 1_000_000 else 3
         r = cpu_reference_timing(adj, w, cb_steps, 1, budget_s=25.0)
         cpu = {"value": r["E"] / r["sec_per_step"], "unit": "edge-updates/s", "cores": r["cores"], "kind": "port",
@@ -594,7 +596,7 @@ def run_b200(args, w):
         "dtype": "f32", "data": "synthetic",
         "iters_per_s": 1e3 / ms_per_step,
         "config": workload_config(w, n, E),
-        "details": {"parallelism": "single GPU" if world == 1 else
+        "details": {"profile_mode": bool(args.profile_mode), "parallelism": "single GPU" if world == 1 else
                     (f"vertex-sharded x{world} (v mod N): spring kernel pushes pos+F rows to every replica over NVLink, select "
                      f"publishes the partial lists, 2 device barriers, every rank normalises all rows; no NCCL collective"
                      if exchange == "p2p" else f"vertex-sharded x{world}, NCCL all-gather / all-reduce fallback flow"),
@@ -639,6 +641,8 @@ def main():
     ap.add_argument("--sampler", default="device", choices=["device", "torch"],
                     help="query-edge sampler: the library's keyed bijection, or the reference's torch.randperm stream")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-mode", action="store_true",
+                    help="short run for ncu: no sustained region, no CPU baseline, no set-up timing (the line says so)")
     ap.add_argument("--sample-size", type=int, default=None,
                     help="override the workload's sample size S (>= E: the full-KNN regime, SURVEY 8(f).4)")
     args = ap.parse_args()

@@ -125,6 +125,10 @@ SIGNATURES = {
     "gem_spmv_cols": (c_int, []),
     "gem_spmv_normalized_adjacency": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float,
                                               c_void_p, c_float, c_void_p]),
+    "gem_spmv_normalized_adjacency_vec": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_void_p]),
+    "gem_seed_select_max_k": (c_int, []),
+    "gem_seed_select_workspace_bytes": (c_int, [c_int64, POINTER(c_size_t)]),
+    "gem_seed_select": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "gem_graph_workspace_bytes": (c_int, [c_int64, POINTER(c_size_t)]),
     "gem_graph_count": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "gem_graph_fill": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

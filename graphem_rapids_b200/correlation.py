@@ -86,25 +86,23 @@ def _pagerank_power_iteration(deg: torch.Tensor, apply_m, alpha: float, tol: flo
 
 def pagerank_device(embedder, alpha: float = 0.85, tol: float = 1e-6, max_iter: int = 100) -> torch.Tensor:
     """PageRank of the (undirected) graph by power iteration on the device; the operator is the library's pull
-    SpMV over the symmetric CSR of the spring kernel (column 0 of its 8-column block)."""
+    SpMV over the symmetric CSR of the spring kernel (single right-hand-side form: one 4-byte gather per entry)."""
     if getattr(embedder, "_pad_index", None) is not None:
         raise NotImplementedError("pagerank_device runs on the single-GPU vertex numbering")
     lib, dev, n = embedder._lib, embedder.device, embedder.n
-    m = lib.gem_spmv_cols()
     deg = embedder._row_ptr[1:] - embedder._row_ptr[:-1]
     degf = deg.to(torch.float32)
     dinv = torch.where(degf > 0, degf.clamp_min(1).rsqrt(), torch.zeros_like(degf)).contiguous()
-    z = torch.zeros((n, m), device=dev, dtype=torch.float32)
-    y = torch.empty_like(z)
 
     def apply_m(v):
-        z[:, 0] = v
+        v = v.contiguous()
+        y = torch.empty_like(v)
         st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        _cabi.check(lib.gem_spmv_normalized_adjacency(
+        _cabi.check(lib.gem_spmv_normalized_adjacency_vec(
             ctypes.c_void_p(embedder._row_ptr.data_ptr()), ctypes.c_void_p(embedder._col.data_ptr()),
-            ctypes.c_void_p(dinv.data_ptr()), ctypes.c_void_p(z.data_ptr()), ctypes.c_void_p(y.data_ptr()), n,
-            1.0, 0.0, None, 0.0, st), "gem_spmv_normalized_adjacency")
-        return y[:, 0]
+            ctypes.c_void_p(dinv.data_ptr()), ctypes.c_void_p(v.data_ptr()), ctypes.c_void_p(y.data_ptr()), n, 1.0, st),
+            "gem_spmv_normalized_adjacency_vec")
+        return y
 
     with torch.cuda.device(dev):
         return _pagerank_power_iteration(deg, apply_m, alpha, tol, max_iter)

@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
+#include <stdlib.h>
 #include <type_traits>
 #include <mutex>
 #include "graphem_b200.h"
@@ -669,10 +670,13 @@ __global__ void __launch_bounds__(kThreads) knn_linegraph_hint_kernel(const floa
 //       consecutive candidates from the start of ITS share [b*e/g, (b+1)*e/g) of the candidate range and
 //       records the per-query minimum -> chunkmin[b][q],
 //   (2) the line-graph bound (CTAs >= g, one warp per query; lg_hint() above),
-//   (3) thresholds: the LAST CTA to finish (ticket) takes, per query, the (k+1)-th smallest of the g chunk
-//       minima -- k+1 DISTINCT candidates lie within it, so it bounds the (k+1)-th neighbour distance --
-//       min the line-graph / caller bound, derives the filter threshold, writes the coefficient pairs of
-//       the constant bank, zeroes the scan's survivor counters and bumps the iteration counter.
+//   (3) thresholds: the CTAs fold their minima into `chunks` ~ 4(k+1) slots per query (atomicMax on an
+//       order-reversing key), and the LAST CTA to finish (ticket) takes, per query, the (k+1)-th smallest slot
+//       -- k+1 DISTINCT candidates lie within it, so it bounds the (k+1)-th neighbour distance -- with one thread
+//       per query and a branch-free sorted insertion in registers (a first version walked g = 296 minima through
+//       a shared-memory list: 150 us of dependent shared-memory round trips in one CTA); min the line-graph /
+//       caller bound, derives the filter threshold, writes the coefficient pairs of the constant bank, zeroes
+//       the scan's survivor counters and bumps the iteration counter.
 // Round 1 ran this as hint -> bound -> threshold (three dependent launches, ~50 us at C3, and a bound pass
 // whose floor of one 768-candidate tile per CTA re-evaluated 45-57 % of a 400-500 K-edge problem); here
 // the sample is M ~ 48*sqrt(E) candidates (knn_layout: the size that balances the bound pass against the
@@ -684,17 +688,55 @@ struct PrepArgs {
     const int64_t *row_ptr; const int32_t *col; const float *hint_in; float *hint_out;
     const void *bound_mid; const int2 *bound_edges; int64_t e_bound;
     int g, per, s, kp1;
-    float *chunkmin, *theta, *tau, *qcoef;
+    int chunks;                      // the g bound CTAs fold their per-query minima into `chunks` <= g slots
+    unsigned int *chunkkey;          // [chunks][s] keys 0x7F800000 - bits(min): 0 = +inf (self-cleaning, zero-initialised once)
+    float *theta, *tau, *qcoef;
     uint32_t *counts; int ncounts;
     unsigned int *ticket;
 };
 
+// order-reversing 32-bit key of a float (any sign): larger key = smaller value, never 0 for a non-NaN value
+__device__ __forceinline__ unsigned int prep_key(float v) {
+    const unsigned int b = __float_as_uint(v);
+    const unsigned int asc = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    return ~asc;
+}
+__device__ __forceinline__ float prep_unkey(unsigned int k) {
+    const unsigned int asc = ~k;
+    return __uint_as_float((asc & 0x80000000u) ? (asc & 0x7FFFFFFFu) : ~asc);
+}
+
+// (k+1)-th smallest of the `chunks` slot minima of query q, K = register list length >= kp1; clears the slots
+template <int K>
+__device__ __forceinline__ float prep_kth_smallest(unsigned int *__restrict__ keys, int chunks, int s, int q, int kp1) {
+    float lst[K];
+#pragma unroll
+    for (int r = 0; r < K; ++r) lst[r] = kInf;
+    for (int c0 = 0; c0 < chunks; c0 += 8) {
+        unsigned int kk[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) kk[u] = (c0 + u < chunks) ? __ldcg(keys + (int64_t)(c0 + u) * s + q) : 0u;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (c0 + u < chunks) keys[(int64_t)(c0 + u) * s + q] = 0u;
+            const float x = kk[u] ? prep_unkey(kk[u]) : kInf;
+#pragma unroll
+            for (int r = K - 1; r >= 1; --r) lst[r] = fminf(lst[r], fmaxf(lst[r - 1], x));   // sorted insertion, branch-free
+            lst[0] = fminf(lst[0], x);
+        }
+    }
+    float kth = kInf;
+#pragma unroll
+    for (int r = 0; r < K; ++r)
+        if (r == kp1 - 1) kth = lst[r];
+    return kth;
+}
+
 template <int D>
-__global__ void __launch_bounds__(kThreads) knn_prep_kernel(const PrepArgs A) {
+__global__ void __launch_bounds__(kThreads, 3) knn_prep_kernel(const PrepArgs A) {
     using CandT = typename MidT<D>::T;
     extern __shared__ __align__(16) unsigned char prep_smem[];
     float4 *s_q = reinterpret_cast<float4 *>(prep_smem);                      // (a0,a1,a2,qn) per query
-    float *s_list = reinterpret_cast<float *>(s_q + A.s);                     // last CTA: kp1 x kThreads sorted lists
     __shared__ float red[kWarps][kQB];
     __shared__ __align__(16) CandT tile[kBoundTile];
     __shared__ bool s_last;
@@ -737,15 +779,21 @@ __global__ void __launch_bounds__(kThreads) knn_prep_kernel(const PrepArgs A) {
         const int64_t lo = ((int64_t)blockIdx.x * A.e_bound) / A.g, hi = ((int64_t)(blockIdx.x + 1) * A.e_bound) / A.g;
         const int64_t take = min((int64_t)A.per, hi - lo);
         const CandT *mid = reinterpret_cast<const CandT *>(A.bound_mid);
+        // The pass does not need the exact cdist chain, only a value G with  E <= G + qn (1 + 2^-19)  for the exact chain
+        // value E of the same pair: G = fma(a0,x, fma(a1,y, fma(a2,z, yn (1 + 2^-19)))) -- the scan's 3-FMA filter
+        // expression with the candidate constant inflated instead of deflated, two queries per packed FMA.  Proof:
+        // both chains round quantities bounded by 2 (qn + yn); E makes 5 roundings, G makes 4, so
+        // E <= T + qn + yn + 10u (qn+yn) and T + yn (1 + 32u) <= G + 8u (qn+yn)  (u = 2^-24, T = a.y exactly), hence
+        // E <= G + qn (1 + 18u) + (18u - 32u) yn <= G + qn (1 + 2^-19).
         for (int qb = 0; qb * kQB < A.s; ++qb) {
-            QueryPar qp[kQ];
+            unsigned long long c0[kQ / 2], c1[kQ / 2], c2[kQ / 2];
             float best[kQ];
 #pragma unroll
-            for (int i = 0; i < kQ; ++i) {
-                const int q = qb * kQB + i * 32 + lane;
-                const float4 v = s_q[q < A.s ? q : 0];
-                qp[i].a0 = v.x; qp[i].a1 = v.y; qp[i].a2 = v.z; qp[i].qn = v.w;
-                best[i] = kInf;
+            for (int i = 0; i < kQ / 2; ++i) {
+                const int qa = qb * kQB + (2 * i) * 32 + lane, qc = qa + 32;
+                const float4 va = s_q[qa < A.s ? qa : 0], vc = s_q[qc < A.s ? qc : 0];
+                c0[i] = pack2f(va.x, vc.x); c1[i] = pack2f(va.y, vc.y); c2[i] = pack2f(va.z, vc.z);
+                best[2 * i] = kInf; best[2 * i + 1] = kInf;
             }
             for (int64_t t0 = 0; t0 < take; t0 += kBoundTile) {
                 const int cnt = (int)min((int64_t)kBoundTile, take - t0);
@@ -763,8 +811,18 @@ __global__ void __launch_bounds__(kThreads) knn_prep_kernel(const PrepArgs A) {
                 for (int c = warp; c < cnt; c += kWarps) {
                     float x, y, z, n;
                     cand_xyzn(tile[c], x, y, z, n);
+                    const float npp = __fmul_rn(n, 1.0f + 1.9073486328125e-06f);       // yn (1 + 2^-19)
 #pragma unroll
-                    for (int i = 0; i < kQ; ++i) best[i] = fminf(best[i], chain_mm(qp[i], x, y, z, n, D));
+                    for (int i = 0; i < kQ / 2; ++i) {
+                        unsigned long long f = pack2f(npp, npp);
+                        if (D == 3) f = fma2f(c2[i], pack2f(z, z), f);
+                        f = fma2f(c1[i], pack2f(y, y), f);
+                        f = fma2f(c0[i], pack2f(x, x), f);
+                        float fl, fh;
+                        unpack2f(f, fl, fh);
+                        best[2 * i] = fminf(best[2 * i], fl);
+                        best[2 * i + 1] = fminf(best[2 * i + 1], fh);
+                    }
                 }
             }
 #pragma unroll
@@ -775,7 +833,10 @@ __global__ void __launch_bounds__(kThreads) knn_prep_kernel(const PrepArgs A) {
                 float v = red[0][threadIdx.x];
 #pragma unroll
                 for (int w = 1; w < kWarps; ++w) v = fminf(v, red[w][threadIdx.x]);
-                if (q < A.s) A.chunkmin[(int64_t)blockIdx.x * A.s + q] = v;
+                // fold into slot blockIdx % chunks with atomicMax on an order-REVERSING key (larger key = smaller value,
+                // 0 = empty slot = +inf); NaN / inf leave the slot alone
+                if (q < A.s && v < kInf)
+                    atomicMax(A.chunkkey + (int64_t)((int)blockIdx.x % A.chunks) * A.s + q, prep_key(v));
             }
             __syncthreads();
         }
@@ -789,28 +850,11 @@ __global__ void __launch_bounds__(kThreads) knn_prep_kernel(const PrepArgs A) {
     __threadfence();
     const float *hint = A.hint_in != nullptr ? A.hint_in : (A.row_ptr != nullptr ? A.hint_out : nullptr);
     for (int q = threadIdx.x; q < A.s; q += kThreads) {
-        // sorted list of the kp1 smallest chunk minima of query q (column threadIdx.x of s_list)
-        float *lst = s_list + threadIdx.x;
-        for (int r = 0; r < A.kp1; ++r) lst[r * kThreads] = kInf;
-        float worst = kInf;
-        for (int c0 = 0; c0 < A.g; c0 += 8) {
-            float v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = (c0 + u < A.g) ? __ldcg(A.chunkmin + (int64_t)(c0 + u) * A.s + q) : kInf;
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const float x = v[u];
-                if (x < worst) {                                   // NaN compares false: ignored
-                    int r = A.kp1 - 1;
-                    while (r > 0 && lst[(r - 1) * kThreads] > x) { lst[r * kThreads] = lst[(r - 1) * kThreads]; --r; }
-                    lst[r * kThreads] = x;
-                    worst = lst[(A.kp1 - 1) * kThreads];
-                }
-            }
-        }
-        float ta = kInf;
-        if (worst < kInf) ta = __fsqrt_rn(fmaxf(worst, 0.f)) + 0.f;
-        if (hint != nullptr) ta = fminf(ta, __ldcg(hint + q));
+        // list lengths 16 / 40 / 64 cover k+1 <= 64; the launch bound (3 CTAs per SM, what the bound pass wants) keeps
+        // the kernel at <= 85 registers, so only the 64-entry variant (k >= 40) spills part of its list to local memory
+        const float worst = A.kp1 <= 16 ? prep_kth_smallest<16>(A.chunkkey, A.chunks, A.s, q, A.kp1)
+                          : A.kp1 <= 40 ? prep_kth_smallest<40>(A.chunkkey, A.chunks, A.s, q, A.kp1)
+                                        : prep_kth_smallest<64>(A.chunkkey, A.chunks, A.s, q, A.kp1);
         const float4 qv = (A.qmid_in != nullptr || (int)blockIdx.x < A.g) ? s_q[q] : make_float4(0.f, 0.f, 0.f, 0.f);
         QueryPar qp;
         if (A.qmid_in != nullptr || (int)blockIdx.x < A.g) {
@@ -821,6 +865,11 @@ __global__ void __launch_bounds__(kThreads) knn_prep_kernel(const PrepArgs A) {
             cand_xyzn(__ldcg(reinterpret_cast<const CandT *>(A.qmid_out) + q), x, y, z, n);
             qp.a0 = -2.f * x; qp.a1 = -2.f * y; qp.a2 = -2.f * z; qp.qn = n;
         }
+        // `worst` = (k+1)-th smallest G: k+1 distinct candidates have exact chain values <= worst + qn (1 + 2^-19)
+        float ta = kInf;
+        if (worst < kInf)
+            ta = __fsqrt_rn(fmaxf(__fadd_ru(worst, __fmul_ru(qp.qn, 1.0f + 1.9073486328125e-06f)), 0.f)) + 0.f;
+        if (hint != nullptr) ta = fminf(ta, __ldcg(hint + q));
         A.theta[q] = filter_threshold(ta, qp.qn);
         A.tau[q] = ta;
         // staging copy of the constant-bank table: pair m = q/2, component q&1
@@ -1018,7 +1067,8 @@ __global__ void __launch_bounds__(kScanThreads, 2) knn_scan_kernel(const typenam
                                                                    uint32_t *__restrict__ counts,
                                                                    uint64_t *__restrict__ keys, int cap,
                                                                    uint32_t *__restrict__ tile_counter,
-                                                                   unsigned long long *__restrict__ stats, int qb, int slot) {
+                                                                   unsigned long long *__restrict__ stats, int qb, int slot,
+                                                                   int qs) {
     // qb (query block) and slot (coefficient bank) are kernel PARAMETERS, not blockIdx.y: ptxas keeps parameter-derived values in
     // uniform registers, which the constant-bank coefficient addressing below depends on
     using CandT = typename MidT<D>::T;
@@ -1030,7 +1080,16 @@ __global__ void __launch_bounds__(kScanThreads, 2) knn_scan_kernel(const typenam
 
     const int lane = threadIdx.x & 31;
     const int warp = __reduce_max_sync(0xffffffffu, (int)(threadIdx.x >> 5));   // uniform register (see the block id below)
+    // qs > 0 (small problems: fewer candidate blocks than warps on the GPU) splits the 128 query pairs into 2^qs parts;
+    // CTA c works on part c % 2^qs for the candidate blocks c / 2^qs + i * (G / 2^qs): the main loop AND the slow path of
+    // a candidate block then run on 2^qs warps (round 1 ran E = 5 K as 27 blocks on 27 warps: 65 us of serial slow
+    // path).  The part comes from blockIdx.x, which keeps the coefficient addressing on the uniform datapath (a
+    // per-warp part derived from the block ordinal turned the UR operands off: 144 -> 0 of 144 FFMA2).
     const int64_t nblocks = (e + kCandBlock - 1) / kCandBlock;
+    const int nparts = 1 << qs;
+    const int part = (int)(blockIdx.x & (unsigned)(nparts - 1));      // this CTA's query part (all of its warps)
+    const int cta_in_part = (int)(blockIdx.x >> qs), ctas_per_part = (int)(gridDim.x >> qs);   // gridDim.x % 2^qs == 0
+    const int mc_lo = part * ((kQB / 2) >> qs), mc_n = (kQB / 2) >> qs;
 
     if (threadIdx.x < kQB) {   // per-query state of this CTA
         const int q = qb * kQB + threadIdx.x;
@@ -1066,7 +1125,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) knn_scan_kernel(const typenam
     // CTA).  A global atomic in this instruction stream makes ptxas give up the uniform datapath for
     // the whole main loop (measured: FFMA2 with UR operands 144 -> 0), a shared one does not.
     auto fetch = [&](int st) {
-        const int64_t b = (int64_t)blockIdx.x + (int64_t)atomicAdd(&s_next, 1u) * gridDim.x;
+        const int64_t b = (int64_t)cta_in_part + (int64_t)atomicAdd(&s_next, 1u) * ctas_per_part;
         if (b >= nblocks) {
             blk_id[warp][st] = -1;
             mbar_arrive(&full_bar[warp][st]);
@@ -1119,7 +1178,8 @@ __global__ void __launch_bounds__(kScanThreads, 2) knn_scan_kernel(const typenam
             }
             uint32_t hitmask = 0;
             static_assert(kQB / 2 / kPairChunk <= 32, "one bit per pair chunk");
-            for (int mc = 0; mc < kQB / 2; mc += kPairChunk) {
+            for (int mcr = 0; mcr < mc_n; mcr += kPairChunk) {
+                const int mc = mc_lo + mcr;
                 bool any = false;
 #pragma unroll
                 for (int u = 0; u < kPairChunk; ++u) {                // per pair of queries: 3*kC FFMA2, min, 2 compares
@@ -1920,6 +1980,139 @@ __global__ void __launch_bounds__(kThreads) spmv_norm_adj_kernel(const int64_t *
     }
 }
 
+// single right-hand side (PageRank power iteration of the correlation harness): y[v] = alpha * dinv[v] * sum_w dinv[w] x[w]
+__global__ void __launch_bounds__(kThreads) spmv_norm_adj_vec_kernel(const int64_t *__restrict__ row_ptr,
+                                                                     const int32_t *__restrict__ col,
+                                                                     const float *__restrict__ dinv,
+                                                                     const float *__restrict__ x, float *__restrict__ y,
+                                                                     int64_t n, float alpha) {
+    const int g = threadIdx.x & (kGrp - 1);
+    const int64_t stride = ((int64_t)gridDim.x * kThreads) / kGrp;
+    const int64_t first = ((int64_t)blockIdx.x * kThreads + threadIdx.x) / kGrp;
+    const int64_t warp_first = ((int64_t)blockIdx.x * kThreads + (threadIdx.x & ~31)) / kGrp;
+    for (int64_t base = warp_first, v = first; base < n; base += stride, v += stride) {
+        float a = 0.f;
+        const bool valid = v < n;
+        if (valid) {
+            const int64_t r0 = row_ptr[v], r1 = row_ptr[v + 1];
+            for (int64_t t = r0 + g; t < r1; t += kGrp) {
+                const int w = __ldg(col + t);
+                a = fmaf(__ldg(dinv + w), __ldg(x + w), a);
+            }
+        }
+#pragma unroll
+        for (int m = 1; m < kGrp; m <<= 1) a += __shfl_xor_sync(0xffffffffu, a, m);
+        if (valid && g == 0) y[v] = alpha * dinv[v] * a;
+    }
+}
+
+// ==========================================================================================
+// SURVEY 8(f).3 -- graphem_seed_selection (influence.py:28-37): the k vertices with the largest radial distance,
+//   radial = np.linalg.norm(positions, axis=1);  seeds = np.argsort(-radial)[:k]
+// on the device, so a 10 M-vertex layout is never copied to the host to pick k seeds.  radius = sqrt of the
+// left-to-right fp32 sum of squares (numpy's add.reduce over 2-3 elements, bit for bit); the order is (radius
+// descending, vertex id ascending) -- numpy's default argsort is not stable, so ties (exactly equal radii) are the
+// one place where its order is unspecified; the id tie-break makes this one deterministic.
+// Method: every vertex has the 64-bit key (radius bits << 32) | (2^32-1 - id): keys are DISTINCT and descending key
+// order is the wanted order, so a most-significant-digit radix select (6 passes of 11 bits: histogram of the digit
+// among the keys that match the prefix found so far, then one CTA picks the digit holding the k-th largest) finds
+// the exact k-th key; one more pass collects the k keys >= it, a last one ranks them.  Every pass recomputes the
+// radii from the positions (16 bytes per vertex), nothing of size n is materialised.
+// ==========================================================================================
+constexpr int kSeedBits = 11;
+constexpr int kSeedBins = 1 << kSeedBits;
+constexpr int kSeedPasses = 6;                       // 6 * 11 = 66 >= 64
+struct SeedState { unsigned long long prefix; unsigned long long k_rem; unsigned long long collected; };
+
+__device__ __forceinline__ unsigned long long seed_key(const float *__restrict__ pos, int64_t row, int d, int ld, int64_t id) {
+    const float *p = pos + row * ld;
+    float s = p[0] * p[0];
+    for (int j = 1; j < d; ++j) s = s + p[j] * p[j];                 // -fmad=false: not contracted
+    const float r = __fsqrt_rn(s) + 0.f;
+    return ((unsigned long long)__float_as_uint(r) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)id);
+}
+__host__ __device__ inline int seed_shift(int pass) { const int s = 64 - kSeedBits * (pass + 1); return s < 0 ? 0 : s; }
+__host__ __device__ inline int seed_width(int pass) { return pass == kSeedPasses - 1 ? 64 - kSeedBits * (kSeedPasses - 1) : kSeedBits; }
+
+__global__ void __launch_bounds__(kThreads) seed_hist_kernel(const float *__restrict__ pos, int64_t n, int d, int ld,
+                                                             const int64_t *__restrict__ pad_index, int pass,
+                                                             const SeedState *__restrict__ state,
+                                                             unsigned int *__restrict__ hist) {
+    __shared__ unsigned int sh[kSeedBins];
+    for (int i = threadIdx.x; i < kSeedBins; i += kThreads) sh[i] = 0;
+    __syncthreads();
+    const unsigned long long prefix = state->prefix;
+    const int shift = seed_shift(pass), width = seed_width(pass);
+    const int hi_shift = shift + width;                               // bits above the current digit = the prefix
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t v = (int64_t)blockIdx.x * kThreads + threadIdx.x; v < n; v += stride) {
+        const unsigned long long key = seed_key(pos, pad_index ? pad_index[v] : v, d, ld, v);
+        const bool match = hi_shift >= 64 ? true : ((key >> hi_shift) == prefix);
+        if (match) atomicAdd(&sh[(unsigned int)(key >> shift) & ((1u << width) - 1u)], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kSeedBins; i += kThreads)
+        if (sh[i]) atomicAdd(hist + i, sh[i]);
+}
+
+// one CTA: the digit whose bucket holds the k_rem-th largest matching key; prefix <- (prefix << width) | digit
+__global__ void __launch_bounds__(1024) seed_pick_kernel(SeedState *__restrict__ state, unsigned int *__restrict__ hist, int pass) {
+    __shared__ unsigned long long above[kSeedBins];                   // keys in buckets strictly above bin i
+    __shared__ unsigned int sh[kSeedBins];
+    const int width = seed_width(pass), bins = 1 << width;
+    for (int i = threadIdx.x; i < kSeedBins; i += blockDim.x) { sh[i] = i < bins ? hist[i] : 0u; hist[i] = 0u; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long acc = 0;
+        for (int i = bins - 1; i >= 0; --i) { above[i] = acc; acc += sh[i]; }
+    }
+    __syncthreads();
+    const unsigned long long k_rem = state->k_rem;
+    __syncthreads();
+    for (int i = threadIdx.x; i < bins; i += blockDim.x) {
+        if (above[i] < k_rem && k_rem <= above[i] + sh[i]) {            // exactly one bin
+            state->prefix = (state->prefix << width) | (unsigned long long)i;
+            state->k_rem = k_rem - above[i];
+        }
+    }
+}
+
+// keys >= the k-th largest key (state->prefix after the last pass): exactly k of them, in arbitrary order
+__global__ void __launch_bounds__(kThreads) seed_collect_kernel(const float *__restrict__ pos, int64_t n, int d, int ld,
+                                                                const int64_t *__restrict__ pad_index,
+                                                                SeedState *__restrict__ state,
+                                                                unsigned long long *__restrict__ keys, int64_t k) {
+    const unsigned long long thr = state->prefix;
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t v = (int64_t)blockIdx.x * kThreads + threadIdx.x; v < n; v += stride) {
+        const unsigned long long key = seed_key(pos, pad_index ? pad_index[v] : v, d, ld, v);
+        if (key >= thr) {
+            const unsigned long long slot = atomicAdd(&state->collected, 1ull);
+            if ((int64_t)slot < k) keys[slot] = key;
+        }
+    }
+}
+
+// rank the k collected keys (distinct) by counting: out[rank] = (id, radius), descending key
+__global__ void __launch_bounds__(kThreads) seed_rank_kernel(const unsigned long long *__restrict__ keys, int64_t k,
+                                                             int64_t *__restrict__ out_idx, float *__restrict__ out_r) {
+    __shared__ unsigned long long tile[kThreads];
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const unsigned long long mine = i < k ? keys[i] : 0ull;
+    int64_t rank = 0;
+    for (int64_t b0 = 0; b0 < k; b0 += kThreads) {
+        __syncthreads();
+        tile[threadIdx.x] = (b0 + threadIdx.x < k) ? keys[b0 + threadIdx.x] : 0ull;
+        __syncthreads();
+        const int m = (int)min((int64_t)kThreads, k - b0);
+        for (int u = 0; u < m; ++u) rank += tile[u] > mine;
+    }
+    if (i < k) {
+        out_idx[rank] = (int64_t)(0xFFFFFFFFu - (uint32_t)(mine & 0xFFFFFFFFull));
+        if (out_r) out_r[rank] = __uint_as_float((uint32_t)(mine >> 32));
+    }
+}
+
 // ==========================================================================================
 // SURVEY 8(f).2 -- graph arrays on the device: _validate_adjacency + _extract_edges_from_adjacency
 // (embedder_pytorch.py:182-245) take a scipy CSR to the upper-triangular (E,2) edge list in nonzero() order on
@@ -2129,6 +2322,7 @@ inline int grid_for(int64_t work, int per_sm) {
 // ---- KNN fast path plumbing -------------------------------------------------------------------
 struct KnnLayout {
     int g;                  // scan CTAs over the candidate axis
+    int qs;                 // log2 of the query split of the scan's work items
     int g_max;              // upper bound of g and of the bound pass's chunk count (sizes chunkmin / cap)
     int cap;                // published candidates kept per query  (>= g * kp1: cannot overflow)
     int64_t sb;             // queries per batch
@@ -2143,9 +2337,13 @@ KnnLayout knn_layout(int64_t e, int64_t s, int kp1) {
     // scan grid: every warp of a CTA is its own consumer of 192-candidate blocks, so a small problem gets only as
     // many CTAs as it has blocks for (round 1 launched 2 x SMs CTAs for 27 blocks at E = 5 K)
     const int64_t nblocks = (e + kCandBlock - 1) / kCandBlock;
-    int64_t g = (nblocks + kWarps - 1) / kWarps;
+    int qs = 0;                                           // query split: up to 8 work items per candidate block
+    while (qs < 3 && (nblocks << (qs + 1)) <= (int64_t)L.g_max * kWarps) ++qs;
+    static_assert(((kQB / 2) >> 3) % kPairChunk == 0, "a query part is a whole number of pair chunks");
+    L.qs = qs;
+    int64_t g = ((nblocks + kWarps - 1) / kWarps) << qs;      // CTAs per query part x parts
     if (g < 1) g = 1;
-    if (g > L.g_max) g = L.g_max;
+    if (g > L.g_max) g = (L.g_max >> qs) << qs;
     L.g = (int)g;
     int cap = (L.g_max * kp1 + 255) / 256 * 256;      // every CTA publishes at most kp1 keys per query
     if (cap < 1024) cap = 1024;
@@ -2165,12 +2363,14 @@ KnnLayout knn_layout(int64_t e, int64_t s, int kp1) {
     return L;
 }
 
-// Size of the bound pass's candidate sample.  Expected filter passes of the scan: (k+1) * E / M per query, each a
-// ~50-instruction warp-level slow-path event; the bound pass costs ~56 warp instructions per sampled candidate (256
-// queries): the sum is minimal at M = sqrt(228 * (k+1) * E) ~ 15 * sqrt((k+1) * E).  `scale` > 1 buys a tighter bound
-// where the preparation is hidden behind other work (single GPU: it runs next to the spring kernel).
+// Size of the bound pass's candidate sample.  Expected filter passes of the scan: (k+1) * E / M per query; measured on
+// B200 (C3: scan 154 us at M = 227 K, 171 us at M = 99 K) a pass costs ~300 issue cycles of its SM sub-partition
+// (warp-level slow-path event + exact re-check + insertion), i.e. ~400 warp instructions, while the bound pass costs
+// ~56 warp instructions per sampled candidate (256 queries): the sum is minimal at
+// M = sqrt(400 * 256 * (k+1) * E / 56) ~ 43 * sqrt((k+1) * E).  `scale` > 1 buys a tighter bound where the
+// preparation is hidden behind other work (single GPU: it runs next to the spring kernel).
 inline int64_t bound_sample_size(int64_t e_bound, int kp1, float scale) {
-    double m = 15.0 * sqrt((double)kp1 * (double)e_bound) * (scale > 0.f ? scale : 1.f);
+    double m = 43.0 * sqrt((double)kp1 * (double)e_bound) * (scale > 0.f ? scale : 1.f);
     if (m < 8192.0) m = 8192.0;
     if (m > (double)e_bound) m = (double)e_bound;
     return (int64_t)m;
@@ -2184,7 +2384,7 @@ inline int64_t bound_sample_size(int64_t e_bound, int kp1, float scale) {
 template <int D>
 int knn_prepare(const KnnLayout &L, char *w, PrepArgs A, int64_t bound_samples, int slot, cudaStream_t st) {
     if (slot < 0 || slot >= kCoefSlots) return GEM_E_BADARG;
-    A.chunkmin = reinterpret_cast<float *>(w + L.off_chunkmin);
+    A.chunkkey = reinterpret_cast<unsigned int *>(w + L.off_chunkmin);
     A.theta = reinterpret_cast<float *>(w + L.off_theta);
     A.tau = reinterpret_cast<float *>(w + L.off_tau);
     A.counts = reinterpret_cast<uint32_t *>(w + L.off_counts);
@@ -2199,10 +2399,15 @@ int knn_prepare(const KnnLayout &L, char *w, PrepArgs A, int64_t bound_samples, 
     if (g > A.e_bound) g = A.e_bound;
     A.g = (int)g;
     A.per = (int)((m + g - 1) / g);
+    int chunks = 4 * A.kp1;                                   // ~13 % looser than the (k+1)-th smallest SAMPLE (slot collisions)
+    if (chunks < 32) chunks = 32;
+    if (chunks > 128) chunks = 128;
+    if (chunks > A.g) chunks = A.g;
+    A.chunks = chunks;
     const bool lg = A.row_ptr != nullptr && A.col != nullptr && A.qmid_in == nullptr && A.hint_out != nullptr;
     if (!lg) { A.row_ptr = nullptr; A.col = nullptr; }
     const int grid = A.g + (lg ? (A.s + kWarps - 1) / kWarps : 0);
-    const size_t smem = (size_t)A.s * sizeof(float4) + (size_t)A.kp1 * kThreads * sizeof(float);
+    const size_t smem = (size_t)A.s * sizeof(float4);
     knn_prep_kernel<D><<<grid, kThreads, smem, st>>>(A);
     GEM_CHECK_LAUNCH();
     stage_mark();                                                   // GEM_STAGE_KNN_BOUND (the fused preparation)
@@ -2229,7 +2434,7 @@ int knn_scan_select(const KnnLayout &L, char *w, const float *mid, int64_t e, co
     for (int qb = 0; qb * kQB < sb; ++qb) {        // S = 256: one launch
         knn_scan_kernel<D><<<L.g, kScanThreads, scan_smem, st>>>(
             reinterpret_cast<const CandT *>(mid), e, qm, sb, kp1, theta, tau, counts, keys, L.cap, counts + L.sb,
-            g_knn_stats ? reinterpret_cast<unsigned long long *>(w + L.off_stats) : nullptr, qb, slot);
+            g_knn_stats ? reinterpret_cast<unsigned long long *>(w + L.off_stats) : nullptr, qb, slot, L.qs);
         GEM_CHECK_LAUNCH();
     }
     stage_mark();                                                   // GEM_STAGE_KNN_SCAN
@@ -2309,7 +2514,7 @@ int gem_init(void) {
     GEM_CUDA(cudaFuncSetAttribute(knn_scan_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)scan_smem_bytes(16, kMaxFastKp1)));
     GEM_CUDA(cudaFuncSetAttribute(knn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    const int prep_smem = kMaxBatchQ * (int)sizeof(float4) + kMaxFastKp1 * kThreads * (int)sizeof(float);
+    const int prep_smem = kMaxBatchQ * (int)sizeof(float4);
     GEM_CUDA(cudaFuncSetAttribute(knn_prep_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, prep_smem));
     GEM_CUDA(cudaFuncSetAttribute(knn_prep_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, prep_smem));
     if (dev >= 0 && dev < kMaxDevices && g_aux[dev].st == nullptr) {
@@ -2905,9 +3110,15 @@ int gem_layout_step(const gem_plan *p, void *stream) {
         if (have_hint) { A.row_ptr = p->row_ptr; A.col = p->col; A.hint_out = p->tau_hint; }
         A.bound_edges = ed; A.e_bound = p->e;                           // midpoints recomputed from (pos, edges): no wait for `mid`
         A.s = (int)p->s; A.kp1 = p->kp1;
-        // the preparation is hidden behind the spring kernel here: a 4x larger sample than the balanced size buys a
-        // tighter bound (fewer slow-path events inside the scan, which IS on the critical path)
-        const int64_t samples = bound_sample_size(p->e, p->kp1, overlap ? 4.f : 1.f);
+        // the preparation is hidden behind the spring kernel here: a 2x larger sample than the balanced size buys a
+        // tighter bound (fewer slow-path events inside the scan, which IS on the critical path); the profiling
+        // variant uses the same size so that its scan stage is the production scan
+        static const float scale_env = [] {                       // tuning knob (bench sweeps): GEM_BOUND_SCALE
+            const char *v = getenv("GEM_BOUND_SCALE");
+            const float f = v ? (float)atof(v) : 0.f;
+            return f > 0.f ? f : 2.f;
+        }();
+        const int64_t samples = bound_sample_size(p->e, p->kp1, scale_env);
         rc = p->d == 2 ? knn_prepare<2>(L, w, A, samples, p->coef_slot, side) : knn_prepare<3>(L, w, A, samples, p->coef_slot, side);
         if (rc) return rc;
         if (overlap) {
@@ -3011,6 +3222,51 @@ int gem_spmv_normalized_adjacency(const int64_t *row_ptr, const int32_t *col, co
     if (((uintptr_t)x & 15) || ((uintptr_t)y & 15) || (z && ((uintptr_t)z & 15))) return GEM_E_BADARG;
     const int grid = grid_for(n * kGrp, 8);
     spmv_norm_adj_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(row_ptr, col, dinv_sqrt, x, y, n, alpha, beta, z, gamma);
+    GEM_CHECK_LAUNCH();
+    return GEM_OK;
+}
+
+int gem_spmv_normalized_adjacency_vec(const int64_t *row_ptr, const int32_t *col, const float *dinv_sqrt, const float *x,
+                                      float *y, int64_t n, float alpha, void *stream) {
+    if (!row_ptr || !col || !dinv_sqrt || !x || !y || n <= 0 || y == x) return GEM_E_BADARG;
+    const int grid = grid_for(n * kGrp, 8);
+    spmv_norm_adj_vec_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(row_ptr, col, dinv_sqrt, x, y, n, alpha);
+    GEM_CHECK_LAUNCH();
+    return GEM_OK;
+}
+
+int gem_seed_select_max_k(void) { return 1 << 16; }
+
+int gem_seed_select_workspace_bytes(int64_t k, size_t *bytes) {
+    if (!bytes || k <= 0) return GEM_E_BADARG;
+    *bytes = 256 + kSeedBins * sizeof(unsigned int) + (size_t)k * sizeof(unsigned long long);
+    return GEM_OK;
+}
+
+int gem_seed_select(const float *pos, int64_t n, int d, const int64_t *pad_index, int64_t k, int64_t *out_idx, float *out_radius,
+                    void *ws, size_t ws_bytes, void *stream) {
+    if (!pos || !out_idx || n <= 0 || d <= 0 || k <= 0 || k > n || n >= ((int64_t)1 << 32)) return GEM_E_BADARG;
+    if (k > gem_seed_select_max_k()) return GEM_E_BADARG;
+    const size_t need = 256 + kSeedBins * sizeof(unsigned int) + (size_t)k * sizeof(unsigned long long);
+    if (!ws || ws_bytes < need || ((uintptr_t)ws & 255)) return GEM_E_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    SeedState *state = reinterpret_cast<SeedState *>(ws);
+    unsigned int *hist = reinterpret_cast<unsigned int *>(reinterpret_cast<char *>(ws) + 256);
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(ws) + 256 + kSeedBins * sizeof(unsigned int));
+    GEM_CUDA(cudaMemsetAsync(ws, 0, 256 + kSeedBins * sizeof(unsigned int), st));
+    const SeedState init = {0ull, (unsigned long long)k, 0ull};
+    GEM_CUDA(cudaMemcpyAsync(state, &init, sizeof(init), cudaMemcpyHostToDevice, st));
+    const int ld = row_pitch(d);
+    const int grid = grid_for(n, 8);
+    for (int pass = 0; pass < kSeedPasses; ++pass) {
+        seed_hist_kernel<<<grid, kThreads, 0, st>>>(pos, n, d, ld, pad_index, pass, state, hist);
+        GEM_CHECK_LAUNCH();
+        seed_pick_kernel<<<1, 1024, 0, st>>>(state, hist, pass);
+        GEM_CHECK_LAUNCH();
+    }
+    seed_collect_kernel<<<grid, kThreads, 0, st>>>(pos, n, d, ld, pad_index, state, keys, k);
+    GEM_CHECK_LAUNCH();
+    seed_rank_kernel<<<(unsigned)((k + kThreads - 1) / kThreads), kThreads, 0, st>>>(keys, k, out_idx, out_radius);
     GEM_CHECK_LAUNCH();
     return GEM_OK;
 }

@@ -376,6 +376,23 @@ int gem_spmv_normalized_adjacency(const int64_t *row_ptr, const int32_t *col, co
                                   float *y, int64_t n, float alpha, float beta, const float *z, float gamma,
                                   void *stream);
 
+/* Single right-hand side form (the PageRank power iteration of the correlation harness): y = alpha * (M x), x, y (n) fp32. */
+int gem_spmv_normalized_adjacency_vec(const int64_t *row_ptr, const int32_t *col, const float *dinv_sqrt, const float *x,
+                                      float *y, int64_t n, float alpha, void *stream);
+
+/* SURVEY 8(f).3, the caller graphem_seed_selection (graphem_rapids/influence.py:28-37):
+ *   radial = np.linalg.norm(positions, axis=1); seeds = np.argsort(-radial)[:k]
+ * on the device: out_idx[0..k) = the k vertex ids with the largest radius, ordered by (radius descending, id ascending),
+ * out_radius (optional) their radii.  radius = sqrt of the left-to-right fp32 sum of squares (numpy's value bit for bit).
+ * pos: (n_pad, ld) position buffer; pad_index (n) int64: vertex id -> row, or NULL (identity).  A 64-bit
+ * most-significant-digit radix select over the keys (radius bits, ~id) recomputed from the positions in every pass:
+ * 14 launches, no host synchronisation, nothing of size n materialised.  k <= gem_seed_select_max_k(), n < 2^32;
+ * ws: gem_seed_select_workspace_bytes(k) bytes, 256-byte aligned. */
+int gem_seed_select_max_k(void);
+int gem_seed_select_workspace_bytes(int64_t k, size_t *bytes);
+int gem_seed_select(const float *pos, int64_t n, int d, const int64_t *pad_index, int64_t k, int64_t *out_idx,
+                    float *out_radius, void *ws, size_t ws_bytes, void *stream);
+
 /* SURVEY 8(f).2, graph arrays on the device.  Replaces the host work of _validate_adjacency +
  * _extract_edges_from_adjacency (embedder_pytorch.py:182-245: adjacency.nonzero(), rows < cols, column_stack,
  * H2D of the int64 list) and the host build of the symmetric CSR of the pull kernels, for an adjacency whose CSR

@@ -63,6 +63,16 @@ def test_seed_selection_semantics():
     assert emb.ran == 7 and seeds == [4, 1, 3] and all(isinstance(s, int) for s in seeds)
 
 
+def test_seed_selection_reference_order_is_numpy_argsort_with_id_tie_break():
+    from graphem_rapids_b200.influence import seed_selection_reference
+    rng = np.random.default_rng(0)
+    pos = rng.standard_normal((5000, 3)).astype(np.float32)
+    r = np.linalg.norm(pos, axis=1)
+    assert seed_selection_reference(pos, 40) == np.argsort(-r)[:40].tolist()          # distinct radii: numpy's list
+    pos[[7, 3, 11]] = np.float32(9.0)                                                 # exact ties -> ascending id
+    assert seed_selection_reference(pos, 4)[:3] == [3, 7, 11]
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
 def test_fails_loudly_without_cuda():
     adj = gr.generate_random_regular(50, 4, seed=0)

@@ -670,7 +670,17 @@ def test_full_size_one_iteration_vs_oracle(workload):
         assert torch.equal(emb_b.last_sampled_indices.cpu(), samp2)
         ref2 = oracle.layout_step(torch.from_numpy(before_last), edges, samp2, n_neighbors=k, strict=True)
         assert torch.equal(emb_b._bufs["knn_idx"].cpu(), ref2["knn_full"])
-        assert rel_inf(emb_b.positions, ref2["new_pos"].numpy()) <= TOL
+        # After a few iterations the hubs of the preferential-attachment graph (degree in the thousands) sit far out
+        # (|x| ~ 100): the reference's fp32 index_add_ accumulates their thousands of force terms SEQUENTIALLY, and that
+        # rounding error -- not the kernels' -- is what remains between the two (measured 1.4e-5 of the largest
+        # coordinate).  Checked against the exact (fp64) value of the reference's formula, same intersection forces:
+        # the CUDA result is within 1e-5 of it, and closer to it than the fp32 oracle is.
+        p64 = torch.from_numpy(before_last).double()
+        truth = oracle.update(p64, oracle.spring_forces(p64, edges, 0.2, 1.0), ref2["F_inter"].double()).numpy()
+        err_gpu, err_ref = rel_inf(emb_b.positions, truth), rel_inf(ref2["new_pos"].numpy(), truth)
+        print(f"c3 iteration 3: |cuda - fp64| {err_gpu:.2e}  |fp32 oracle - fp64| {err_ref:.2e}")
+        assert err_gpu <= TOL and err_gpu <= err_ref
+        assert rel_inf(emb_b.positions, ref2["new_pos"].numpy()) <= TOL + err_ref
         # replayed == eager (same kernels, same order of the deterministic parts; atomics may reorder the few
         # intersection terms that hit one vertex)
         assert torch.equal(emb._bufs["knn_idx"], emb_b._bufs["knn_idx"])
@@ -798,3 +808,34 @@ def test_positions_setter_getter_round_trip(n, d):
         assert float(emb._pos[:, 3].abs().max()) == 0.0          # pad lane stays zero
     with pytest.raises(ValueError):
         emb.positions = x0[:-1]
+
+
+@pytest.mark.parametrize("n,d,k", [(1000, 3, 1), (1000, 3, 1000), (200000, 3, 100), (200000, 2, 5000), (1_000_000, 3, 64)])
+def test_seed_select_kernel_equals_numpy_order(n, d, k):
+    """gem_seed_select (fused radius + 64-bit radix select) == np.argsort(-np.linalg.norm(pos, axis=1))[:k], radii bit
+    for bit numpy's; exactly equal radii (duplicated rows, planted on purpose) come out by ascending vertex id."""
+    import graphem_rapids_b200 as gr
+    from graphem_rapids_b200.influence import device_seed_selection, seed_selection_reference
+    adj = gr.generate_random_regular(n, 4, seed=1)
+    rng = np.random.default_rng(n + k)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    dup = rng.integers(0, n, size=max(4, n // 50))
+    x[dup] = x[dup[0]] * np.float32(3.0)                       # a block of exactly tied, large radii
+    x[rng.integers(0, n, size=5)] = 0.0                        # and some zeros
+    emb = gr.GraphEmbedderPyTorch(adj, n_components=d, device="cuda:0", verbose=False, seed=0, initial_positions=x)
+    seeds, rad = device_seed_selection(emb, k, return_radii=True)
+    want = seed_selection_reference(x, k)
+    assert seeds == want
+    r = np.linalg.norm(x, axis=1)
+    assert np.array_equal(np.asarray(rad, dtype=np.float32), r[want])
+    # where the radii are distinct this IS the reference's list
+    rs = r[seed_selection_reference(x, min(k + 1, n))]            # one more than k: a tie may straddle the cut
+    distinct = np.ones(len(rs), dtype=bool)
+    distinct[1:] &= rs[1:] != rs[:-1]
+    distinct[:-1] &= rs[:-1] != rs[1:]
+    distinct = distinct[:k]
+    ref = np.argsort(-r)[:k]
+    assert np.array_equal(np.asarray(seeds)[distinct], ref[distinct])
+    # the public caller: runs the layout first, then selects on the device
+    s2 = gr.graphem_seed_selection(emb, min(k, 50), num_iterations=3)
+    assert s2 == seed_selection_reference(emb.positions, min(k, 50))
