@@ -312,7 +312,9 @@ def run_b200(args, w):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a rank-divergent bug must not hold N GPUs for the default 10-minute watchdog
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
 
     def barrier():
         if world > 1:
@@ -383,7 +385,12 @@ def run_b200(args, w):
 
     # ---- sustained: >= 2 s of back-to-back replays (no flush: every array of the step is larger than it can keep
     # in L2 across an iteration only at C4/C5; said in the line), clocks sampled over the whole region
-    sus_iters = int(min(max(2.2e3 / max(total_ms / K, 1e-3), K), 200000))
+    est_ms = total_ms / K
+    if world > 1:                              # the iteration count must be the SAME on every rank (device barriers inside)
+        t = torch.tensor([est_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        est_ms = float(t.item())
+    sus_iters = int(min(max(2.2e3 / max(est_ms, 1e-3), K), 200000))
     if args.profile_mode:
         sus_iters = 2
     sus_iters += sus_iters & 1
@@ -473,11 +480,17 @@ def run_b200(args, w):
                           "vs": "replica comparison only (sampler='torch' streams differ between two objects in one process)"}
             ref_emb.close()
         if emb.exchange == "p2p":
-            ph = emb.profile_phases(20)
-            t = torch.tensor([ph[k] for k in emb.PHASES], device=dev, dtype=torch.float64)
+            try:
+                ph = emb.profile_phases(20)
+                vals = [ph[k] for k in emb.PHASES]
+            except Exception as exc:  # pylint: disable=broad-exception-caught
+                vals, ph = [-1.0] * len(emb.PHASES), {"error": repr(exc)}
+            t = torch.tensor(vals, device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             phase_us = {"end_of_phase_us_since_step_start_max_over_ranks": dict(zip(emb.PHASES, [round(float(x), 1) for x in t.tolist()])),
                         "note": "external CUDA events inside the captured iteration; prep and colsum run on the side stream"}
+            if "error" in ph:
+                phase_us["error"] = ph["error"]
 
     # max over ranks
     if world > 1:

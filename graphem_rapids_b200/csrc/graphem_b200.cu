@@ -690,7 +690,7 @@ struct PrepArgs {
     int g, per, s, kp1;
     int chunks;                      // the g bound CTAs fold their per-query minima into `chunks` <= g slots
     unsigned int *chunkkey;          // [chunks][s] keys 0x7F800000 - bits(min): 0 = +inf (self-cleaning, zero-initialised once)
-    float *theta, *tau, *qcoef;
+    float *theta, *tau, *qcoef;      // qcoef: where the coefficient pairs go (the constant-bank slot itself, or a staging copy)
     uint32_t *counts; int ncounts;
     unsigned int *ticket;
 };
@@ -712,19 +712,20 @@ __device__ __forceinline__ float prep_kth_smallest(unsigned int *__restrict__ ke
     float lst[K];
 #pragma unroll
     for (int r = 0; r < K; ++r) lst[r] = kInf;
-    for (int c0 = 0; c0 < chunks; c0 += 8) {
-        unsigned int kk[8];
+    // the loads of a batch are all in flight before the first is consumed (one L2 round trip per 16 slots, not per slot)
+    for (int c0 = 0; c0 < chunks; c0 += 16) {
+        unsigned int kk[16];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) kk[u] = (c0 + u < chunks) ? __ldcg(keys + (int64_t)(c0 + u) * s + q) : 0u;
+        for (int u = 0; u < 16; ++u) kk[u] = (c0 + u < chunks) ? __ldcg(keys + (int64_t)(c0 + u) * s + q) : 0u;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            if (c0 + u < chunks) keys[(int64_t)(c0 + u) * s + q] = 0u;
+        for (int u = 0; u < 16; ++u) {
             const float x = kk[u] ? prep_unkey(kk[u]) : kInf;
 #pragma unroll
             for (int r = K - 1; r >= 1; --r) lst[r] = fminf(lst[r], fmaxf(lst[r - 1], x));   // sorted insertion, branch-free
             lst[0] = fminf(lst[0], x);
         }
     }
+    for (int c = 0; c < chunks; ++c) keys[(int64_t)c * s + q] = 0u;          // self-cleaning: empty slots for the next launch
     float kth = kInf;
 #pragma unroll
     for (int r = 0; r < K; ++r)
@@ -1067,10 +1068,12 @@ __global__ void __launch_bounds__(kScanThreads, 2) knn_scan_kernel(const typenam
                                                                    uint32_t *__restrict__ counts,
                                                                    uint64_t *__restrict__ keys, int cap,
                                                                    uint32_t *__restrict__ tile_counter,
-                                                                   unsigned long long *__restrict__ stats, int qb, int slot,
+                                                                   unsigned long long *__restrict__ stats, int qb0, int slot,
                                                                    int qs) {
-    // qb (query block) and slot (coefficient bank) are kernel PARAMETERS, not blockIdx.y: ptxas keeps parameter-derived values in
-    // uniform registers, which the constant-bank coefficient addressing below depends on
+    const int qb = qb0 + (int)blockIdx.y;
+    // query block = blockIdx.y (+ qb0): a batch of up to 1024 queries is ONE launch of (g, blocks) CTAs.  Block indices and
+    // kernel parameters are uniform by construction, which the constant-bank coefficient addressing below depends on
+    // (ptxas keeps them in uniform registers; a per-warp value read from shared memory does not qualify)
     using CandT = typename MidT<D>::T;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const ScanShared S = scan_shared<sizeof(CandT)>(smem_raw, kp1);
@@ -1580,6 +1583,8 @@ __global__ void __launch_bounds__(kThreads) topk_merge_intersect_kernel(const fl
             qa = make_float4(a2.x, a2.y, 0.f, 0.f); qb4 = make_float4(b2.x, b2.y, 0.f, 0.f);
         }
     }
+    if (t < kMaxFastKp1) s_nb[t] = -1;                        // a rank nobody claims (fewer than kp1 real entries, NaN
+                                                              // distances) must read as "no neighbour" in the tail
     for (int i = t; i < total; i += blockDim.x) {
         const int p = i / kp1, r = i % kp1;
         sd[i] = dists[(int64_t)p * dist_stride + (int64_t)q * kp1 + r] + 0.f;
@@ -2320,6 +2325,9 @@ inline int grid_for(int64_t work, int per_sm) {
 }
 
 // ---- KNN fast path plumbing -------------------------------------------------------------------
+constexpr int kMaxDevices = 64;
+float *g_coef_bank[kMaxDevices];       // device address of c_qcoef per device (gem_init)
+
 struct KnnLayout {
     int g;                  // scan CTAs over the candidate axis
     int qs;                 // log2 of the query split of the scan's work items
@@ -2337,8 +2345,11 @@ KnnLayout knn_layout(int64_t e, int64_t s, int kp1) {
     // scan grid: every warp of a CTA is its own consumer of 192-candidate blocks, so a small problem gets only as
     // many CTAs as it has blocks for (round 1 launched 2 x SMs CTAs for 27 blocks at E = 5 K)
     const int64_t nblocks = (e + kCandBlock - 1) / kCandBlock;
-    int qs = 0;                                           // query split: up to 8 work items per candidate block
-    while (qs < 3 && (nblocks << (qs + 1)) <= (int64_t)L.g_max * kWarps) ++qs;
+    // query split: up to 8 work items per candidate block, until every warp of the GPU has ~4 items to balance (a
+    // 500 K-candidate shard is 2605 blocks for 2368 warps: without the split the scan takes as long as its unluckiest
+    // warp's two whole blocks)
+    int qs = 0;
+    while (qs < 3 && (nblocks << qs) < (int64_t)4 * L.g_max * kWarps) ++qs;
     static_assert(((kQB / 2) >> 3) % kPairChunk == 0, "a query part is a whole number of pair chunks");
     L.qs = qs;
     int64_t g = ((nblocks + kWarps - 1) / kWarps) << qs;      // CTAs per query part x parts
@@ -2408,13 +2419,25 @@ int knn_prepare(const KnnLayout &L, char *w, PrepArgs A, int64_t bound_samples, 
     if (!lg) { A.row_ptr = nullptr; A.col = nullptr; }
     const int grid = A.g + (lg ? (A.s + kWarps - 1) / kWarps : 0);
     const size_t smem = (size_t)A.s * sizeof(float4);
+    // Query coefficients of this batch -> constant bank slot (uniform operands of the scan's packed FMAs).  The last CTA
+    // of the preparation kernel stores them straight into the slot through the symbol's device address: constant
+    // memory may be modified from the device as long as no concurrently running grid reads it (CUDA programming guide,
+    // __constant__), and the slot's only reader is this object's scan, ordered behind this kernel.  That removes a
+    // ~6 us device-to-device copy node from the path of every iteration.  GEM_COEF_STAGED=1 restores the staged copy.
+    int dev = 0;
+    GEM_CUDA(cudaGetDevice(&dev));
+    static const bool staged = [] { const char *v = getenv("GEM_COEF_STAGED"); return v && v[0] == '1'; }();
+    float *bank = (dev >= 0 && dev < kMaxDevices) ? g_coef_bank[dev] : nullptr;
+    float *staging = A.qcoef;
+    const bool direct = !staged && bank != nullptr;
+    if (direct) A.qcoef = bank + (size_t)slot * 2 * 3 * (kMaxBatchQ / 2);
     knn_prep_kernel<D><<<grid, kThreads, smem, st>>>(A);
     GEM_CHECK_LAUNCH();
     stage_mark();                                                   // GEM_STAGE_KNN_BOUND (the fused preparation)
-    // query coefficients of this batch -> constant bank (uniform operands of the scan's packed FMAs)
-    GEM_CUDA(cudaMemcpyToSymbolAsync(c_qcoef, A.qcoef, sizeof(float2) * 3 * (kMaxBatchQ / 2),
-                                     (size_t)slot * sizeof(float2) * 3 * (kMaxBatchQ / 2), cudaMemcpyDeviceToDevice, st));
-    stage_mark();                                                   // GEM_STAGE_KNN_THRESHOLD (the copy)
+    if (!direct)
+        GEM_CUDA(cudaMemcpyToSymbolAsync(c_qcoef, staging, sizeof(float2) * 3 * (kMaxBatchQ / 2),
+                                         (size_t)slot * sizeof(float2) * 3 * (kMaxBatchQ / 2), cudaMemcpyDeviceToDevice, st));
+    stage_mark();                                                   // GEM_STAGE_KNN_THRESHOLD (the copy, staged mode only)
     return GEM_OK;
 }
 
@@ -2431,10 +2454,11 @@ int knn_scan_select(const KnnLayout &L, char *w, const float *mid, int64_t e, co
     uint64_t *keys = reinterpret_cast<uint64_t *>(w + L.off_keys);
     const size_t scan_smem = scan_smem_bytes((int)sizeof(CandT), kp1);
     const size_t sel_smem = (size_t)L.cap * sizeof(uint64_t);
-    for (int qb = 0; qb * kQB < sb; ++qb) {        // S = 256: one launch
-        knn_scan_kernel<D><<<L.g, kScanThreads, scan_smem, st>>>(
+    {
+        const dim3 grid((unsigned)L.g, (unsigned)((sb + kQB - 1) / kQB));       // S = 256: (g, 1)
+        knn_scan_kernel<D><<<grid, kScanThreads, scan_smem, st>>>(
             reinterpret_cast<const CandT *>(mid), e, qm, sb, kp1, theta, tau, counts, keys, L.cap, counts + L.sb,
-            g_knn_stats ? reinterpret_cast<unsigned long long *>(w + L.off_stats) : nullptr, qb, slot, L.qs);
+            g_knn_stats ? reinterpret_cast<unsigned long long *>(w + L.off_stats) : nullptr, 0, slot, L.qs);
         GEM_CHECK_LAUNCH();
     }
     stage_mark();                                                   // GEM_STAGE_KNN_SCAN
@@ -2477,7 +2501,6 @@ int knn_fast(const float *mid, int64_t e, int64_t idx_offset, const float *qmid,
 }
 
 // second stream + fork/join events of gem_layout_step, per device (created by gem_init)
-constexpr int kMaxDevices = 64;
 struct AuxStream { cudaStream_t st = nullptr; cudaEvent_t fork = nullptr, join = nullptr, spring = nullptr, stats = nullptr; };
 AuxStream g_aux[kMaxDevices];
 // gem_layout_step enqueues on two streams with library-owned events: one enqueue at a time per process
@@ -2517,6 +2540,11 @@ int gem_init(void) {
     const int prep_smem = kMaxBatchQ * (int)sizeof(float4);
     GEM_CUDA(cudaFuncSetAttribute(knn_prep_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, prep_smem));
     GEM_CUDA(cudaFuncSetAttribute(knn_prep_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, prep_smem));
+    if (dev >= 0 && dev < kMaxDevices) {
+        void *bank = nullptr;
+        GEM_CUDA(cudaGetSymbolAddress(&bank, c_qcoef));
+        g_coef_bank[dev] = reinterpret_cast<float *>(bank);
+    }
     if (dev >= 0 && dev < kMaxDevices && g_aux[dev].st == nullptr) {
         // the one exception to "the library owns nothing": a non-blocking side stream and two events, so
         // that gem_layout_step can run the KNN preparation concurrently with the spring kernel
@@ -3110,13 +3138,12 @@ int gem_layout_step(const gem_plan *p, void *stream) {
         if (have_hint) { A.row_ptr = p->row_ptr; A.col = p->col; A.hint_out = p->tau_hint; }
         A.bound_edges = ed; A.e_bound = p->e;                           // midpoints recomputed from (pos, edges): no wait for `mid`
         A.s = (int)p->s; A.kp1 = p->kp1;
-        // the preparation is hidden behind the spring kernel here: a 2x larger sample than the balanced size buys a
-        // tighter bound (fewer slow-path events inside the scan, which IS on the critical path); the profiling
-        // variant uses the same size so that its scan stage is the production scan
+        // balanced sample size (bound_sample_size): measured on C3, 0.5x / 1x / 2x / 4x give 0.297 / 0.291 / 0.297 /
+        // 0.312 ms per iteration -- the preparation shares the SMs with the spring kernel, a larger sample delays both
         static const float scale_env = [] {                       // tuning knob (bench sweeps): GEM_BOUND_SCALE
             const char *v = getenv("GEM_BOUND_SCALE");
             const float f = v ? (float)atof(v) : 0.f;
-            return f > 0.f ? f : 2.f;
+            return f > 0.f ? f : 1.f;
         }();
         const int64_t samples = bound_sample_size(p->e, p->kp1, scale_env);
         rc = p->d == 2 ? knn_prepare<2>(L, w, A, samples, p->coef_slot, side) : knn_prepare<3>(L, w, A, samples, p->coef_slot, side);

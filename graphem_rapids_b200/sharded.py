@@ -241,8 +241,9 @@ class CudaStages:
 
     def _mark(self, name, side=False):
         if self._marks is not None:
-            ev = self._marks.setdefault(name, torch.cuda.Event(enable_timing=True, external=True))
-            ev.record(self._side if side else torch.cuda.current_stream(self.device))
+            if name not in self._marks:      # external events only exist for capture (timing nodes inside a CUDA graph)
+                self._marks[name] = torch.cuda.Event(enable_timing=True, external=torch.cuda.is_current_stream_capturing())
+            self._marks[name].record(self._side if side else torch.cuda.current_stream(self.device))
 
     # ------------------------------------------------------------------ product flow over peer-mapped buffers
     p2p_ready = False
@@ -305,7 +306,10 @@ class CudaStages:
         a.qmid_out = eng.qmid.data_ptr()
         a.row_ptr, a.col, a.tau_hint_out = self.row_ptr.data_ptr(), self.col.data_ptr(), eng.tau_hint.data_ptr()
         # bound with the WHOLE (replicated) edge list: the same global thresholds on every rank, no exchange
-        a.bound_edges, a.e_bound, a.bound_samples = self.edges32.data_ptr(), L.n_edges, 0
+        # (half the balanced sample size: here the preparation is on the critical path -- it overlaps only the short,
+        # NVLink-bound spring kernel -- while a rank's share of the scan's slow-path events is 1/world of the total)
+        a.bound_edges, a.e_bound = self.edges32.data_ptr(), L.n_edges
+        a.bound_samples = max(8192, int(0.5 * 43.0 * (kp1 * L.n_edges) ** 0.5))
         a.coef_slot = self.coef_slot
         a.ws, a.ws_bytes = ws.data_ptr(), self._knn_ws_bytes
         _cabi.check(lib.gem_knn_prep(ctypes.byref(a), self._side_ptr()), "gem_knn_prep")

@@ -156,7 +156,8 @@ def _nccl_worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    import datetime
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev, timeout=datetime.timedelta(seconds=120))
     try:
         n, d, k = 40000 * max(1, world // 2), 3, 10
         adj = gr.generate_ba(n, 4, seed=1)
@@ -165,14 +166,21 @@ def _nccl_worker(rank, world, port, out):
                                    seed=4, initial_positions=pos0)
         ref = torch.from_numpy(pos0)
         ok, worst = True, 0.0
+        flags = {}
         for it in range(3):                                                   # eager steps of the product flow vs the oracle
             emb.update_positions()
             samp = emb.last_sampled_indices.cpu()
             o = oracle.layout_step(ref, emb.edges.cpu(), samp, n_neighbors=k, strict=True)
-            ok &= bool(torch.equal(emb._engine.knn_idx.cpu(), o["knn_full"]))
+            flags[f"knn_it{it}"] = bool(torch.equal(emb._engine.knn_idx.cpu(), o["knn_full"]))
             got = emb.positions
-            worst = max(worst, rel_inf(got, o["new_pos"].numpy()))
+            flags[f"pos_it{it}"] = rel_inf(got, o["new_pos"].numpy())
+            worst = max(worst, flags[f"pos_it{it}"])
             ref = torch.from_numpy(got)
+        ok &= all(v for k_, v in flags.items() if k_.startswith("knn"))
+        # the private stage methods take positions / edges in ORIGINAL vertex numbering on a multi-rank object too
+        F = emb._compute_spring_forces(torch.from_numpy(pos0), emb.edges).cpu().numpy()
+        flags["stage_api_spring"] = rel_inf(F, oracle.spring_forces(torch.from_numpy(pos0), emb.edges.cpu(), 0.2, 1.0).numpy())
+        ok &= flags["stage_api_spring"] <= TOL
         print(f'[{rank}] exchange: {emb.exchange}', flush=True)
         assert emb.exchange == "p2p"
         # CUDA-graph replay of the whole sharded step (kernels on both streams, peer stores, device barriers; one graph
@@ -186,20 +194,25 @@ def _nccl_worker(rank, world, port, out):
             emb2.update_positions()
         emb.run_layout_device(5)
         torch.cuda.synchronize()
-        ok &= bool(torch.equal(emb.last_sampled_indices, emb2.last_sampled_indices))
-        worst = max(worst, rel_inf(emb.positions, emb2.positions) * 1e-2)      # atomics reorder sums: 1e-3 allowed
+        flags["samples_replay_vs_eager"] = bool(torch.equal(emb.last_sampled_indices, emb2.last_sampled_indices))
+        flags["pos_replay_vs_nccl_flow"] = rel_inf(emb.positions, emb2.positions)
+        ok &= flags["samples_replay_vs_eager"]
+        worst = max(worst, flags["pos_replay_vs_nccl_flow"] * 1e-2)           # atomics reorder sums: 1e-3 allowed
         mine = emb._pos.clone()
         dist.broadcast(mine, src=0)
         same = bool(torch.equal(mine, emb._pos))
+        flags["replicas_identical"] = same
         # host I/O split across the ranks: every rank uploads its chunk, all replicas end up with the whole array
         lo, hi = emb.chunk_rows()
         full = np.random.default_rng(5).standard_normal((n, d)).astype(np.float32)
         emb.load_positions_chunk(torch.from_numpy(full[lo:hi]).pin_memory())
         torch.cuda.synchronize()
-        same &= bool(np.array_equal(emb.positions, full))
+        flags["chunk_upload"] = bool(np.array_equal(emb.positions, full))
         back = torch.empty((hi - lo, d), dtype=torch.float32).pin_memory()
         emb.read_positions_chunk(back)
-        same &= bool(np.array_equal(back.numpy(), full[lo:hi]))
+        flags["chunk_download"] = bool(np.array_equal(back.numpy(), full[lo:hi]))
+        same &= flags["chunk_upload"] and flags["chunk_download"]
+        print(f"[{rank}] flags: {flags}", flush=True)
         flag = torch.tensor([int(ok and same and worst <= TOL)], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if rank == 0:
