@@ -491,6 +491,13 @@ def run_b200(args, w):
                         "note": "external CUDA events inside the captured iteration; prep and colsum run on the side stream"}
             if "error" in ph:
                 phase_us["error"] = ph["error"]
+            try:
+                kt = emb.profile_kernels(10, scan_ctas=True)
+            except Exception as exc:  # pylint: disable=broad-exception-caught
+                kt = {"error": repr(exc)}
+            phase_us["kernel_begin_end_us_rank0"] = kt
+            phase_us["kernel_note"] = ("%globaltimer stamps written by the kernels inside the replayed iteration of rank 0 "
+                                       "(first CTA start, last CTA end), relative to the first kernel's start")
 
     # max over ranks
     if world > 1:
@@ -570,6 +577,12 @@ def run_b200(args, w):
                                    "frac": t_roof * 1e3 / (total_ms / K),
                                    "frac_sustained": t_roof * 1e3 / sus_ms}
 
+    kernel_timeline = None
+    if world == 1 and rank == 0:
+        try:
+            kernel_timeline = emb.profile_kernels(10, scan_ctas=True)
+        except Exception as exc:  # pylint: disable=broad-exception-caught
+            kernel_timeline = {"error": repr(exc)}
     exchange = emb.exchange if world > 1 else None
     if world > 1:
         emb.close()            # captured graphs hold barrier / NCCL kernels: release them before the communicator
@@ -637,6 +650,8 @@ def run_b200(args, w):
         line["parity"] = parity
     if phase_us is not None:
         line["phase_us"] = phase_us
+    if kernel_timeline is not None:
+        line["kernel_begin_end_us"] = kernel_timeline      # %globaltimer stamps inside the replayed iteration
     if setup is not None:
         line["graph_setup_s"] = setup          # constructor with given initial positions: device vs host graph build
     print(json.dumps(line), flush=True)

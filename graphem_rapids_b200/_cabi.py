@@ -14,6 +14,7 @@ from . import build as _build
 
 _lib = None
 ABI_VERSION = 3
+STAMP_NAMES = ["knn_prep", "spring_csr", "colsum", "knn_scan", "knn_select", "topk_merge_intersect", "normalise"]
 STAGE_NAMES = ["sample", "spring_mid", "query_mid", "knn_bound", "knn_threshold", "knn_scan", "knn_select",
                "knn_fallback", "intersect", "update"]
 _inited_devices = set()
@@ -79,7 +80,11 @@ SIGNATURES = {
     "gem_spring_update_csr": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64,
                                       c_int, c_float, c_float, c_void_p, c_void_p, c_int64, c_void_p]),
     "gem_spring_update_csr_push": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64,
-                                           c_int, c_float, c_float, POINTER(c_void_p), c_int, c_void_p, c_int64, c_void_p]),
+                                           c_int, c_float, c_float, POINTER(c_void_p), c_int, c_void_p, c_int64, c_void_p,
+                                           c_void_p]),
+    "gem_debug_stamps": (c_int, [c_void_p]),
+    "gem_debug_stamp_count": (c_int, []),
+    "gem_debug_stamp_words": (c_int, []),
     "gem_coef_slots": (c_int, []),
     "gem_coef_slot_acquire": (c_int, [POINTER(c_int)]),
     "gem_coef_slot_release": (c_int, [c_int]),

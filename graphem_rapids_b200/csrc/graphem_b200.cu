@@ -50,6 +50,36 @@ int num_sms() {
 constexpr int kMaxPeers = 16;
 struct PeerPtrs { float *p[kMaxPeers]; };
 
+// Optional kernel time stamps (gem_debug_stamps): when a buffer is registered, the first thread of every CTA of the
+// iteration's kernels records %globaltimer -- begin = min over CTAs, end = max over CTAs -- into slot 2*id / 2*id+1.
+// This is how the per-kernel timeline INSIDE a multi-rank CUDA-graph replay is measured (ncu must not wrap a
+// multi-rank command, and events between launches cannot separate the two kernels of one C call).
+__device__ unsigned long long *d_stamps = nullptr;
+enum { kStampPrep = 0, kStampSpring, kStampColsum, kStampScan, kStampSelect, kStampMerge, kStampNormalise, kStampCount };
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void stamp_begin(int id) {
+    if (threadIdx.x == 0) {
+        unsigned long long *st = d_stamps;
+        if (st != nullptr) atomicMin(st + 2 * id, globaltimer_ns());
+    }
+}
+__device__ __forceinline__ void stamp_end(int id) {
+    if (threadIdx.x == 0) {
+        unsigned long long *st = d_stamps;
+        if (st != nullptr) atomicMax(st + 2 * id + 1, globaltimer_ns());
+    }
+}
+
+struct StampScope {                      // begin at construction, end at every exit of the kernel
+    int id;
+    __device__ __forceinline__ explicit StampScope(int i) : id(i) { stamp_begin(i); }
+    __device__ __forceinline__ ~StampScope() { stamp_end(id); }
+};
+
 // optional per-stage CUDA events (gem_profile_step); nullptr on the product path
 struct StageTimer {
     cudaEvent_t ev[GEM_NUM_STAGES + 1];
@@ -169,6 +199,7 @@ __global__ void __launch_bounds__(kThreads) spring_mid_kernel(const float *__res
 // kHubDeg (hubs of preferential-attachment graphs) are left to one CTA each (blocks >= main_blocks).
 constexpr int kGrp = 4;
 constexpr int kHubDeg = 128;
+constexpr int kSpringChunk = 512;           // vertices per dynamic work claim (8 passes of a CTA)
 
 // The pull form evaluates every edge twice, so its arithmetic matters: sqrt and 1/x come from the
 // SFU (sqrt.approx / rcp.approx, <= 1 ulp each) instead of the ~40-instruction IEEE sequences of
@@ -235,7 +266,8 @@ __global__ void __launch_bounds__(kThreads) spring_csr_kernel(const float *__res
                                                               int n_hub_blocks, float neg_k_attr, float l_min,
                                                               float *__restrict__ force,
                                                               typename MidT<D>::T *__restrict__ mid, int64_t mid_base,
-                                                              const SpringPeers sp) {
+                                                              const SpringPeers sp, unsigned int *__restrict__ work) {
+    const StampScope stamp(kStampSpring);
     if ((int)blockIdx.x < n_hub_blocks) {
         // ---- one CTA per hub row; scheduled first so the long rows overlap the bulk of the work
         const int64_t v = hubs[blockIdx.x];
@@ -267,11 +299,36 @@ __global__ void __launch_bounds__(kThreads) spring_csr_kernel(const float *__res
     const int mb = (int)blockIdx.x - n_hub_blocks;
     const int64_t stride = ((int64_t)(gridDim.x - n_hub_blocks) * kThreads) / kGrp;
     const int64_t nv = v_end - v_begin;
-    // every lane of a warp runs the same number of outer iterations (the shuffles need all 32 lanes)
-    const int64_t first = ((int64_t)mb * kThreads + threadIdx.x) / kGrp;
-    const int64_t warp_first = ((int64_t)mb * kThreads + (threadIdx.x & ~31)) / kGrp;
-    for (int64_t base = warp_first, i = first; base < nv; base += stride, i += stride) {
-        const bool valid = i < nv;
+    // Vertex ranges: work == nullptr -> static grid stride; else chunks of kSpringChunk vertices claimed from a global
+    // counter (work[0]; work[1] = exit ticket: the last CTA out zeroes both).  In gem_layout_step the KNN preparation
+    // kernel shares the SMs with this one for its first ~40 us; the CTAs of a static grid that could only start once
+    // it had left all had a full share of the rows ahead of them (spring kernel 77 us alone, 94 us in the step).
+    __shared__ unsigned int s_claim;
+    if (work != nullptr) {
+        if (threadIdx.x == 0) s_claim = atomicAdd(work, 1u);
+        __syncthreads();
+    }
+    constexpr int kPass = kThreads / kGrp;                            // vertices per CTA pass
+    const int64_t n_claims = (nv + kSpringChunk - 1) / kSpringChunk;
+    for (;;) {
+        int64_t end = nv, step = stride;
+        // every lane of a warp runs the same number of outer iterations (the shuffles need all 32 lanes)
+        int64_t i0 = ((int64_t)mb * kThreads + threadIdx.x) / kGrp;
+        int64_t b0 = ((int64_t)mb * kThreads + (threadIdx.x & ~31)) / kGrp;
+        if (work != nullptr) {
+            // claim c = the passes {c, c + n_claims, c + 2 n_claims, ...} of 64 vertices: interleaved over the whole
+            // range like the static stride (contiguous chunks put all the high-degree rows of a hub-first vertex
+            // order into a few claims: measured 181 us instead of 94 us on the preferential-attachment graph)
+            const int64_t c = (int64_t)s_claim;
+            __syncthreads();                                         // everyone has read the claim
+            if (c >= n_claims) break;
+            if (threadIdx.x == 0) s_claim = atomicAdd(work, 1u);     // next claim: its latency hides behind this one
+            step = n_claims * kPass;
+            i0 = c * kPass + threadIdx.x / kGrp;
+            b0 = c * kPass + (threadIdx.x & ~31) / kGrp;
+        }
+    for (int64_t base = b0, i = i0; base < end; base += step, i += step) {
+        const bool valid = i < end;
         const int64_t v = v_begin + (valid ? i : 0);
         int deg = 0, lo = 0;
         const int32_t *cp = col;
@@ -307,6 +364,12 @@ __global__ void __launch_bounds__(kThreads) spring_csr_kernel(const float *__res
         acc = acc + shfl_xor_vec(acc, 1);
         acc = acc + shfl_xor_vec(acc, 2);
         if (valid && !hub && g == 0) spring_emit<D, FUSE>(pv, acc, force, v, v_begin, sp);   // isolated vertices too
+    }
+        if (work == nullptr) break;
+        __syncthreads();                                             // the next claim is in shared memory
+    }
+    if (work != nullptr && threadIdx.x == 0) {
+        if (atomicAdd(work + 1, 1u) == gridDim.x - (unsigned)n_hub_blocks - 1u) { work[0] = 0u; work[1] = 0u; }
     }
 }
 
@@ -540,12 +603,18 @@ constexpr int kBoundTile = 768;             // bound pass: candidates per smem t
 constexpr int kC = 6;                       // scan: candidates per lane
 constexpr int kCandBlock = 32 * kC;         // scan: candidates per warp and tile
 constexpr int kWStages = 2;                 // scan: TMA stages per warp (warp-private ring)
-constexpr int kTile = kWarps * kWStages * kCandBlock;   // scan: candidates staged per CTA at any time
+// scan CTA: ONE per SM with 16 warps.  Two 8-warp CTAs per SM (round 1) shared the SM unevenly -- the warp schedulers
+// favour the older CTA: on C3 the first CTA of every SM ended after ~131 us, the second after ~176 us, i.e. every SM ran
+// its last ~45 us at half occupancy.  One CTA whose 16 warps draw blocks from one counter ends all at once.
+constexpr int kScanWarps = 16;
+constexpr int kScanThreads = 32 * kScanWarps;
+constexpr int kTile = kScanWarps * kWStages * kCandBlock;   // scan: candidates staged per CTA at any time
 constexpr int kPairChunk = 8;               // scan: query pairs between two slow-path checks
 constexpr int kMaxBatchQ = 1024;            // queries per scan batch (= constant-bank coefficient capacity)
 constexpr float kSlack = 3.814697265625e-06f;   // 2^-18, see DESIGN.md (filter error budget)
 constexpr int kSurvMax = 1024;
-constexpr int kMaxFastKp1 = 64;
+constexpr int kSelectCapMax = 24576;        // keys per query the select kernel can stage (192 KB of shared memory)
+constexpr int kMaxFastKp1 = 56;           // the 16-warp scan CTA: staging (96 KB) + 256 lists of k+1 keys must fit 227 KB
 
 __device__ __forceinline__ void cand_xyzn(const float4 &c, float &x, float &y, float &z, float &n) { x = c.x; y = c.y; z = c.z; n = c.w; }
 __device__ __forceinline__ void cand_xyzn(const float2 &c, float &x, float &y, float &z, float &n) { x = c.x; y = c.y; z = 0.f; n = c.x * c.x + c.y * c.y; }
@@ -735,6 +804,7 @@ __device__ __forceinline__ float prep_kth_smallest(unsigned int *__restrict__ ke
 
 template <int D>
 __global__ void __launch_bounds__(kThreads, 3) knn_prep_kernel(const PrepArgs A) {
+    const StampScope stamp(kStampPrep);
     using CandT = typename MidT<D>::T;
     extern __shared__ __align__(16) unsigned char prep_smem[];
     float4 *s_q = reinterpret_cast<float4 *>(prep_smem);                      // (a0,a1,a2,qn) per query
@@ -909,9 +979,9 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// dynamic shared memory of the scan: [stages kWarps*kWStages*kCandBlock CandT][lists kQB*kp1 u64][bound kQB u64]
+// dynamic shared memory of the scan: [stages kScanWarps*kWStages*kCandBlock CandT][lists kQB*kp1 u64][bound kQB u64]
 //                                    [lqpar kQB float4][ltheta kQB f32][lcount kQB i32][lock kQB i32][wslot kQB i32]
-__host__ __device__ inline size_t scan_smem_bytes(int cand_bytes, int kp1) {
+__host__ __device__ constexpr size_t scan_smem_bytes(int cand_bytes, int kp1) {
     return (size_t)kTile * cand_bytes + (size_t)kQB * kp1 * 8 + (size_t)kQB * 8 + (size_t)kQB * 16 +
            (size_t)kQB * 4 * 4;
 }
@@ -1059,9 +1129,8 @@ __device__ __noinline__ void scan_slow_block(unsigned char *smem_raw, int kp1, u
 // simply takes fewer blocks, and the tail of the launch is one block, not one CTA-wide tile) and
 // stages them in a warp-private ring of kWStages TMA bulk copies (cp.async.bulk -> UBLKCP) with one
 // mbarrier per stage.  No CTA-wide tile hand-off, no producer warp, no inter-warp waiting.
-constexpr int kScanThreads = kThreads;
 template <int D>
-__global__ void __launch_bounds__(kScanThreads, 2) knn_scan_kernel(const typename MidT<D>::T *__restrict__ mid, int64_t e,
+__global__ void __launch_bounds__(kScanThreads, 1) knn_scan_kernel(const typename MidT<D>::T *__restrict__ mid, int64_t e,
                                                                    const float *__restrict__ qmid, int s, int kp1,
                                                                    const float *__restrict__ theta,
                                                                    const float *__restrict__ tau,
@@ -1071,14 +1140,15 @@ __global__ void __launch_bounds__(kScanThreads, 2) knn_scan_kernel(const typenam
                                                                    unsigned long long *__restrict__ stats, int qb0, int slot,
                                                                    int qs) {
     const int qb = qb0 + (int)blockIdx.y;
+    const StampScope stamp(kStampScan);
     // query block = blockIdx.y (+ qb0): a batch of up to 1024 queries is ONE launch of (g, blocks) CTAs.  Block indices and
     // kernel parameters are uniform by construction, which the constant-bank coefficient addressing below depends on
     // (ptxas keeps them in uniform registers; a per-warp value read from shared memory does not qualify)
     using CandT = typename MidT<D>::T;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const ScanShared S = scan_shared<sizeof(CandT)>(smem_raw, kp1);
-    __shared__ __align__(8) uint64_t full_bar[kWarps][kWStages];
-    __shared__ int blk_id[kWarps][kWStages];                 // -1: no more blocks
+    __shared__ __align__(8) uint64_t full_bar[kScanWarps][kWStages];
+    __shared__ int blk_id[kScanWarps][kWStages];             // -1: no more blocks
     __shared__ unsigned int s_next;                          // next block ordinal of this CTA
 
     const int lane = threadIdx.x & 31;
@@ -1114,7 +1184,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) knn_scan_kernel(const typenam
     }
     if (threadIdx.x == 0) {
         s_next = 0;
-        for (int w = 0; w < kWarps; ++w)
+        for (int w = 0; w < kScanWarps; ++w)
             for (int i = 0; i < kWStages; ++i) mbar_init(&full_bar[w][i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -1181,6 +1251,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) knn_scan_kernel(const typenam
             }
             uint32_t hitmask = 0;
             static_assert(kQB / 2 / kPairChunk <= 32, "one bit per pair chunk");
+            static_assert(scan_smem_bytes(16, kMaxFastKp1) + 1024 <= 227 * 1024, "scan CTA exceeds the shared memory of an SM");
             for (int mcr = 0; mcr < mc_n; mcr += kPairChunk) {
                 const int mc = mc_lo + mcr;
                 bool any = false;
@@ -1470,6 +1541,7 @@ __device__ __forceinline__ void select_emit(const SelectOut &so, int64_t pos, in
 __global__ void __launch_bounds__(kThreads) knn_select_kernel(const uint32_t *__restrict__ counts,
                                                               const uint64_t *__restrict__ keys, int cap, int kp1,
                                                               const SelectOut so, FusedIntersect fx) {
+    const StampScope stamp(kStampSelect);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *all = reinterpret_cast<uint64_t *>(smem_raw);        // cap
     __shared__ uint64_t sub[kThreads];
@@ -1562,6 +1634,7 @@ __global__ void __launch_bounds__(kThreads) topk_merge_intersect_kernel(const fl
                                                                         int64_t s, int kp1, int64_t *__restrict__ out_idx,
                                                                         float *__restrict__ out_dist, FusedIntersect fx,
                                                                         const MergePublish mp) {
+    const StampScope stamp(kStampMerge);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ int64_t s_nb[kMaxFastKp1];
     const int total = parts * kp1;
@@ -1655,6 +1728,7 @@ template <int LD>
 __global__ void __launch_bounds__(kThreads) update_pass1_kernel(float *__restrict__ pos, const float *__restrict__ fs,
                                                                 const float *__restrict__ fi, int64_t n,
                                                                 void *__restrict__ ws) {
+    const StampScope stamp(kStampColsum);
     // vectorised over whole rows: LD floats per row (2 or 4)
     using VT = typename std::conditional<LD == 2, float2, float4>::type;
     double sum[LD], sq[LD];
@@ -1746,6 +1820,7 @@ __device__ __forceinline__ void col_stats(const double *sums, int ld, int j, int
 template <int LD>
 __global__ void __launch_bounds__(kThreads) update_pass2_kernel(float *pos, const float *src, int64_t n,
                                                                 int64_t n_total, int d, const void *__restrict__ ws) {
+    const StampScope stamp(kStampNormalise);
     using VT = typename std::conditional<LD == 2, float2, float4>::type;
     const double *sums = reinterpret_cast<const double *>(ws);
     // the fp64 divide / sqrt of the column statistics once per CTA, not once per thread
@@ -1778,6 +1853,7 @@ __global__ void __launch_bounds__(kThreads) update_pass2_bcast_kernel(PeerPtrs p
                                                                       int64_t row_begin, int64_t n, int64_t n_total,
                                                                       int d, const void *__restrict__ ws,
                                                                       const double *__restrict__ rank_sums, int nslots) {
+    const StampScope stamp(kStampNormalise);
     using VT = typename std::conditional<LD == 2, float2, float4>::type;
     // rank_sums != nullptr: the column sums arrive as one (2*LD)-double slot per rank (pushed by the peers);
     // every rank adds them in rank order, so all ranks normalise with bit-identical statistics
@@ -2340,8 +2416,9 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 KnnLayout knn_layout(int64_t e, int64_t s, int kp1) {
     KnnLayout L;
-    L.g_max = 2 * num_sms();
+    L.g_max = 2 * num_sms();                              // bound-pass CTAs / chunk slots
     if (L.g_max > 1024) L.g_max = 1024;
+    const int g_scan_max = num_sms();                     // scan: one 16-warp CTA per SM
     // scan grid: every warp of a CTA is its own consumer of 192-candidate blocks, so a small problem gets only as
     // many CTAs as it has blocks for (round 1 launched 2 x SMs CTAs for 27 blocks at E = 5 K)
     const int64_t nblocks = (e + kCandBlock - 1) / kCandBlock;
@@ -2349,14 +2426,17 @@ KnnLayout knn_layout(int64_t e, int64_t s, int kp1) {
     // 500 K-candidate shard is 2605 blocks for 2368 warps: without the split the scan takes as long as its unluckiest
     // warp's two whole blocks)
     int qs = 0;
-    while (qs < 3 && (nblocks << qs) < (int64_t)4 * L.g_max * kWarps) ++qs;
+    while (qs < 3 && (nblocks << qs) < (int64_t)4 * g_scan_max * kScanWarps) ++qs;
     static_assert(((kQB / 2) >> 3) % kPairChunk == 0, "a query part is a whole number of pair chunks");
     L.qs = qs;
-    int64_t g = ((nblocks + kWarps - 1) / kWarps) << qs;      // CTAs per query part x parts
+    // Grid: ONE resident wave (2 CTAs per SM), blocks owned statically and interleaved.  Measured alternative: 4 waves of
+    // shorter CTAs (to let the hardware block scheduler even out the non-uniform slow-path cost) made the C3 scan 238 us
+    // instead of 150 us -- with ~2 blocks per warp the quantisation of a CTA's work costs more than the balancing gains.
+    int64_t g = ((nblocks + kScanWarps - 1) / kScanWarps) << qs;      // one block per warp: CTAs per query part x parts
     if (g < 1) g = 1;
-    if (g > L.g_max) g = (L.g_max >> qs) << qs;
+    if (g > g_scan_max) g = (g_scan_max >> qs) << qs;
     L.g = (int)g;
-    int cap = (L.g_max * kp1 + 255) / 256 * 256;      // every CTA publishes at most kp1 keys per query
+    int cap = (int)((L.g_max * (int64_t)kp1 + 255) / 256 * 256);  // every CTA publishes at most kp1 keys per query
     if (cap < 1024) cap = 1024;
     L.cap = cap;
     L.sb = s < kMaxBatchQ ? s : kMaxBatchQ;              // <= 4 query blocks per batch
@@ -2536,7 +2616,7 @@ int gem_init(void) {
                                   (int)scan_smem_bytes(8, kMaxFastKp1)));
     GEM_CUDA(cudaFuncSetAttribute(knn_scan_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)scan_smem_bytes(16, kMaxFastKp1)));
-    GEM_CUDA(cudaFuncSetAttribute(knn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    GEM_CUDA(cudaFuncSetAttribute(knn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelectCapMax * 8));
     const int prep_smem = kMaxBatchQ * (int)sizeof(float4);
     GEM_CUDA(cudaFuncSetAttribute(knn_prep_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, prep_smem));
     GEM_CUDA(cudaFuncSetAttribute(knn_prep_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, prep_smem));
@@ -2563,6 +2643,13 @@ int gem_abi_struct_sizes(size_t *out4) {
     out4[3] = sizeof(gem_merge_publish);
     return GEM_OK;
 }
+
+int gem_debug_stamps(unsigned long long *buffer) {
+    GEM_CUDA(cudaMemcpyToSymbol(d_stamps, &buffer, sizeof(buffer)));
+    return GEM_OK;
+}
+int gem_debug_stamp_count(void) { return kStampCount; }
+int gem_debug_stamp_words(void) { return 2 * kStampCount; }
 
 int gem_coef_slots(void) { return kCoefSlots; }
 
@@ -2620,7 +2707,7 @@ int gem_hub_degree(void) { return kHubDeg; }
 static int spring_csr_launch(const float *pos, const int64_t *row_ptr, const int32_t *col, const int64_t *up_ptr,
                              int64_t v_begin, int64_t v_end, const int32_t *hubs, int64_t n_hubs, int d, float k_attr,
                              float l_min, float *force, float *mid, int64_t mid_base, bool fuse, void *stream,
-                             const SpringPeers *peers = nullptr) {
+                             const SpringPeers *peers = nullptr, unsigned int *work = nullptr) {
     SpringPeers sp = {};
     if (peers) sp = *peers;
     if (sp.world > 0 && !fuse) return GEM_E_BADARG;
@@ -2646,7 +2733,7 @@ static int spring_csr_launch(const float *pos, const int64_t *row_ptr, const int
 #define GEM_SPRING_LAUNCH(DD, FF)                                                                                  \
     spring_csr_kernel<DD, FF><<<grid, kThreads, 0, st>>>(pos, row_ptr, col, up_ptr, v_begin, v_end, hubs, (int)n_hubs, \
                                                          -k_attr, l_min, force,                                       \
-                                                         reinterpret_cast<typename MidT<DD>::T *>(mid), mid_base, sp)
+                                                         reinterpret_cast<typename MidT<DD>::T *>(mid), mid_base, sp, work)
     if (d == 2 && !f) GEM_SPRING_LAUNCH(2, false);
     if (d == 3 && !f) GEM_SPRING_LAUNCH(3, false);
     if (d == 2 && f) GEM_SPRING_LAUNCH(2, true);
@@ -2673,8 +2760,8 @@ int gem_spring_update_csr(const float *pos, const int64_t *row_ptr, const int32_
 int gem_spring_update_csr_push(const float *pos, const int64_t *row_ptr, const int32_t *col, const int64_t *up_ptr,
                                int64_t v_begin, int64_t v_end, const int32_t *hubs, int64_t n_hubs, int d, float k_attr,
                                float l_min, float *const *peer_raw_host, int world, float *mid, int64_t mid_base,
-                               void *stream) {
-    if (!peer_raw_host || world < 1 || world > kMaxPeers) return GEM_E_BADARG;
+                               void *work, void *stream) {
+    if (!peer_raw_host || world < 1 || world > kMaxPeers || ((uintptr_t)work & 3)) return GEM_E_BADARG;
     SpringPeers sp = {};
     sp.world = world;
     for (int r = 0; r < world; ++r) {
@@ -2682,7 +2769,7 @@ int gem_spring_update_csr_push(const float *pos, const int64_t *row_ptr, const i
         sp.peers.p[r] = peer_raw_host[r];
     }
     return spring_csr_launch(pos, row_ptr, col, up_ptr, v_begin, v_end, hubs, n_hubs, d, k_attr, l_min, nullptr, mid, mid_base,
-                             true, stream, &sp);
+                             true, stream, &sp, reinterpret_cast<unsigned int *>(work));
 }
 
 int gem_sample_edges(uint64_t seed, int64_t *iter_counter, int bump_counter, int64_t e, int64_t s, int64_t *samp,
@@ -2994,8 +3081,14 @@ static bool layout_can_fuse(const gem_plan *p) {
 }
 static int layout_spring(const gem_plan *p, void *st, bool fuse) {
     if (p->row_ptr && p->col && p->up_ptr && (p->d == 2 || p->d == 3))
+    {
+        // dynamic row claims (counters inside the ticket block of the zero-initialised statistics workspace)
+        unsigned int *work = (((uintptr_t)p->stats_ws & 255) == 0)
+                                 ? reinterpret_cast<unsigned int *>(reinterpret_cast<char *>(p->stats_ws) + ws_ticket_off(row_pitch(p->d)) + 64)
+                                 : nullptr;
         return spring_csr_launch(p->pos, p->row_ptr, p->col, p->up_ptr, 0, p->n, p->hubs, p->n_hubs, p->d, p->k_attr,
-                                 p->l_min, p->force, p->mid, 0, fuse, st);
+                                 p->l_min, p->force, p->mid, 0, fuse, st, nullptr, work);
+    }
     return gem_spring_midpoints(p->pos, p->edges, p->n, p->e, p->d, p->k_attr, p->l_min, p->force, p->mid, st);
 }
 

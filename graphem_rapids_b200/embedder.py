@@ -585,6 +585,38 @@ class GraphEmbedderPyTorch:
             _cabi.check(self._lib.gem_profile_step(ctypes.byref(plan), self._stream(), ms), "gem_profile_step")
         return dict(zip(_cabi.STAGE_NAMES, [float(x) for x in ms]))
 
+    def profile_kernels(self, iterations: int = 10, scan_ctas: bool = False):
+        """Per-kernel timeline of the replayed iteration: {kernel: (begin_us, end_us)} relative to the first kernel's
+        start, median over `iterations` replays, from %globaltimer stamps written by the kernels themselves
+        (gem_debug_stamps)."""
+        lib = self._lib
+        nk, words = lib.gem_debug_stamp_count(), lib.gem_debug_stamp_words()
+        with torch.cuda.device(self.device):
+            self.run_layout_device(4)
+            buf = torch.zeros((words,), device=self.device, dtype=torch.int64)
+            reset = torch.zeros((words,), dtype=torch.int64, device=self.device)
+            reset[0:2 * nk:2] = -1                                        # begin = ~0, end = 0
+            torch.cuda.synchronize(self.device)
+            _cabi.check(lib.gem_debug_stamps(ctypes.c_void_p(buf.data_ptr())), "gem_debug_stamps")
+            rows, ctas = [], None
+            try:
+                for _ in range(int(iterations)):
+                    buf.copy_(reset)
+                    self.run_layout_device(1)
+                    torch.cuda.synchronize(self.device)
+                    raw = buf.cpu().numpy().astype(np.uint64)
+                    v = raw[: 2 * nk].reshape(nk, 2)
+                    ran = v[:, 1] > 0
+                    t0 = v[ran, 0].min()
+                    rows.append(np.where(ran[:, None], (v.astype(np.float64) - float(t0)) * 1e-3, np.nan))
+
+            finally:
+                _cabi.check(lib.gem_debug_stamps(None), "gem_debug_stamps")
+        med = np.nanmedian(np.asarray(rows), axis=0)
+        out = {name: (round(float(med[i, 0]), 1), round(float(med[i, 1]), 1)) for i, name in enumerate(_cabi.STAMP_NAMES)
+               if not np.isnan(med[i, 0])}
+        return out
+
     def fp32_peak_flops(self) -> float:
         """Measured FP32 FMA throughput of this device in flop/s (gem_fp32_peak_probe)."""
         out, out2 = ctypes.c_double(0.0), ctypes.c_double(0.0)

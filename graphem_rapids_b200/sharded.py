@@ -270,6 +270,7 @@ class CudaStages:
         self._barrier = barrier
         self._touched = torch.zeros((max(4 * S * max(kp1 - 1, 1), 1),), device=self.device, dtype=torch.int32)
         self._counters = torch.zeros((2,), device=self.device, dtype=torch.int32)
+        self._spring_work = torch.zeros((2,), device=self.device, dtype=torch.int32)
         self.p2p_ready = True
 
     @staticmethod
@@ -306,10 +307,8 @@ class CudaStages:
         a.qmid_out = eng.qmid.data_ptr()
         a.row_ptr, a.col, a.tau_hint_out = self.row_ptr.data_ptr(), self.col.data_ptr(), eng.tau_hint.data_ptr()
         # bound with the WHOLE (replicated) edge list: the same global thresholds on every rank, no exchange
-        # (half the balanced sample size: here the preparation is on the critical path -- it overlaps only the short,
-        # NVLink-bound spring kernel -- while a rank's share of the scan's slow-path events is 1/world of the total)
-        a.bound_edges, a.e_bound = self.edges32.data_ptr(), L.n_edges
-        a.bound_samples = max(8192, int(0.5 * 43.0 * (kp1 * L.n_edges) ** 0.5))
+        # (the balanced sample size: measured on 2 and 8 B200 the preparation then ends with the NVLink-bound spring kernel)
+        a.bound_edges, a.e_bound, a.bound_samples = self.edges32.data_ptr(), L.n_edges, 0
         a.coef_slot = self.coef_slot
         a.ws, a.ws_bytes = ws.data_ptr(), self._knn_ws_bytes
         _cabi.check(lib.gem_knn_prep(ctypes.byref(a), self._side_ptr()), "gem_knn_prep")
@@ -320,7 +319,7 @@ class CudaStages:
             _cabi.check(lib.gem_spring_update_csr_push(_ptr(eng.pos), _ptr(self.row_ptr), _ptr(self.col), _ptr(self.up_ptr),
                                                        eng.vb, eng.ve, hubs, n_hubs, self.d, self.k_attr, self.L_min,
                                                        self._raw_peers[par], self.world, _ptr(eng.mid), eng.e_lo,
-                                                       self._s()), "gem_spring_update_csr_push")
+                                                       _ptr(self._spring_work), self._s()), "gem_spring_update_csr_push")
         self._mark("spring")
         self._spring_done.record(main)
         # column sums of the own new rows: a read-only pass on the side stream, next to the scan
@@ -487,7 +486,7 @@ class ShardedGraphEmbedder(GraphEmbedderPyTorch):
         self._symm = None
         S, kp1 = max(eng.S, 1), eng.kp1
         e_loc = eng.e_hi - eng.e_lo
-        want = (self._world > 1 and use_symmetric_memory and kp1 <= 64
+        want = (self._world > 1 and use_symmetric_memory
                 and bool(self._lib.gem_knn_fast_path(e_loc, self.n_edges, self.n_components, S, kp1)))
         ok = torch.tensor([1 if want else 0], device=self.device)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self._group)          # every rank must take the same flow

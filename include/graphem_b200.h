@@ -93,11 +93,13 @@ int gem_spring_update_csr(const float *pos, const int64_t *row_ptr, const int32_
  * the store phase of the FIRST kernel of the iteration, not a collective behind the last one.  Rows that later
  * receive intersection forces are re-published by gem_topk_merge_intersect; after one cross-rank barrier every rank
  * normalises all rows locally (gem_update_normalise_push with world = 1).  The caller double-buffers the raw
- * buffers by iteration parity (a fast rank may start iteration t+1 while a slow one still normalises t). */
+ * buffers by iteration parity (a fast rank may start iteration t+1 while a slow one still normalises t).
+ * work (optional): 2 x uint32, zero-initialised once by the caller -- the kernel then claims its vertex ranges
+ * dynamically (it shares the SMs with the KNN preparation kernel; a static split leaves late CTAs a full share). */
 int gem_spring_update_csr_push(const float *pos, const int64_t *row_ptr, const int32_t *col, const int64_t *up_ptr,
                                int64_t v_begin, int64_t v_end, const int32_t *hubs, int64_t n_hubs, int d,
                                float k_attr, float l_min, float *const *peer_raw_host, int world, float *mid,
-                               int64_t mid_base, void *stream);
+                               int64_t mid_base, void *work, void *stream);
 
 /* Sampling of the query edges.  Replaces `torch.randperm(E, device)[:S]` / `arange(E)`
  * (_locate_knn_midpoints, :404-413) by a keyed bijection of [0,e) evaluated at 0..s-1
@@ -130,6 +132,18 @@ int gem_knn_midpoints(const float *mid, int64_t e, int64_t idx_offset, int d, co
 int gem_knn_midpoints_shard(const float *mid, int64_t e, int64_t e_total, int64_t idx_offset, int d,
                             const float *qmid, int64_t s, int kp1, int mm_mode, const float *tau_hint,
                             int64_t *out_idx, float *out_dist, void *ws, size_t ws_bytes, int coef_slot, void *stream);
+/* Diagnostics: kernel time stamps.  With a device buffer of gem_debug_stamp_words() uint64 registered (NULL: off,
+ * the default), every CTA of the iteration's kernels folds %globaltimer (ns) into [2*id] (atomicMin: first CTA start)
+ * and [2*id+1] (atomicMax: last CTA end); ids: 0 knn_prep, 1 spring_csr, 2 column sums, 3 knn_scan, 4 knn_select,
+ * 5 topk_merge_intersect, 6 normalise.  The caller resets the buffer ([2*id] = ~0, [2*id+1] = 0) before the step it
+ * wants to see.  This is how the per-kernel timeline inside a multi-rank CUDA-graph replay is measured.
+ * Synchronous (cudaMemcpyToSymbol): call outside capture. */
+int gem_debug_stamps(unsigned long long *buffer);
+int gem_debug_stamp_count(void);
+/* size of the buffer in uint64 words (2 per kernel id).  (Per-CTA stamps inside the scan kernel were tried and removed:
+ * one extra global store in its prologue made ptxas drop the uniform-register operands of the whole main loop.) */
+int gem_debug_stamp_words(void);
+
 /* Coefficient slots.  The scan reads the query coefficients (-2q) as uniform-register operands from a __constant__
  * table; the table has gem_coef_slots() independent slots per device, and every KNN entry point below takes the
  * slot it may use (`coef_slot`).  An object that issues KNN work owns one slot for its lifetime
@@ -160,7 +174,7 @@ int gem_coef_slot_release(int slot);
  *   idx_offset_bytes (int64 rows) / dist_offset_bytes (fp32 rows): the rank's partial list is published by the
  *   kernel that produces it.
  * Valid only when gem_knn_fast_path(e, e_total, d, s, kp1) returns 1 (matmul-mode cdist, d in {2,3},
- * e >= 2048, k+1 <= 64 and <= e, s <= 1024); otherwise use gem_knn_midpoints_shard. */
+ * e >= 2048, k+1 <= 56 and <= e, s <= 1024); otherwise use gem_knn_midpoints_shard. */
 int gem_knn_fast_path(int64_t e, int64_t e_total, int d, int64_t s, int kp1);
 typedef struct gem_knn_prep_args {
     int32_t d, kp1;

@@ -73,3 +73,30 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
                 assert "oracle." not in src.replace("oracle/", ""), f
+
+
+def test_scan_kernel_keeps_uniform_register_operands():
+    """The scan's packed FMAs take the query coefficients as UNIFORM-register operands (SASS: FFMA2 R, R.F32, UR.F32x2, R)
+    -- the difference between ~46 and ~60 TFLOP/s of the loop.  ptxas drops that form silently for the whole
+    main loop when the kernel's instruction stream changes in ways it dislikes (a global atomic, an extra global store
+    in the prologue, a per-warp query index ...), so the built library is checked: every FFMA2 of knn_scan_kernel
+    has a UR operand, and the bulk copies are there (UBLKCP)."""
+    import re
+    import shutil
+    import subprocess
+    from graphem_rapids_b200 import build
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", build.LIB], capture_output=True, text=True, check=True).stdout
+    seen = 0
+    for fn in sass.split("Function : ")[1:]:
+        name = fn.split("\n", 1)[0]
+        if "knn_scan_kernel" not in name:
+            continue
+        seen += 1
+        ffma2 = [ln for ln in fn.splitlines() if "FFMA2" in ln]
+        assert len(ffma2) >= 96, (name, len(ffma2))
+        assert all(re.search(r"\bUR\d+", ln) for ln in ffma2), f"{name}: FFMA2 without uniform operand"
+        assert "UBLKCP" in fn, f"{name}: no bulk-copy (TMA) instruction"
+    assert seen == 2
