@@ -584,6 +584,7 @@ def run_b200(args, w):
         except Exception as exc:  # pylint: disable=broad-exception-caught
             kernel_timeline = {"error": repr(exc)}
     exchange = emb.exchange if world > 1 else None
+    emb_multicast = bool(emb.multicast) if world > 1 else False
     if world > 1:
         emb.close()            # captured graphs hold barrier / NCCL kernels: release them before the communicator
     if rank != 0:
@@ -623,7 +624,8 @@ def run_b200(args, w):
         "iters_per_s": 1e3 / ms_per_step,
         "config": workload_config(w, n, E),
         "details": {"profile_mode": bool(args.profile_mode), "parallelism": "single GPU" if world == 1 else
-                    (f"vertex-sharded x{world} (v mod N): spring kernel pushes pos+F rows to every replica over NVLink, select "
+                    (f"vertex-sharded x{world} (v mod N): spring kernel pushes pos+F rows to every replica over NVLink "
+                     f"({'NVSwitch multicast stores, multimem.st' if emb_multicast else 'unicast peer stores'}), select "
                      f"publishes the partial lists, 2 device barriers, every rank normalises all rows; no NCCL collective"
                      if exchange == "p2p" else f"vertex-sharded x{world}, NCCL all-gather / all-reduce fallback flow"),
                     "step": "one replay of the CUDA graph of one iteration (run_layout's production path)",

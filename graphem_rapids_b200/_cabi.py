@@ -80,8 +80,8 @@ SIGNATURES = {
     "gem_spring_update_csr": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64,
                                       c_int, c_float, c_float, c_void_p, c_void_p, c_int64, c_void_p]),
     "gem_spring_update_csr_push": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64,
-                                           c_int, c_float, c_float, POINTER(c_void_p), c_int, c_void_p, c_int64, c_void_p,
-                                           c_void_p]),
+                                           c_int, c_float, c_float, POINTER(c_void_p), c_int, c_int, c_void_p, c_void_p,
+                                           c_int64, c_void_p, c_void_p]),
     "gem_debug_stamps": (c_int, [c_void_p]),
     "gem_debug_stamp_count": (c_int, []),
     "gem_debug_stamp_words": (c_int, []),

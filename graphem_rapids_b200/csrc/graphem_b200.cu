@@ -199,7 +199,6 @@ __global__ void __launch_bounds__(kThreads) spring_mid_kernel(const float *__res
 // kHubDeg (hubs of preferential-attachment graphs) are left to one CTA each (blocks >= main_blocks).
 constexpr int kGrp = 4;
 constexpr int kHubDeg = 128;
-constexpr int kSpringChunk = 512;           // vertices per dynamic work claim (8 passes of a CTA)
 
 // The pull form evaluates every edge twice, so its arithmetic matters: sqrt and 1/x come from the
 // SFU (sqrt.approx / rcp.approx, <= 1 ulp each) instead of the ~40-instruction IEEE sequences of
@@ -247,13 +246,30 @@ constexpr int kUpdBlocksMax = 1184;    // 148 * 8
 // the raw (unnormalised) position buffer -- the rank's own and, through peer-mapped pointers (NVLink P2P stores),
 // the others'.  The exchange of the updated positions therefore starts with the first finished row and runs
 // underneath the KNN scan instead of after it; every rank normalises all rows locally once the column sums are known.
-struct SpringPeers { PeerPtrs peers; int world; };
+// mc != nullptr: the NVSwitch MULTICAST mapping of the raw buffers (torch symmetric memory: multicast_ptr).  One
+// multimem.st per row leaves this GPU once and is replicated by the switch into every rank's replica, instead of
+// world-1 unicast stores (at 8 GPUs: 2 MB instead of 14 MB of NVLink egress per rank and iteration); the rank's own
+// replica is also written directly, so its own kernels never depend on the switch's loop-back.
+struct SpringPeers { PeerPtrs peers; int world; int self; float *mc; };
+__device__ __forceinline__ void multimem_store(float *base, int64_t row, Vec<3> v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                 ::"l"(reinterpret_cast<float4 *>(base) + row), "f"(v.x), "f"(v.y), "f"(v.z), "f"(0.f) : "memory");
+}
+__device__ __forceinline__ void multimem_store(float *base, int64_t row, Vec<2> v) {
+    asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};"
+                 ::"l"(reinterpret_cast<float2 *>(base) + row), "f"(v.x), "f"(v.y) : "memory");
+}
 template <int D, bool FUSE>
 __device__ __forceinline__ void spring_emit(const Vec<D> &pv, const Vec<D> &acc, float *__restrict__ out, int64_t v,
                                             int64_t v_begin, const SpringPeers &sp) {
     if (!FUSE) { acc.store(out, v - v_begin); return; }
     const Vec<D> nv = pv + acc;                                      // :799 (total force = spring part here)
     if (sp.world == 0) { nv.store(out, v - v_begin); return; }
+    if (sp.mc != nullptr) {
+        nv.store(sp.peers.p[sp.self], v);
+        multimem_store(sp.mc, v, nv);
+        return;
+    }
     for (int r = 0; r < sp.world; ++r) nv.store(sp.peers.p[r], v);
 }
 
@@ -266,7 +282,8 @@ __global__ void __launch_bounds__(kThreads) spring_csr_kernel(const float *__res
                                                               int n_hub_blocks, float neg_k_attr, float l_min,
                                                               float *__restrict__ force,
                                                               typename MidT<D>::T *__restrict__ mid, int64_t mid_base,
-                                                              const SpringPeers sp, unsigned int *__restrict__ work) {
+                                                              const SpringPeers sp, unsigned int *__restrict__ work,
+                                                              int passes_per_claim) {
     const StampScope stamp(kStampSpring);
     if ((int)blockIdx.x < n_hub_blocks) {
         // ---- one CTA per hub row; scheduled first so the long rows overlap the bulk of the work
@@ -292,6 +309,7 @@ __global__ void __launch_bounds__(kThreads) spring_csr_kernel(const float *__res
             for (int w = 0; w < kWarps; ++w)
                 for (int j = 0; j < 3; ++j) t[j] += red[w][j];
             spring_emit<D, FUSE>(pv, vec_from3<D>(t), force, v, v_begin, sp);
+            if (FUSE && sp.mc != nullptr) __threadfence_system();
         }
         return;
     }
@@ -309,14 +327,14 @@ __global__ void __launch_bounds__(kThreads) spring_csr_kernel(const float *__res
         __syncthreads();
     }
     constexpr int kPass = kThreads / kGrp;                            // vertices per CTA pass
-    const int64_t n_claims = (nv + kSpringChunk - 1) / kSpringChunk;
+    const int64_t n_claims = (nv + (int64_t)passes_per_claim * kPass - 1) / ((int64_t)passes_per_claim * kPass);
     for (;;) {
         int64_t end = nv, step = stride;
         // every lane of a warp runs the same number of outer iterations (the shuffles need all 32 lanes)
         int64_t i0 = ((int64_t)mb * kThreads + threadIdx.x) / kGrp;
         int64_t b0 = ((int64_t)mb * kThreads + (threadIdx.x & ~31)) / kGrp;
         if (work != nullptr) {
-            // claim c = the passes {c, c + n_claims, c + 2 n_claims, ...} of 64 vertices: interleaved over the whole
+            // claim c = the passes_per_claim passes {c, c + n_claims, c + 2 n_claims, ...} of 64 vertices: interleaved over the whole
             // range like the static stride (contiguous chunks put all the high-degree rows of a hub-first vertex
             // order into a few claims: measured 181 us instead of 94 us on the preferential-attachment graph)
             const int64_t c = (int64_t)s_claim;
@@ -371,6 +389,7 @@ __global__ void __launch_bounds__(kThreads) spring_csr_kernel(const float *__res
     if (work != nullptr && threadIdx.x == 0) {
         if (atomicAdd(work + 1, 1u) == gridDim.x - (unsigned)n_hub_blocks - 1u) { work[0] = 0u; work[1] = 0u; }
     }
+    if (FUSE && sp.mc != nullptr) __threadfence_system();           // multicast rows performed before the kernel retires
 }
 
 // generic n_components (d != 2,3): scalar loops, pitch d (pos/force) and d+1 (mid)
@@ -762,6 +781,7 @@ struct PrepArgs {
     float *theta, *tau, *qcoef;      // qcoef: where the coefficient pairs go (the constant-bank slot itself, or a staging copy)
     uint32_t *counts; int ncounts;
     unsigned int *ticket;
+    double *zero_doubles; int n_zero_doubles;     // the iteration's correction accumulator (cleared by the last CTA)
 };
 
 // order-reversing 32-bit key of a float (any sign): larger key = smaller value, never 0 for a non-NaN value
@@ -949,6 +969,7 @@ __global__ void __launch_bounds__(kThreads, 3) knn_prep_kernel(const PrepArgs A)
         A.qcoef[(2 * (kMaxBatchQ / 2) + q / 2) * 2 + (q & 1)] = qp.a2;
     }
     for (int i = threadIdx.x; i < A.ncounts; i += kThreads) A.counts[i] = 0;   // the scan's survivor / tile counters
+    if (A.zero_doubles != nullptr && (int)threadIdx.x < A.n_zero_doubles) A.zero_doubles[threadIdx.x] = 0.0;
     if (threadIdx.x == 0) {
         *A.ticket = 0;
         if (A.bump && A.iter_counter) *A.iter_counter = *A.iter_counter + 1;    // every CTA has read it (ticket)
@@ -1819,10 +1840,17 @@ __device__ __forceinline__ void col_stats(const double *sums, int ld, int j, int
 
 template <int LD>
 __global__ void __launch_bounds__(kThreads) update_pass2_kernel(float *pos, const float *src, int64_t n,
-                                                                int64_t n_total, int d, const void *__restrict__ ws) {
+                                                                int64_t n_total, int d, const void *__restrict__ ws,
+                                                                const double *__restrict__ corr) {
     const StampScope stamp(kStampNormalise);
     using VT = typename std::conditional<LD == 2, float2, float4>::type;
-    const double *sums = reinterpret_cast<const double *>(ws);
+    // corr (optional): exact change of (sum, sum of squares) caused by the intersection forces, accumulated separately
+    // from the column sums so that the kernel adding them does not have to wait for the column-sum pass
+    __shared__ double s_tot[2 * LD];
+    if (threadIdx.x < 2 * LD)
+        s_tot[threadIdx.x] = reinterpret_cast<const double *>(ws)[threadIdx.x] + (corr ? corr[threadIdx.x] : 0.0);
+    __syncthreads();
+    const double *sums = s_tot;
     // the fp64 divide / sqrt of the column statistics once per CTA, not once per thread
     __shared__ float s_mean[LD], s_sd[LD];
     if (threadIdx.x < LD) {
@@ -2730,10 +2758,15 @@ static int spring_csr_launch(const float *pos, const int64_t *row_ptr, const int
     }
     const int main_blocks = grid_for((v_end - v_begin) * kGrp, oc);
     const int grid = main_blocks + (int)n_hubs;
+    // dynamic claims: ~8 per CTA (a 500 K-row shard split into 8-pass claims gave each CTA one or two of them: 80 us
+    // instead of 56 us), at most 8 passes of 64 vertices each
+    int64_t ppc = ((v_end - v_begin) / (kThreads / kGrp)) / ((int64_t)8 * main_blocks);
+    if (ppc < 1) ppc = 1;
+    if (ppc > 8) ppc = 8;
 #define GEM_SPRING_LAUNCH(DD, FF)                                                                                  \
     spring_csr_kernel<DD, FF><<<grid, kThreads, 0, st>>>(pos, row_ptr, col, up_ptr, v_begin, v_end, hubs, (int)n_hubs, \
                                                          -k_attr, l_min, force,                                       \
-                                                         reinterpret_cast<typename MidT<DD>::T *>(mid), mid_base, sp, work)
+                                                         reinterpret_cast<typename MidT<DD>::T *>(mid), mid_base, sp, work, (int)ppc)
     if (d == 2 && !f) GEM_SPRING_LAUNCH(2, false);
     if (d == 3 && !f) GEM_SPRING_LAUNCH(3, false);
     if (d == 2 && f) GEM_SPRING_LAUNCH(2, true);
@@ -2759,11 +2792,15 @@ int gem_spring_update_csr(const float *pos, const int64_t *row_ptr, const int32_
 
 int gem_spring_update_csr_push(const float *pos, const int64_t *row_ptr, const int32_t *col, const int64_t *up_ptr,
                                int64_t v_begin, int64_t v_end, const int32_t *hubs, int64_t n_hubs, int d, float k_attr,
-                               float l_min, float *const *peer_raw_host, int world, float *mid, int64_t mid_base,
-                               void *work, void *stream) {
-    if (!peer_raw_host || world < 1 || world > kMaxPeers || ((uintptr_t)work & 3)) return GEM_E_BADARG;
+                               float l_min, float *const *peer_raw_host, int world, int rank, float *multicast_raw,
+                               float *mid, int64_t mid_base, void *work, void *stream) {
+    if (!peer_raw_host || world < 1 || world > kMaxPeers || rank < 0 || rank >= world || ((uintptr_t)work & 3) ||
+        ((uintptr_t)multicast_raw & 15))
+        return GEM_E_BADARG;
     SpringPeers sp = {};
     sp.world = world;
+    sp.self = rank;
+    sp.mc = multicast_raw;
     for (int r = 0; r < world; ++r) {
         if (!peer_raw_host[r]) return GEM_E_BADARG;
         sp.peers.p[r] = peer_raw_host[r];
@@ -3056,8 +3093,8 @@ int gem_update_positions(float *pos, const float *f_spring, const float *f_inter
             GEM_CHECK_LAUNCH();
         }
         if (phase != 1) {
-            if (d == 2) update_pass2_kernel<2><<<grid, kThreads, 0, st>>>(pos, pos, n, n_total, d, stats_ws);
-            else update_pass2_kernel<4><<<grid, kThreads, 0, st>>>(pos, pos, n, n_total, d, stats_ws);
+            if (d == 2) update_pass2_kernel<2><<<grid, kThreads, 0, st>>>(pos, pos, n, n_total, d, stats_ws, nullptr);
+            else update_pass2_kernel<4><<<grid, kThreads, 0, st>>>(pos, pos, n, n_total, d, stats_ws, nullptr);
             GEM_CHECK_LAUNCH();
         }
     } else {
@@ -3231,6 +3268,14 @@ int gem_layout_step(const gem_plan *p, void *stream) {
         if (have_hint) { A.row_ptr = p->row_ptr; A.col = p->col; A.hint_out = p->tau_hint; }
         A.bound_edges = ed; A.e_bound = p->e;                           // midpoints recomputed from (pos, edges): no wait for `mid`
         A.s = (int)p->s; A.kp1 = p->kp1;
+        // fused form: the intersection forces' corrections of the column sums go to their own accumulator (inside the
+        // ticket block of the statistics workspace), cleared here, so that the select kernel need not wait for the
+        // column-sum pass -- which only gets SMs once the scan's CTAs retire
+        double *corr = nullptr;
+        if (layout_can_fuse(p) && (((uintptr_t)p->stats_ws & 255) == 0)) {
+            corr = reinterpret_cast<double *>(reinterpret_cast<char *>(p->stats_ws) + ws_ticket_off(row_pitch(p->d)) + 128);
+            A.zero_doubles = corr; A.n_zero_doubles = 2 * row_pitch(p->d);
+        }
         // balanced sample size (bound_sample_size): measured on C3, 0.5x / 1x / 2x / 4x give 0.297 / 0.291 / 0.297 /
         // 0.312 ms per iteration -- the preparation shares the SMs with the spring kernel, a larger sample delays both
         static const float scale_env = [] {                       // tuning knob (bench sweeps): GEM_BOUND_SCALE
@@ -3261,9 +3306,9 @@ int gem_layout_step(const gem_plan *p, void *stream) {
             // total = spring + inter (:796): the repulsion goes straight into the spring accumulator
             fx.pos = p->pos; fx.edges = ed; fx.samp = p->samp; fx.force = p->force;
             fx.k_inter = p->k_inter; fx.d = p->d; fx.v_begin = 0; fx.v_end = (int)p->n;
-            fx.sums = fuse ? reinterpret_cast<double *>(p->stats_ws) : nullptr;
+            fx.sums = fuse ? corr : nullptr;
         }
-        cudaEvent_t before_select = (fuse && overlap) ? g_aux[dev].stats : nullptr;
+        cudaEvent_t before_select = nullptr;
         SelectOut so = {};
         so.idx = p->knn_idx; so.dist = p->knn_dist;
         rc = p->d == 2 ? knn_scan_select<2>(L, w, p->mid, p->e, p->qmid, (int)p->s, p->kp1, so, fx, p->coef_slot, main_st, before_select)
@@ -3272,8 +3317,9 @@ int gem_layout_step(const gem_plan *p, void *stream) {
         stage_mark();                                                   // GEM_STAGE_INTERSECT (fused into the select kernel)
         if (fuse) {                                                     // normalise p->force (new positions) into p->pos
             const int grid = grid_for(p->n, 8);
-            if (p->d == 2) update_pass2_kernel<2><<<grid, kThreads, 0, main_st>>>(p->pos, p->force, p->n, p->n, p->d, p->stats_ws);
-            else update_pass2_kernel<4><<<grid, kThreads, 0, main_st>>>(p->pos, p->force, p->n, p->n, p->d, p->stats_ws);
+            if (overlap) GEM_CUDA(cudaStreamWaitEvent(main_st, g_aux[dev].stats, 0));       // the column sums
+            if (p->d == 2) update_pass2_kernel<2><<<grid, kThreads, 0, main_st>>>(p->pos, p->force, p->n, p->n, p->d, p->stats_ws, corr);
+            else update_pass2_kernel<4><<<grid, kThreads, 0, main_st>>>(p->pos, p->force, p->n, p->n, p->d, p->stats_ws, corr);
             GEM_CHECK_LAUNCH();
             rc = GEM_OK;
         } else {

@@ -39,6 +39,29 @@ def _ptr(t: Optional[torch.Tensor]):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
 
+class _nvtx_range:
+    """NVTX range around the host-side phases (construction, graph build, initial embedding, run_layout, captures) when
+    GEM_NVTX=1 -- the reference has no tracing hooks at all; the kernels themselves show up by
+    name in Nsight Systems / Compute."""
+    _on = None
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _nvtx_range._on is None:
+            import os
+            _nvtx_range._on = os.environ.get("GEM_NVTX", "0") == "1"
+        if _nvtx_range._on:
+            torch.cuda.nvtx.range_push(self.name)
+        return self
+
+    def __exit__(self, *exc):
+        if _nvtx_range._on:
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
 def _acquire_coef_slot(lib, device_index: int) -> int:
     slot = ctypes.c_int(-1)
     with torch.cuda.device(device_index):
@@ -142,7 +165,8 @@ class GraphEmbedderPyTorch:
         # symmetric CSR + per-vertex upper-edge offsets for the pull kernels.  Built by the library on the
         # device when the adjacency allows it, else by partition.py on the host.
         self._world, self._rank = self._world_and_rank()
-        built = self._graph_arrays_device(adjacency)
+        with _nvtx_range("gem.graph_build"):
+            built = self._graph_arrays_device(adjacency)
         if built is not None:
             self._layout, self.edges, self._edges32, self._row_ptr, self._col, self._up_ptr, self._hubs = built
             self.n_edges = int(self._edges32.shape[0])
@@ -184,7 +208,8 @@ class GraphEmbedderPyTorch:
         if initial_positions is not None:
             self.positions = initial_positions
         else:
-            self._positions = self._compute_laplacian_embedding()
+            with _nvtx_range("gem.initial_embedding"):
+                self._positions = self._compute_laplacian_embedding()
 
     # ------------------------------------------------------------------ input handling
     def _validate_adjacency(self, adjacency):
@@ -657,7 +682,7 @@ class GraphEmbedderPyTorch:
             pos0 = self._pos.clone()
             next0 = b["samp_next"].clone()
             torch.cuda.synchronize(self.device)
-            with torch.cuda.graph(graph):
+            with _nvtx_range("gem.capture_iteration"), torch.cuda.graph(graph):
                 if torch_samp:
                     cur = torch.cuda.current_stream(self.device)
                     b["samp"].copy_(b["samp_next"])
@@ -686,7 +711,7 @@ class GraphEmbedderPyTorch:
             self.logger.info("Running layout for %d iterations", num_iterations)
         if self.n_edges == 0 and num_iterations > 0:
             raise RuntimeError("selected index k out of range")
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), _nvtx_range(f"gem.run_layout[{int(num_iterations)}]"):
             if self.n_neighbors + 1 > self.n_edges and num_iterations > 0:
                 raise RuntimeError("selected index k out of range")
             if num_iterations > 1 and self._graph_ok():

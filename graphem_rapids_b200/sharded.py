@@ -250,7 +250,7 @@ class CudaStages:
     peer_ptrs = None            # kept for introspection: device pointers of every rank's position buffer
 
     def attach_p2p(self, pos_ptrs, raw_ptrs, xchg_ptrs, raw_local: torch.Tensor, xchg_local: torch.Tensor,
-                   list_bytes: int, S: int, kp1: int, barrier):
+                   list_bytes: int, S: int, kp1: int, barrier, raw_multicast_ptr: int = 0):
         """pos_ptrs / raw_ptrs / xchg_ptrs: base device pointers of EVERY rank's position buffer (n_pad, ld), raw buffer
         (2, n_pad, ld) and exchange area (2 x [world x list_bytes | world x 2*ld doubles]) as seen from this process
         (torch.distributed._symmetric_memory buffer_ptrs, or plain pointers of sibling engines on one GPU);
@@ -266,6 +266,8 @@ class CudaStages:
         self._parity_bytes = (world * self._list_bytes + self._stats_bytes + 255) // 256 * 256
         raw_stride = self.L.n_pad * self.ld * 4
         self._raw_peers = [(ctypes.c_void_p * world)(*[int(p) + par * raw_stride for p in raw_ptrs]) for par in (0, 1)]
+        # NVSwitch multicast mapping of the raw buffers (0: none -> world-1 unicast stores per row)
+        self._raw_mc = [int(raw_multicast_ptr) + par * raw_stride for par in (0, 1)] if raw_multicast_ptr else None
         self._xchg_peers = (ctypes.c_void_p * world)(*[int(p) for p in xchg_ptrs])
         self._barrier = barrier
         self._touched = torch.zeros((max(4 * S * max(kp1 - 1, 1), 1),), device=self.device, dtype=torch.int32)
@@ -318,8 +320,10 @@ class CudaStages:
         if eng.ve > eng.vb:
             _cabi.check(lib.gem_spring_update_csr_push(_ptr(eng.pos), _ptr(self.row_ptr), _ptr(self.col), _ptr(self.up_ptr),
                                                        eng.vb, eng.ve, hubs, n_hubs, self.d, self.k_attr, self.L_min,
-                                                       self._raw_peers[par], self.world, _ptr(eng.mid), eng.e_lo,
-                                                       _ptr(self._spring_work), self._s()), "gem_spring_update_csr_push")
+                                                       self._raw_peers[par], self.world, self.rank,
+                                                       ctypes.c_void_p(self._raw_mc[par]) if self._raw_mc else None,
+                                                       _ptr(eng.mid), eng.e_lo, _ptr(self._spring_work), self._s()),
+                        "gem_spring_update_csr_push")
         self._mark("spring")
         self._spring_done.record(main)
         # column sums of the own new rows: a read-only pass on the side stream, next to the scan
@@ -460,7 +464,7 @@ class ShardedGraphEmbedder(GraphEmbedderPyTorch):
     (identically seeded) default generator -- the ids are then compared across ranks in debug runs only."""
 
     def __init__(self, adjacency, n_components=2, *args, process_group=None, use_symmetric_memory=True,
-                 ownership="strided", **kwargs):
+                 use_multicast=False, ownership="strided", **kwargs):
         if not dist.is_initialized():
             raise RuntimeError("ShardedGraphEmbedder needs an initialised torch.distributed process group")
         self._group = process_group
@@ -506,8 +510,17 @@ class ShardedGraphEmbedder(GraphEmbedderPyTorch):
                 self._symm = dict(pos=h_pos, raw=h_raw, xchg=h_x, raw_t=raw, xchg_t=xchg)
                 self._pos = pos_buf
                 eng.pos = pos_buf
+                import os
+                mc = 0
+                # EXPERIMENTAL, off by default (GEM_MULTICAST=1 or use_multicast=True): the rows of the spring kernel go out
+                # as NVSwitch multicast stores (multimem.st.relaxed.sys + fence.sys).  Measured on 2 B200: same iteration
+                # time, but in the 2-rank test ONE replica ended with rows that differ -- the unicast re-publication of a
+                # row that received intersection forces (merge kernel) can overtake the multicast copy of the same row on
+                # another route.  A correct protocol keeps both on one route (or tags rows with the iteration number).
+                if use_multicast or os.environ.get("GEM_MULTICAST", "0") == "1":
+                    mc = int(getattr(h_raw, "multicast_ptr", 0) or 0)
                 stages.attach_p2p(h_pos.buffer_ptrs, h_raw.buffer_ptrs, h_x.buffer_ptrs, raw, xchg, eng._nb, S, kp1,
-                                  barrier=lambda ch: h_x.barrier(channel=int(ch)))
+                                  barrier=lambda ch: h_x.barrier(channel=int(ch)), raw_multicast_ptr=mc)
             except Exception as exc:  # pylint: disable=broad-exception-caught
                 # never silent: the fallback is another design (NCCL collectives) with other performance
                 self.logger.warning("symmetric memory unavailable (%s): falling back to the NCCL all-gather flow", exc)
@@ -536,6 +549,11 @@ class ShardedGraphEmbedder(GraphEmbedderPyTorch):
     def exchange(self) -> str:
         """Which flow the iteration runs ('p2p': peer stores over symmetric memory + 2 barriers; 'nccl')."""
         return "p2p" if self._engine.st.p2p_ready else "nccl"
+
+    @property
+    def multicast(self) -> bool:
+        """Are the position rows pushed with NVSwitch multicast stores (multimem.st)?"""
+        return bool(self._engine.st.p2p_ready and self._engine.st._raw_mc)
 
     def _world_and_rank(self):
         return dist.get_world_size(self._group), dist.get_rank(self._group)

@@ -94,12 +94,15 @@ int gem_spring_update_csr(const float *pos, const int64_t *row_ptr, const int32_
  * receive intersection forces are re-published by gem_topk_merge_intersect; after one cross-rank barrier every rank
  * normalises all rows locally (gem_update_normalise_push with world = 1).  The caller double-buffers the raw
  * buffers by iteration parity (a fast rank may start iteration t+1 while a slow one still normalises t).
+ * multicast_raw (optional): the NVSwitch multicast mapping of the same raw buffers (symmetric-memory multicast_ptr):
+ * one multimem.st per row is replicated by the switch into every replica (the rank's own, peer_raw_host[rank], is
+ * also written directly) instead of world-1 unicast stores.
  * work (optional): 2 x uint32, zero-initialised once by the caller -- the kernel then claims its vertex ranges
  * dynamically (it shares the SMs with the KNN preparation kernel; a static split leaves late CTAs a full share). */
 int gem_spring_update_csr_push(const float *pos, const int64_t *row_ptr, const int32_t *col, const int64_t *up_ptr,
                                int64_t v_begin, int64_t v_end, const int32_t *hubs, int64_t n_hubs, int d,
-                               float k_attr, float l_min, float *const *peer_raw_host, int world, float *mid,
-                               int64_t mid_base, void *work, void *stream);
+                               float k_attr, float l_min, float *const *peer_raw_host, int world, int rank,
+                               float *multicast_raw, float *mid, int64_t mid_base, void *work, void *stream);
 
 /* Sampling of the query edges.  Replaces `torch.randperm(E, device)[:S]` / `arange(E)`
  * (_locate_knn_midpoints, :404-413) by a keyed bijection of [0,e) evaluated at 0..s-1

@@ -208,10 +208,31 @@ def _nccl_worker(rank, world, port, out):
             flags[f"replay_pos_{it}"] = rel_inf(emb.positions, o["new_pos"].numpy())
             ok &= flags[f"replay_knn_{it}"]
             worst = max(worst, flags[f"replay_pos_{it}"])
+        torch.cuda.synchronize()
         mine = emb._pos.clone()
         dist.broadcast(mine, src=0)
         same = bool(torch.equal(mine, emb._pos))
         flags["replicas_identical"] = same
+        if emb.exchange == "p2p":
+            # locate a mismatch: the raw (unnormalised) replicas of both parities and the statistics slots
+            st = emb._engine.st
+            for par in (0, 1):
+                r0 = st._raw_local[par].clone()
+                dist.broadcast(r0, src=0)
+                bad = (r0 != st._raw_local[par]).any(dim=1).nonzero().reshape(-1)
+                flags[f"raw{par}_rows_differ"] = int(bad.numel())
+                if bad.numel():
+                    owners = torch.unique(bad // emb._layout.slice).tolist()
+                    flags[f"raw{par}_owner_ranks"] = owners
+                    flags[f"raw{par}_maxdiff"] = float((r0 - st._raw_local[par]).abs().max())
+                _, _, stats = st._parity_views(emb._engine, par)
+                s0 = stats.clone()
+                dist.broadcast(s0, src=0)
+                flags[f"stats{par}_equal"] = bool(torch.equal(s0, stats))
+            if not same:
+                bad = (mine != emb._pos).any(dim=1).nonzero().reshape(-1)
+                flags["pos_rows_differ"] = int(bad.numel())
+                flags["pos_maxdiff"] = float((mine - emb._pos).abs().max())
         # host I/O split across the ranks: every rank uploads its chunk, all replicas end up with the whole array
         lo, hi = emb.chunk_rows()
         full = np.random.default_rng(5).standard_normal((n, d)).astype(np.float32)
