@@ -782,6 +782,7 @@ struct PrepArgs {
     uint32_t *counts; int ncounts;
     unsigned int *ticket;
     double *zero_doubles; int n_zero_doubles;     // the iteration's correction accumulator (cleared by the last CTA)
+    int coef_q0;                                  // first query slot of this batch inside the coefficient bank (0 or 512)
 };
 
 // order-reversing 32-bit key of a float (any sign): larger key = smaller value, never 0 for a non-NaN value
@@ -964,9 +965,10 @@ __global__ void __launch_bounds__(kThreads, 3) knn_prep_kernel(const PrepArgs A)
         A.theta[q] = filter_threshold(ta, qp.qn);
         A.tau[q] = ta;
         // staging copy of the constant-bank table: pair m = q/2, component q&1
-        A.qcoef[(0 * (kMaxBatchQ / 2) + q / 2) * 2 + (q & 1)] = qp.a0;
-        A.qcoef[(1 * (kMaxBatchQ / 2) + q / 2) * 2 + (q & 1)] = qp.a1;
-        A.qcoef[(2 * (kMaxBatchQ / 2) + q / 2) * 2 + (q & 1)] = qp.a2;
+        const int qc = q + A.coef_q0;
+        A.qcoef[(0 * (kMaxBatchQ / 2) + qc / 2) * 2 + (qc & 1)] = qp.a0;
+        A.qcoef[(1 * (kMaxBatchQ / 2) + qc / 2) * 2 + (qc & 1)] = qp.a1;
+        A.qcoef[(2 * (kMaxBatchQ / 2) + qc / 2) * 2 + (qc & 1)] = qp.a2;
     }
     for (int i = threadIdx.x; i < A.ncounts; i += kThreads) A.counts[i] = 0;   // the scan's survivor / tile counters
     if (A.zero_doubles != nullptr && (int)threadIdx.x < A.n_zero_doubles) A.zero_doubles[threadIdx.x] = 0.0;
@@ -1160,7 +1162,9 @@ __global__ void __launch_bounds__(kScanThreads, 1) knn_scan_kernel(const typenam
                                                                    uint32_t *__restrict__ tile_counter,
                                                                    unsigned long long *__restrict__ stats, int qb0, int slot,
                                                                    int qs) {
-    const int qb = qb0 + (int)blockIdx.y;
+    const int qb = qb0 + (int)blockIdx.y;                 // query block: of the coefficient bank AND of the per-query arrays
+                                                          // (a batch in the upper half of the bank passes shifted array
+                                                          // pointers; a second, blockIdx.y-only index costs the UR operands)
     const StampScope stamp(kStampScan);
     // query block = blockIdx.y (+ qb0): a batch of up to 1024 queries is ONE launch of (g, blocks) CTAs.  Block indices and
     // kernel parameters are uniform by construction, which the constant-bank coefficient addressing below depends on
@@ -1275,7 +1279,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) knn_scan_kernel(const typenam
             static_assert(scan_smem_bytes(16, kMaxFastKp1) + 1024 <= 227 * 1024, "scan CTA exceeds the shared memory of an SM");
             for (int mcr = 0; mcr < mc_n; mcr += kPairChunk) {
                 const int mc = mc_lo + mcr;
-                bool any = false;
+                unsigned int any = 0u;
 #pragma unroll
                 for (int u = 0; u < kPairChunk; ++u) {                // per pair of queries: 3*kC FFMA2, min, 2 compares
                     const int m = qb * (kQB / 2) + mc + u;               // direct constant-bank indexing -> LDCU
@@ -1296,8 +1300,12 @@ __global__ void __launch_bounds__(kScanThreads, 1) knn_scan_kernel(const typenam
                     const float mh = fminf(min3f(hi[0], hi[1], hi[2]), min3f(hi[3], hi[4], hi[5]));
                     float tx, ty;
                     unpack2f(th2[mc + u], tx, ty);                    // one LDS.64; thresholds tighten while we run
-                    any |= (ml <= tx);
-                    any |= (mh <= ty);
+                    // compare results as all-ones / zero words OR-ed by one 3-input LOP3 per pair (a bool accumulator
+                    // compiled into a chain of 15 dependent SELs per chunk)
+                    unsigned int c_lo, c_hi;
+                    asm("set.le.u32.f32 %0, %1, %2;" : "=r"(c_lo) : "f"(ml), "f"(tx));
+                    asm("set.le.u32.f32 %0, %1, %2;" : "=r"(c_hi) : "f"(mh), "f"(ty));
+                    any |= c_lo | c_hi;
                 }
                 if (any) hitmask |= 1u << (mc / kPairChunk);
             }
@@ -2431,6 +2439,15 @@ inline int grid_for(int64_t work, int per_sm) {
 // ---- KNN fast path plumbing -------------------------------------------------------------------
 constexpr int kMaxDevices = 64;
 float *g_coef_bank[kMaxDevices];       // device address of c_qcoef per device (gem_init)
+// second stream + fork/join events of gem_layout_step and of the batched KNN pipeline, per device (created by gem_init)
+struct AuxStream {
+    cudaStream_t st = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr, spring = nullptr, stats = nullptr;
+    cudaEvent_t pipe_prep[2] = {nullptr, nullptr}, pipe_sel[2] = {nullptr, nullptr};
+};
+AuxStream g_aux[kMaxDevices];
+// the library-owned side stream and its events are shared by every caller on a device: one enqueue at a time per process
+std::mutex g_step_mutex;
 
 struct KnnLayout {
     int g;                  // scan CTAs over the candidate axis
@@ -2454,7 +2471,8 @@ KnnLayout knn_layout(int64_t e, int64_t s, int kp1) {
     // 500 K-candidate shard is 2605 blocks for 2368 warps: without the split the scan takes as long as its unluckiest
     // warp's two whole blocks)
     int qs = 0;
-    while (qs < 3 && (nblocks << qs) < (int64_t)4 * g_scan_max * kScanWarps) ++qs;
+    const int64_t nqb = s >= kMaxBatchQ ? kMaxBatchQ / (2 * kQB) : (s + kQB - 1) / kQB;    // query blocks of one launch (>= 2 when batched)
+    while (qs < 3 && ((nblocks * nqb) << qs) < (int64_t)4 * g_scan_max * kScanWarps) ++qs;
     static_assert(((kQB / 2) >> 3) % kPairChunk == 0, "a query part is a whole number of pair chunks");
     L.qs = qs;
     // Grid: ONE resident wave (2 CTAs per SM), blocks owned statically and interleaved.  Measured alternative: 4 waves of
@@ -2553,7 +2571,7 @@ int knn_prepare(const KnnLayout &L, char *w, PrepArgs A, int64_t bound_samples, 
 template <int D>
 int knn_scan_select(const KnnLayout &L, char *w, const float *mid, int64_t e, const float *qm, int sb, int kp1,
                     const SelectOut &so, const FusedIntersect &fx, int slot, cudaStream_t st,
-                    cudaEvent_t before_select = nullptr) {
+                    cudaEvent_t before_select = nullptr, int qb0 = 0) {
     using CandT = typename MidT<D>::T;
     if (slot < 0 || slot >= kCoefSlots) return GEM_E_BADARG;
     float *theta = reinterpret_cast<float *>(w + L.off_theta);
@@ -2564,9 +2582,13 @@ int knn_scan_select(const KnnLayout &L, char *w, const float *mid, int64_t e, co
     const size_t sel_smem = (size_t)L.cap * sizeof(uint64_t);
     {
         const dim3 grid((unsigned)L.g, (unsigned)((sb + kQB - 1) / kQB));       // S = 256: (g, 1)
+        // qb0 != 0 (upper half of the coefficient slot): the kernel indexes bank AND arrays by qb0 + blockIdx.y, so the
+        // per-query arrays are passed shifted back by qb0 * kQB queries (never dereferenced below their start)
+        const int64_t sh = (int64_t)qb0 * kQB;
         knn_scan_kernel<D><<<grid, kScanThreads, scan_smem, st>>>(
-            reinterpret_cast<const CandT *>(mid), e, qm, sb, kp1, theta, tau, counts, keys, L.cap, counts + L.sb,
-            g_knn_stats ? reinterpret_cast<unsigned long long *>(w + L.off_stats) : nullptr, 0, slot, L.qs);
+            reinterpret_cast<const CandT *>(mid), e, qm - sh * mid_pitch(D), sb + (int)sh, kp1, theta - sh, tau - sh, counts - sh,
+            keys - sh * L.cap, L.cap, counts + L.sb,
+            g_knn_stats ? reinterpret_cast<unsigned long long *>(w + L.off_stats) : nullptr, qb0, slot, L.qs);
         GEM_CHECK_LAUNCH();
     }
     stage_mark();                                                   // GEM_STAGE_KNN_SCAN
@@ -2582,37 +2604,71 @@ bool knn_fast_applicable(int mm, int d, int64_t e, int kp1) {
     return mm && (d == 2 || d == 3) && e >= 2048 && kp1 <= kMaxFastKp1 && kp1 <= e && e < ((int64_t)1 << 32);
 }
 
+// Batched KNN (more queries than one preparation handles: the full-KNN regime sample_size = E).
+// Serial form: batches of 1024 queries, each preparation -> scan -> select on `st`.
+// Pipelined form (workspace of 2 layouts given, library side stream available, not under the stage timer): batches
+// of 512 queries alternate between the two halves of the coefficient slot and the two workspaces; the preparation of
+// batch b runs on the side stream next to the scan of batch b-1 and may start once the select of batch b-2 has
+// released its half -- the scan, the only FP32-bound part, runs back to back on `st`.
 template <int D>
 int knn_fast(const float *mid, int64_t e, int64_t idx_offset, const float *qmid, int64_t s, int kp1,
              const float *tau_hint, int64_t *out_idx, float *out_dist, void *ws, size_t ws_bytes, int slot,
              cudaStream_t st) {
-    const KnnLayout L = knn_layout(e, s, kp1);
+    KnnLayout L = knn_layout(e, s, kp1);
     if (ws == nullptr || ws_bytes < L.total || ((uintptr_t)ws & 255)) return GEM_E_WORKSPACE;
     if (((uintptr_t)mid & 15) || ((uintptr_t)qmid & 15)) return GEM_E_BADARG;
     char *w = reinterpret_cast<char *>(ws);
     const int mld = mid_pitch(D);
     FusedIntersect none = {};
-    for (int64_t q0 = 0; q0 < s; q0 += L.sb) {
-        const int sb = (int)((s - q0) < L.sb ? (s - q0) : L.sb);
+    int dev = 0;
+    GEM_CUDA(cudaGetDevice(&dev));
+    const bool pipelined = s > kMaxBatchQ && ws_bytes >= 2 * L.total && g_timer == nullptr && dev >= 0 && dev < kMaxDevices &&
+                           g_aux[dev].st != nullptr && g_aux[dev].st != st;
+    if (!pipelined) {
+        for (int64_t q0 = 0; q0 < s; q0 += L.sb) {
+            const int sb = (int)((s - q0) < L.sb ? (s - q0) : L.sb);
+            const float *qm = qmid + q0 * mld;
+            PrepArgs A = {};
+            A.qmid_in = qm; A.hint_in = tau_hint ? tau_hint + q0 : nullptr;
+            A.bound_mid = mid; A.e_bound = e; A.s = sb; A.kp1 = kp1;
+            int rc = knn_prepare<D>(L, w, A, 0, slot, st);
+            if (rc) return rc;
+            SelectOut so = {};
+            so.idx = out_idx + q0 * kp1; so.dist = out_dist + q0 * kp1; so.idx_offset = idx_offset;
+            rc = knn_scan_select<D>(L, w, mid, e, qm, sb, kp1, so, none, slot, st);
+            if (rc) return rc;
+        }
+        return GEM_OK;
+    }
+    std::lock_guard<std::mutex> lock(g_step_mutex);
+    AuxStream &ax = g_aux[dev];
+    const int64_t bsz = kMaxBatchQ / 2;
+    GEM_CUDA(cudaEventRecord(ax.fork, st));                       // the side stream starts behind the caller's prior work
+    GEM_CUDA(cudaStreamWaitEvent(ax.st, ax.fork, 0));
+    int64_t b = 0;
+    for (int64_t q0 = 0; q0 < s; q0 += bsz, ++b) {
+        const int h = (int)(b & 1);
+        const int sb = (int)((s - q0) < bsz ? (s - q0) : bsz);
         const float *qm = qmid + q0 * mld;
+        char *wh = w + (size_t)h * L.total;
+        if (b >= 2) GEM_CUDA(cudaStreamWaitEvent(ax.st, ax.pipe_sel[h], 0));      // half h released by batch b-2
         PrepArgs A = {};
         A.qmid_in = qm; A.hint_in = tau_hint ? tau_hint + q0 : nullptr;
         A.bound_mid = mid; A.e_bound = e; A.s = sb; A.kp1 = kp1;
-        int rc = knn_prepare<D>(L, w, A, 0, slot, st);
+        A.coef_q0 = h * (int)bsz;
+        int rc = knn_prepare<D>(L, wh, A, 0, slot, ax.st);
         if (rc) return rc;
+        GEM_CUDA(cudaEventRecord(ax.pipe_prep[h], ax.st));
+        GEM_CUDA(cudaStreamWaitEvent(st, ax.pipe_prep[h], 0));
         SelectOut so = {};
         so.idx = out_idx + q0 * kp1; so.dist = out_dist + q0 * kp1; so.idx_offset = idx_offset;
-        rc = knn_scan_select<D>(L, w, mid, e, qm, sb, kp1, so, none, slot, st);
+        rc = knn_scan_select<D>(L, wh, mid, e, qm, sb, kp1, so, none, slot, st, nullptr, h * (int)(bsz / kQB));
         if (rc) return rc;
+        GEM_CUDA(cudaEventRecord(ax.pipe_sel[h], st));
     }
     return GEM_OK;
 }
 
-// second stream + fork/join events of gem_layout_step, per device (created by gem_init)
-struct AuxStream { cudaStream_t st = nullptr; cudaEvent_t fork = nullptr, join = nullptr, spring = nullptr, stats = nullptr; };
-AuxStream g_aux[kMaxDevices];
-// gem_layout_step enqueues on two streams with library-owned events: one enqueue at a time per process
-std::mutex g_step_mutex;
 // owners of the constant-bank coefficient slots, per device (gem_coef_slot_acquire / _release)
 bool g_slot_used[kMaxDevices][kCoefSlots];
 std::mutex g_slot_mutex;
@@ -2661,6 +2717,10 @@ int gem_init(void) {
         GEM_CUDA(cudaEventCreateWithFlags(&g_aux[dev].join, cudaEventDisableTiming));
         GEM_CUDA(cudaEventCreateWithFlags(&g_aux[dev].spring, cudaEventDisableTiming));
         GEM_CUDA(cudaEventCreateWithFlags(&g_aux[dev].stats, cudaEventDisableTiming));
+        for (int i = 0; i < 2; ++i) {
+            GEM_CUDA(cudaEventCreateWithFlags(&g_aux[dev].pipe_prep[i], cudaEventDisableTiming));
+            GEM_CUDA(cudaEventCreateWithFlags(&g_aux[dev].pipe_sel[i], cudaEventDisableTiming));
+        }
     }
     return GEM_OK;
 }
@@ -2832,7 +2892,8 @@ int gem_query_midpoints(const float *pos, const int32_t *edges, const int64_t *s
 
 int gem_knn_workspace_bytes(int64_t e, int d, int64_t s, int kp1, size_t *bytes) {
     if (!bytes || e <= 0 || s <= 0 || kp1 <= 0 || d <= 0) return GEM_E_BADARG;
-    *bytes = knn_layout(e, s, kp1).total;
+    const KnnLayout L = knn_layout(e, s, kp1);
+    *bytes = s > kMaxBatchQ ? 2 * L.total : L.total;      // batched problems: two workspaces (pipelined preparation / scan)
     return GEM_OK;
 }
 
