@@ -80,6 +80,27 @@ struct StampScope {                      // begin at construction, end at every 
     __device__ __forceinline__ ~StampScope() { stamp_end(id); }
 };
 
+#ifdef GEM_SCAN_DIAG
+// diagnostic build only (scripts/scan_diag.py): per-CTA %globaltimer points of the scan kernel, thread 0
+__device__ unsigned long long *d_scan_diag = nullptr;
+#define GEM_DIAG_DECL unsigned long long dg[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}
+#define GEM_DIAG_T(i) do { if (threadIdx.x == 0) dg[i] = globaltimer_ns(); } while (0)
+#define GEM_DIAG_FLUSH() do { if (threadIdx.x == 0 && d_scan_diag != nullptr) { \
+        unsigned long long *o = d_scan_diag + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 12; \
+        for (int i_ = 0; i_ < 12; ++i_) o[i_] = dg[i_]; } } while (0)
+__device__ unsigned long long *d_prep_diag = nullptr;
+__device__ unsigned long long *d_sel_diag = nullptr;     // per select CTA: t0, after staging, after shrinking, after ranking, end, n0, n
+__device__ unsigned long long *d_q_diag = nullptr;       // per query: [0] re-checks passed, [1] accepted, [2] tau bits, [3] theta bits, [4] qn bits
+#define GEM_PDIAG_FLUSH() do { if (threadIdx.x == 0 && d_prep_diag != nullptr) { \
+        unsigned long long *o = d_prep_diag + (size_t)blockIdx.x * 12; \
+        for (int i_ = 0; i_ < 12; ++i_) o[i_] = dg[i_]; } } while (0)
+#else
+#define GEM_DIAG_DECL
+#define GEM_DIAG_T(i)
+#define GEM_DIAG_FLUSH()
+#define GEM_PDIAG_FLUSH()
+#endif
+
 // optional per-stage CUDA events (gem_profile_step); nullptr on the product path
 struct StageTimer {
     cudaEvent_t ev[GEM_NUM_STAGES + 1];
@@ -631,7 +652,6 @@ constexpr int kTile = kScanWarps * kWStages * kCandBlock;   // scan: candidates 
 constexpr int kPairChunk = 8;               // scan: query pairs between two slow-path checks
 constexpr int kMaxBatchQ = 1024;            // queries per scan batch (= constant-bank coefficient capacity)
 constexpr float kSlack = 3.814697265625e-06f;   // 2^-18, see DESIGN.md (filter error budget)
-constexpr int kSurvMax = 1024;
 constexpr int kSelectCapMax = 24576;        // keys per query the select kernel can stage (192 KB of shared memory)
 constexpr int kMaxFastKp1 = 56;           // the 16-warp scan CTA: staging (96 KB) + 256 lists of k+1 keys must fit 227 KB
 
@@ -661,17 +681,16 @@ __device__ __forceinline__ unsigned long long fma2f(unsigned long long a, unsign
     return d;
 }
 
-// conservative filter threshold for "distance <= ta": with U = largest fp32 whose sqrt_rn is <= ta,
+// conservative filter threshold for "distance <= ta": with U >= every fp32 v whose sqrt_rn(v) is <= ta,
 //   fma(a0,y0,fma(a1,y1,fma(a2,y2,yn*(1-c)))) <= U - qn + c*qn      (right side rounded up)
 // holds for every candidate whose exact chain distance is <= ta (error budget: DESIGN.md).
+// U in closed form: sqrt_rn(v) <= ta  =>  sqrt(v) <= ta + ulp(ta)/2 <= ta (1 + 2^-24)  =>  v <= ta^2 (1 + 2^-24)^2 <
+// ta^2 (1 + 2^-22) <= RU(RU(ta*ta) * (1 + 2^-22)).  (The first version searched the exact largest such v with up to 16
+// software square roots; the scan calls this under a per-query lock on every replacement in a full list, where it
+// was most of the ~1.5 us a locked insertion cost.  The filter's own slack is 2^-18, sixteen times wider.)
 __device__ __forceinline__ float filter_threshold(float ta, float qn) {
     if (!(ta < kInf)) return kInf;
-    float u = __fmul_rn(ta, ta);
-    for (int it = 0; it < 8 && __fsqrt_rn(u) > ta; ++it) u = __uint_as_float(__float_as_uint(u) - 1);
-    for (int it = 0; it < 8; ++it) {
-        const float un = __uint_as_float(__float_as_uint(u) + 1);
-        if (__fsqrt_rn(un) <= ta) u = un; else break;
-    }
+    const float u = __fmul_ru(__fmul_ru(ta, ta), 1.0f + 2.384185791015625e-07f);
     float th = __fadd_ru(__fsub_ru(u, qn), __fmul_ru(kSlack, qn));
     return __fadd_ru(th, 1e-37f);
 }
@@ -754,9 +773,9 @@ __global__ void __launch_bounds__(kThreads) knn_linegraph_hint_kernel(const floa
 // ---- fused preparation of one query batch: ONE launch ---------------------------------------------
 // Everything the scan needs before it can start depends on the positions only:
 //   (0) the sample (keyed bijection, or ids given by the caller) and the query midpoints,
-//   (1) a stratified bound pass: CTA b < g evaluates the exact cdist chain of ALL queries against `per`
-//       consecutive candidates from the start of ITS share [b*e/g, (b+1)*e/g) of the candidate range and
-//       records the per-query minimum -> chunkmin[b][q],
+//   (1) a stratified bound pass: CTA b < g evaluates a 3-FMA upper bound of the cdist chain of ALL queries against
+//       `per` candidates EVENLY SPACED over ITS share [b*e/g, (b+1)*e/g) of the candidate range and records the
+//       per-query minimum,
 //   (2) the line-graph bound (CTAs >= g, one warp per query; lg_hint() above),
 //   (3) thresholds: the CTAs fold their minima into `chunks` ~ 4(k+1) slots per query (atomicMax on an
 //       order-reversing key), and the LAST CTA to finish (ticket) takes, per query, the (k+1)-th smallest slot
@@ -826,6 +845,8 @@ __device__ __forceinline__ float prep_kth_smallest(unsigned int *__restrict__ ke
 template <int D>
 __global__ void __launch_bounds__(kThreads, 3) knn_prep_kernel(const PrepArgs A) {
     const StampScope stamp(kStampPrep);
+    GEM_DIAG_DECL;
+    GEM_DIAG_T(0);
     using CandT = typename MidT<D>::T;
     extern __shared__ __align__(16) unsigned char prep_smem[];
     float4 *s_q = reinterpret_cast<float4 *>(prep_smem);                      // (a0,a1,a2,qn) per query
@@ -867,6 +888,7 @@ __global__ void __launch_bounds__(kThreads, 3) knn_prep_kernel(const PrepArgs A)
             s_q[q] = make_float4(p.a0, p.a1, p.a2, p.qn);
         }
         __syncthreads();
+        GEM_DIAG_T(1);
         // ---- (1) bound pass over this CTA's stratified sample
         const int64_t lo = ((int64_t)blockIdx.x * A.e_bound) / A.g, hi = ((int64_t)(blockIdx.x + 1) * A.e_bound) / A.g;
         const int64_t take = min((int64_t)A.per, hi - lo);
@@ -889,13 +911,18 @@ __global__ void __launch_bounds__(kThreads, 3) knn_prep_kernel(const PrepArgs A)
             }
             for (int64_t t0 = 0; t0 < take; t0 += kBoundTile) {
                 const int cnt = (int)min((int64_t)kBoundTile, take - t0);
-                const int64_t base = lo + t0;
+                // sample j of this CTA = candidate lo + floor(j * span / take): EVENLY SPACED over the stratum.  The edge
+                // list is sorted by first endpoint, so consecutive candidates are the edges of one vertex and their
+                // midpoints one spatial cluster: a contiguous sample sees a hub's cluster entirely or not at all, and a
+                // query next to an unsampled cluster got a threshold that admitted the whole cluster (measured at C3:
+                // 20 consecutive candidate blocks with 64 slow-path events each, 175 us in ONE warp)
+                const int64_t span = hi - lo;
                 __syncthreads();
                 if (mid != nullptr) {
-                    for (int c = threadIdx.x; c < cnt; c += kThreads) tile[c] = __ldg(mid + base + c);
+                    for (int c = threadIdx.x; c < cnt; c += kThreads) tile[c] = __ldg(mid + lo + ((t0 + c) * span) / take);
                 } else {
                     for (int c = threadIdx.x; c < cnt; c += kThreads) {
-                        const int2 ed = __ldg(A.bound_edges + base + c);
+                        const int2 ed = __ldg(A.bound_edges + lo + ((t0 + c) * span) / take);
                         tile[c] = make_mid(half_sum(Vec<D>::load(A.pos, ed.x), Vec<D>::load(A.pos, ed.y)));
                     }
                 }
@@ -934,11 +961,13 @@ __global__ void __launch_bounds__(kThreads, 3) knn_prep_kernel(const PrepArgs A)
         }
     }
     // ---- (3) the last CTA derives the thresholds
+    GEM_DIAG_T(2);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) s_last = (atomicAdd(A.ticket, 1u) == gridDim.x - 1);
     __syncthreads();
-    if (!s_last) return;
+    GEM_DIAG_T(3);
+    if (!s_last) { GEM_PDIAG_FLUSH(); return; }
     __threadfence();
     const float *hint = A.hint_in != nullptr ? A.hint_in : (A.row_ptr != nullptr ? A.hint_out : nullptr);
     for (int q = threadIdx.x; q < A.s; q += kThreads) {
@@ -970,12 +999,18 @@ __global__ void __launch_bounds__(kThreads, 3) knn_prep_kernel(const PrepArgs A)
         A.qcoef[(1 * (kMaxBatchQ / 2) + qc / 2) * 2 + (qc & 1)] = qp.a1;
         A.qcoef[(2 * (kMaxBatchQ / 2) + qc / 2) * 2 + (qc & 1)] = qp.a2;
     }
+    GEM_DIAG_T(4);
     for (int i = threadIdx.x; i < A.ncounts; i += kThreads) A.counts[i] = 0;   // the scan's survivor / tile counters
     if (A.zero_doubles != nullptr && (int)threadIdx.x < A.n_zero_doubles) A.zero_doubles[threadIdx.x] = 0.0;
     if (threadIdx.x == 0) {
         *A.ticket = 0;
         if (A.bump && A.iter_counter) *A.iter_counter = *A.iter_counter + 1;    // every CTA has read it (ticket)
     }
+#ifdef GEM_SCAN_DIAG
+    GEM_DIAG_T(5);
+    if (threadIdx.x == 0) dg[6] = 1;
+    GEM_PDIAG_FLUSH();
+#endif
 }
 
 // mbarrier / TMA bulk-copy helpers (cp.async.bulk -> SASS UBLKCP)
@@ -1029,64 +1064,143 @@ __device__ __forceinline__ ScanShared scan_shared(unsigned char *smem_raw, int k
     return S;
 }
 
-// Rare path, out of line: candidate (x,y,z,n) with global id `idx` passed the fp32 filter for query
-// slot ql of this CTA; re-evaluate it in the exact cdist chain and insert into the CTA's list.
-//   * list not yet full (the normal regime: a CTA sees ~1/300 of the candidates, so a query's list
-//     rarely fills): lock-free append -- one shared-memory atomicAdd claims a slot, one store fills it;
-//   * list full: under the per-query lock, replace the worst key; the new worst becomes the bound
-//     and tightens the filter threshold (bounded work under poor bounds / thousands of exact ties).
+// Rare path, out of line.  A (query, candidate) pair that passed the fp32 filter is re-evaluated in the exact cdist
+// chain and inserted into the CTA's list of that query:
+//   * list not yet full (the normal regime: a CTA sees 1/148 of the candidates, so a query's list rarely fills):
+//     lock-free append -- one shared-memory atomicAdd claims a slot, one store fills it;
+//   * list full: under the per-query lock, replace the worst key; the new worst becomes the bound and tightens the
+//     filter threshold (bounded work under poor bounds / thousands of exact ties).
 // Slots hold the sentinel ~0 until written, so the first locked visitor can wait for appends in flight.
+//
+// The pairs of a candidate block are first COLLECTED in a warp-private queue (scan_slow_block) and then resolved 32
+// at a time by this function, one pair per lane: the exact chain runs 32 wide no matter which queries passed.  The
+// first version resolved each pair where it was found, inside divergent code with one or two lanes active; at C3 a
+// vertex 1700 sigma away from the rest of the layout makes the cdist chain return 0 for all 5125 of its edges against
+// two sampled queries (|q|^2 ~ 7.5e5 swallows the differences: the reference computes the same zeros and orders
+// them by index), and the 27 warps that owned those candidate blocks spent 38 us each in ~770 serial evaluations
+// while the rest of the GPU waited (scan CTA life: mean 134, max 153 us).
+//
+// Two phases with a warp barrier between them: every lock-free append of THIS warp is complete before any of its lanes
+// enters the locked path, so the wait for an append in flight can only ever wait for another warp.
 constexpr uint64_t kEmptyKey = ~0ull;
+constexpr int kPairQueue = 64;                       // queue entries per warp: < 32 waiting + <= 32 pushed per step
+#ifdef GEM_SCAN_DIAG
+struct ResolveDiag { unsigned long long ns, locked_lanes, spins, evals, calls; };
+#define GEM_RDIAG_PARAM , ResolveDiag &rd
+#define GEM_RDIAG_ARG , rd
+#else
+#define GEM_RDIAG_PARAM
+#define GEM_RDIAG_ARG
+#endif
 template <int D>
-__device__ __forceinline__ void scan_insert(unsigned char *smem_raw, int kp1, int ql, float x, float y, float z, float n,
-                                            uint32_t idx, unsigned long long *stats) {
-    const ScanShared S = scan_shared<sizeof(typename MidT<D>::T)>(smem_raw, kp1);
-    const float4 qv = S.lqpar[ql];
-    QueryPar p;
-    p.a0 = qv.x; p.a1 = qv.y; p.a2 = qv.z; p.qn = qv.w;
-    const uint64_t key = make_key(chain_mm(p, x, y, z, n, D), idx);
-    bool pending = key < S.bound[ql];
-    if (stats) atomicAdd(stats + (pending ? 1 : 0), 1ull);
-    if (!pending) return;
+__device__ __forceinline__ void scan_resolve_pairs(const ScanShared &S, int kp1, const unsigned short *entries, int count,
+                                                   const typename MidT<D>::T *tile, int lane, uint32_t base,
+                                                   unsigned long long *stats GEM_RDIAG_PARAM) {
+#ifdef GEM_SCAN_DIAG
+    const unsigned long long rd_t0 = globaltimer_ns();
+    int rd_spins = 0, rd_evals = 0;
+#endif
+    const bool act = lane < count;
+    const int ent = act ? (int)entries[lane] : 0;
+    __syncwarp();                                           // every lane holds its entry: the queue may be overwritten
+    const int ql = ent >> 8, c = ent & 255;
+    uint64_t key = 0;
+    bool pending = false;
     volatile uint64_t *lst = S.lists + (size_t)ql * kp1;
-    const int slot = atomicAdd(&S.lcount[ql], 1);
-    if (slot < kp1) {                                       // lock-free append
-        lst[slot] = key;
-        if (stats) atomicAdd(stats + 2, 1ull);
-        return;
-    }
-    while (pending) {                                       // canonical SIMT-safe lock: work inside the loop
-        if (atomicCAS(&S.lock[ql], 0, 1) == 0) {
-            __threadfence_block();
-            int ws = S.wslot[ql];
-            if (ws < 0) {                                   // first visitor of a full list: find its worst key
-                uint64_t worst = 0;
-                for (int u = 0; u < kp1; ++u) {
-                    uint64_t ku;
-                    while ((ku = lst[u]) == kEmptyKey) {}   // an append that claimed the slot is still in flight
-                    if (ku >= worst) { worst = ku; ws = u; }
+    if (act) {
+        float x, y, z, n;
+        cand_xyzn(tile[c], x, y, z, n);
+        const float4 qv = S.lqpar[ql];
+        const float np = __fmul_rn(n, 1.0f - kSlack);
+        const float f = (D == 3) ? fmaf(qv.x, x, fmaf(qv.y, y, fmaf(qv.z, z, np))) : fmaf(qv.x, x, fmaf(qv.y, y, np));
+        if (f <= S.ltheta[ql]) {                            // the threshold may have tightened since the pair was queued
+            QueryPar p;
+            p.a0 = qv.x; p.a1 = qv.y; p.a2 = qv.z; p.qn = qv.w;
+            key = make_key(chain_mm(p, x, y, z, n, D), base + (uint32_t)c);
+            pending = key < S.bound[ql];
+#ifdef GEM_SCAN_DIAG
+            rd_evals = 1;
+#endif
+            if (stats) atomicAdd(stats + (pending ? 1 : 0), 1ull);
+#if GEM_SCAN_DIAG >= 2
+            if (d_q_diag != nullptr) atomicAdd(d_q_diag + (size_t)ql * 8 + (pending ? 1 : 0), 1ull);
+#endif
+            if (pending) {
+                const int slot = atomicAdd(&S.lcount[ql], 1);
+                if (slot < kp1) {                           // lock-free append
+                    lst[slot] = key;
+                    pending = false;
+                    if (stats) atomicAdd(stats + 2, 1ull);
                 }
-                S.wslot[ql] = ws;
-                S.bound[ql] = worst;
-                S.ltheta[ql] = fminf(S.ltheta[ql], filter_threshold(key_dist(worst), p.qn));
             }
-            if (key < S.bound[ql]) {
-                lst[ws] = key;                              // replace the current worst, then find the new one
-                uint64_t worst = 0;
-                for (int u = 0; u < kp1; ++u) {
-                    const uint64_t ku = lst[u];
-                    if (ku >= worst) { worst = ku; ws = u; }
-                }
-                S.wslot[ql] = ws;
-                S.bound[ql] = worst;
-                S.ltheta[ql] = fminf(S.ltheta[ql], filter_threshold(key_dist(worst), p.qn));
-                if (stats) atomicAdd(stats + 2, 1ull);
-            }
-            __threadfence_block();
-            atomicExch(&S.lock[ql], 0);
-            pending = false;
         }
     }
+    __syncwarp();
+    // phase 2: lanes whose query list is full.  The WARP takes the query's lock once for all of its lanes that wait on
+    // that query and replaces worst keys cooperatively: the list sits in registers (entries lane and lane + 32), its
+    // maximum comes from two REDUX steps.  (First version: every lane for itself -- a CAS spin against its own warp
+    // mates, two dependent passes over the list per replacement: ~3000 cycles per locked lane, measured.)
+    static_assert(kMaxFastKp1 <= 64, "two list entries per lane");
+    unsigned pendmask = __ballot_sync(0xffffffffu, pending);
+#ifdef GEM_SCAN_DIAG
+    rd.locked_lanes += __popc(pendmask);
+#endif
+    while (pendmask != 0u) {
+        const int q = __shfl_sync(0xffffffffu, ql, __ffs(pendmask) - 1);
+        unsigned same = __ballot_sync(0xffffffffu, pending && ql == q);
+        pendmask &= ~same;
+        if (lane == 0) {
+            while (atomicCAS(&S.lock[q], 0, 1) != 0) {
+#ifdef GEM_SCAN_DIAG
+                ++rd_spins;
+#endif
+            }
+            __threadfence_block();
+        }
+        __syncwarp();
+        volatile uint64_t *l = S.lists + (size_t)q * kp1;
+        // an append (of another warp) that claimed a slot may still be in flight: wait for the sentinel to go
+        uint64_t e0 = 0, e1 = 0;
+        const bool h0 = lane < kp1, h1 = lane + 32 < kp1;
+        if (h0) while ((e0 = l[lane]) == kEmptyKey) {}
+        if (h1) while ((e1 = l[lane + 32]) == kEmptyKey) {}
+        uint64_t worst = 0;
+        for (;;) {
+            // worst key of the list: max over the held entries (keys are unique: the index is part of the key)
+            const uint64_t m = (h1 && e1 > e0) ? e1 : e0;
+            const uint32_t mhi = h0 ? (uint32_t)(m >> 32) : 0u, mlo = (uint32_t)m;
+            const uint32_t whi = __reduce_max_sync(0xffffffffu, mhi);
+            const uint32_t wlo = __reduce_max_sync(0xffffffffu, (h0 && mhi == whi) ? mlo : 0u);
+            worst = ((uint64_t)whi << 32) | wlo;
+            if (same == 0u) break;
+            const int t = __ffs(same) - 1;
+            same &= same - 1;
+            const uint32_t khi = __shfl_sync(0xffffffffu, (uint32_t)(key >> 32), t);
+            const uint32_t klo = __shfl_sync(0xffffffffu, (uint32_t)key, t);
+            const uint64_t kt = ((uint64_t)khi << 32) | klo;
+            if (kt < worst) {                                 // replace the worst key (exactly one lane holds it)
+                if (h0 && e0 == worst) { e0 = kt; l[lane] = kt; }
+                else if (h1 && e1 == worst) { e1 = kt; l[lane + 32] = kt; }
+                if (stats && lane == 0) atomicAdd(stats + 2, 1ull);
+            }
+        }
+        if (lane == 0) {
+            S.bound[q] = worst;
+            S.ltheta[q] = fminf(S.ltheta[q], filter_threshold(key_dist(worst), S.lqpar[q].w));
+        }
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_block();
+            atomicExch(&S.lock[q], 0);
+        }
+    }
+    __syncwarp();
+#ifdef GEM_SCAN_DIAG
+    rd.spins += __reduce_max_sync(0xffffffffu, rd_spins);
+    rd.evals += __reduce_add_sync(0xffffffffu, rd_evals);
+    rd.calls += 1;
+    rd.ns += globaltimer_ns() - rd_t0;
+#endif
 }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
@@ -1108,20 +1222,34 @@ __constant__ float2 c_qcoef[kCoefSlots][3][kMaxBatchQ / 2];
 
 // Rare path, out of line, entered by the WHOLE warp when any lane has a hit.  A set bit c of a
 // lane's `hitmask` says: some (query of the pairs [c*kPairChunk, (c+1)*kPairChunk), candidate of that
-// lane) passed the filter.  The warp resolves one (lane, chunk) event at a time cooperatively: the
+// lane) passed the filter.  The warp examines one (lane, chunk) event at a time cooperatively: the
 // event's 16 queries x kC candidates are spread over the 32 lanes (the candidates are re-read from
-// the staged tile, which every lane can see), so an event costs a few dozen instructions instead of a
-// 96-pair serial re-scan by one lane with 31 lanes idle.  It runs after the whole query block (not
+// the staged tile, which every lane can see); the pairs that pass again are pushed to the warp's queue
+// and resolved 32 at a time (scan_resolve_pairs).  It runs after the whole query block (not
 // inside the pair loop): a call inside the loop keeps ptxas from using uniform registers there.
 template <int D>
 __device__ __noinline__ void scan_slow_block(unsigned char *smem_raw, int kp1, uint32_t hitmask,
-                                             const typename MidT<D>::T *tile, int cb, int lane, int cnt, uint32_t base,
-                                             unsigned long long *stats) {
-    static_assert(kPairChunk == 8 && kC % 2 == 0, "16 queries x (kC/2) candidate pairs per event");
+                                             const typename MidT<D>::T *tile, unsigned short *queue, int lane, int cnt,
+                                             uint32_t base, unsigned long long *stats) {
+    static_assert(kPairChunk == 8 && kC == 6, "16 queries x 3 candidate pairs per event");
+    static_assert(kCandBlock <= 256 && kQB <= 256, "a queue entry is (query << 8) | candidate");
     const ScanShared S = scan_shared<sizeof(typename MidT<D>::T)>(smem_raw, kp1);
+    const uint32_t lt = (1u << lane) - 1u;
+    int nq = 0;                                                        // queued pairs (warp-uniform), < 32 between steps
+#ifdef GEM_SCAN_DIAG
+    unsigned long long diag_ts = 0, diag_ev = 0;
+    ResolveDiag rd = {0, 0, 0, 0, 0};
+    if (lane == 0) diag_ts = globaltimer_ns();
+#if GEM_SCAN_DIAG >= 2
+    stats = reinterpret_cast<unsigned long long *>(queue + kPairQueue);
+#endif
+#endif
     for (;;) {
         const unsigned pend = __ballot_sync(0xffffffffu, hitmask != 0);
         if (!pend) break;
+#ifdef GEM_SCAN_DIAG
+        ++diag_ev;
+#endif
         const int src = __ffs(pend) - 1;                               // lane whose candidates are examined
         const uint32_t hm = __shfl_sync(0xffffffffu, hitmask, src);
         const int ch = __ffs(hm) - 1;
@@ -1129,22 +1257,53 @@ __device__ __noinline__ void scan_slow_block(unsigned char *smem_raw, int kp1, u
         if (stats && lane == 0) atomicAdd(stats + 3, 1ull);
         const int ql = 2 * ch * kPairChunk + (lane & 15);
         const float4 qv = S.lqpar[ql];
-        float th = S.ltheta[ql];
+        const float th = S.ltheta[ql];
+        bool pass[kC / 2];
+        int cc[kC / 2];
 #pragma unroll
-        for (int r = 0; r < kC / 2; ++r) {
-            const int c = cb + ((lane >> 4) + 2 * r) * 32 + src;
+        for (int r = 0; r < kC / 2; ++r) {                             // the three loads are in flight together
+            const int c = ((lane >> 4) + 2 * r) * 32 + src;
+            cc[r] = c;
+            pass[r] = false;
             if (c < cnt) {                                             // slots past the tile's end are never inserted
                 float x, y, z, n;
                 cand_xyzn(tile[c], x, y, z, n);
                 const float np = __fmul_rn(n, 1.0f - kSlack);
                 const float f = (D == 3) ? fmaf(qv.x, x, fmaf(qv.y, y, fmaf(qv.z, z, np))) : fmaf(qv.x, x, fmaf(qv.y, y, np));
-                if (f <= th) {
-                    scan_insert<D>(smem_raw, kp1, ql, x, y, z, n, base + (uint32_t)c, stats);
-                    th = fminf(th, S.ltheta[ql]);
-                }
+                pass[r] = f <= th;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < kC / 2; ++r) {
+            const unsigned m = __ballot_sync(0xffffffffu, pass[r]);
+            if (m == 0u) continue;
+            if (pass[r]) queue[nq + __popc(m & lt)] = (unsigned short)((ql << 8) | cc[r]);
+            nq += __popc(m);
+            __syncwarp();
+            if (nq >= 32) {
+                nq -= 32;
+                scan_resolve_pairs<D>(S, kp1, queue + nq, 32, tile, lane, base, stats GEM_RDIAG_ARG);     // the 32 newest entries
             }
         }
     }
+    if (nq > 0) scan_resolve_pairs<D>(S, kp1, queue, nq, tile, lane, base, stats GEM_RDIAG_ARG);
+#ifdef GEM_SCAN_DIAG
+    if (lane == 0) {
+        unsigned long long *sd = reinterpret_cast<unsigned long long *>(queue + kPairQueue);
+        const unsigned long long dt = globaltimer_ns() - diag_ts;
+        sd[4] += dt;
+#if GEM_SCAN_DIAG < 2
+        sd[3] += diag_ev;
+#endif
+        if (dt > sd[5]) {
+            sd[5] = dt; sd[6] = base / kCandBlock; sd[7] = diag_ev;
+#if GEM_SCAN_DIAG < 2
+            // of the longest call: resolve ns | locked lanes | max spins | exact evaluations | resolve calls
+            sd[0] = rd.ns; sd[1] = (rd.locked_lanes << 32) | rd.spins; sd[2] = (rd.evals << 32) | rd.calls;
+#endif
+        }
+    }
+#endif
 }
 
 // Every warp is its own producer and consumer: it draws blocks of kCandBlock candidates from a
@@ -1166,6 +1325,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) knn_scan_kernel(const typenam
                                                           // (a batch in the upper half of the bank passes shifted array
                                                           // pointers; a second, blockIdx.y-only index costs the UR operands)
     const StampScope stamp(kStampScan);
+    GEM_DIAG_DECL;
+    GEM_DIAG_T(0);
     // query block = blockIdx.y (+ qb0): a batch of up to 1024 queries is ONE launch of (g, blocks) CTAs.  Block indices and
     // kernel parameters are uniform by construction, which the constant-bank coefficient addressing below depends on
     // (ptxas keeps them in uniform registers; a per-warp value read from shared memory does not qualify)
@@ -1175,6 +1336,14 @@ __global__ void __launch_bounds__(kScanThreads, 1) knn_scan_kernel(const typenam
     __shared__ __align__(8) uint64_t full_bar[kScanWarps][kWStages];
     __shared__ int blk_id[kScanWarps][kWStages];             // -1: no more blocks
     __shared__ unsigned int s_next;                          // next block ordinal of this CTA
+#ifdef GEM_SCAN_DIAG
+    // diagnostic build: 8 counters per warp behind its queue ([3] events, [4] slow-path ns, [5] longest call ns, [6] its block, [7] its events)
+    __shared__ __align__(16) unsigned short s_queue[kScanWarps][kPairQueue + 32];
+    if (threadIdx.x < kScanWarps * 8)
+        reinterpret_cast<unsigned long long *>(&s_queue[threadIdx.x >> 3][kPairQueue])[threadIdx.x & 7] = 0ull;
+#else
+    __shared__ unsigned short s_queue[kScanWarps][kPairQueue];   // slow path: (query, candidate) pairs waiting for the exact chain
+#endif
 
     const int lane = threadIdx.x & 31;
     const int warp = __reduce_max_sync(0xffffffffu, (int)(threadIdx.x >> 5));   // uniform register (see the block id below)
@@ -1189,6 +1358,18 @@ __global__ void __launch_bounds__(kScanThreads, 1) knn_scan_kernel(const typenam
     const int cta_in_part = (int)(blockIdx.x >> qs), ctas_per_part = (int)(gridDim.x >> qs);   // gridDim.x % 2^qs == 0
     const int mc_lo = part * ((kQB / 2) >> qs), mc_n = (kQB / 2) >> qs;
 
+#ifdef GEM_SCAN_WARM
+    {   // touch this CTA's coefficient lines once, spread over the warps (a cold constant cache otherwise serves the
+        // first candidate block of EVERY warp one miss after the other)
+        const int lines = mc_n >> 3;                  // 64-byte lines (8 pairs) per coefficient array
+        float sink = 0.f;
+        for (int i = warp; i < D * lines; i += kScanWarps) {
+            const int k = i / lines, ln = i - k * lines;
+            sink += c_qcoef[slot][k][qb * (kQB / 2) + mc_lo + ln * 8].x;
+        }
+        if (sink == 1.2345678e-33f) s_next = 1u;      // never true in practice; keeps the loads (re-initialised below)
+    }
+#endif
     if (threadIdx.x < kQB) {   // per-query state of this CTA
         const int q = qb * kQB + threadIdx.x;
         float ta = -1.f, th = -kInf;
@@ -1199,6 +1380,13 @@ __global__ void __launch_bounds__(kScanThreads, 1) knn_scan_kernel(const typenam
             qv = make_float4(p.a0, p.a1, p.a2, p.qn);
         }
         // initial bound: every key whose distance is <= tau  (key < (tau_bits+1) << 32)
+#ifdef GEM_SCAN_DIAG
+        if (d_q_diag != nullptr && blockIdx.x == 0 && q < s) {
+            d_q_diag[(size_t)threadIdx.x * 8 + 2] = __float_as_uint(ta);
+            d_q_diag[(size_t)threadIdx.x * 8 + 3] = __float_as_uint(th);
+            d_q_diag[(size_t)threadIdx.x * 8 + 4] = __float_as_uint(qv.w);
+        }
+#endif
         S.bound[threadIdx.x] = (q < s) ? (((uint64_t)__float_as_uint(ta) + 1ull) << 32) : 0ull;
         S.lqpar[threadIdx.x] = qv;
         S.ltheta[threadIdx.x] = th;
@@ -1215,6 +1403,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) knn_scan_kernel(const typenam
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
+    GEM_DIAG_T(1);
 
     CandT *stages = reinterpret_cast<CandT *>(smem_raw) + (size_t)warp * kWStages * kCandBlock;
     // lane 0: draw the next block and start its bulk copy into stage st (or post "no more blocks")
@@ -1258,6 +1447,10 @@ __global__ void __launch_bounds__(kScanThreads, 1) knn_scan_kernel(const typenam
         // addresses of the coefficient pairs) stays on the uniform datapath, which ptxas only uses
         // when it can prove the value warp-uniform -- a plain shared-memory load is not
         const int b = __reduce_max_sync(0xffffffffu, blk_id[warp][st]);
+#ifdef GEM_SCAN_DIAG
+        if (it == 0) GEM_DIAG_T(2);
+        if (it == 1) GEM_DIAG_T(8);
+#endif
         if (b < 0) break;
         const int64_t base = (int64_t)b * kCandBlock;
         const int cnt = (int)min((int64_t)kCandBlock, e - base);
@@ -1276,7 +1469,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) knn_scan_kernel(const typenam
             }
             uint32_t hitmask = 0;
             static_assert(kQB / 2 / kPairChunk <= 32, "one bit per pair chunk");
-            static_assert(scan_smem_bytes(16, kMaxFastKp1) + 1024 <= 227 * 1024, "scan CTA exceeds the shared memory of an SM");
+            static_assert(scan_smem_bytes(16, kMaxFastKp1) + 3072 <= 227 * 1024, "scan CTA exceeds the shared memory of an SM");
             for (int mcr = 0; mcr < mc_n; mcr += kPairChunk) {
                 const int mc = mc_lo + mcr;
                 unsigned int any = 0u;
@@ -1309,14 +1502,32 @@ __global__ void __launch_bounds__(kScanThreads, 1) knn_scan_kernel(const typenam
                 }
                 if (any) hitmask |= 1u << (mc / kPairChunk);
             }
+#ifdef GEM_SCAN_DIAG
+            if (it == 0) GEM_DIAG_T(3);
+            if (it == 1) GEM_DIAG_T(9);
+#endif
             if (__any_sync(0xffffffffu, hitmask != 0))
-                scan_slow_block<D>(smem_raw, kp1, hitmask, tile, 0, lane, cnt, (uint32_t)base, stats);
+                scan_slow_block<D>(smem_raw, kp1, hitmask, tile, &s_queue[warp][0], lane, cnt, (uint32_t)base, stats);
+
+#ifdef GEM_SCAN_DIAG
+            if (it == 0) GEM_DIAG_T(4);
+            if (it == 1) GEM_DIAG_T(10);
+            if (threadIdx.x == 0) dg[11] += 1;
+#endif
         }
         __syncwarp();
         if (lane == 0) fetch(st);                           // refill the stage this warp has just finished
         __syncwarp();
     }
+    GEM_DIAG_T(5);
+#ifdef GEM_SCAN_DIAG
+    if (threadIdx.x == 0) s_next = (unsigned int)dg[5];      // a store the barrier cannot be hoisted over
+#endif
     __syncthreads();
+#ifdef GEM_SCAN_DIAG
+    if (threadIdx.x == 0) dg[11] += (s_next == 0xFFFFFFFFu);
+#endif
+    GEM_DIAG_T(6);
     // publish this CTA's survivors: at most kp1 per query, so counts[q] <= gridDim.x * kp1 <= cap
     if (threadIdx.x < kQB) {
         const int q = qb * kQB + threadIdx.x;
@@ -1328,6 +1539,13 @@ __global__ void __launch_bounds__(kScanThreads, 1) knn_scan_kernel(const typenam
                 if (slot + u < (uint32_t)cap) keys[(int64_t)q * cap + slot + u] = lst[u];
         }
     }
+    GEM_DIAG_T(7);
+    GEM_DIAG_FLUSH();
+#ifdef GEM_SCAN_DIAG
+    if (d_scan_diag != nullptr && threadIdx.x < kScanWarps * 8)      // per-warp slow-path counters behind the per-CTA rows
+        d_scan_diag[(size_t)1024 * 12 + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (kScanWarps * 8) + threadIdx.x] =
+            reinterpret_cast<unsigned long long *>(&s_queue[threadIdx.x >> 3][kPairQueue])[threadIdx.x & 7];
+#endif
 }
 
 // merge `parts` sorted partial lists per query by (distance, index); total <= kMaxKp1 * 8
@@ -1571,6 +1789,8 @@ __global__ void __launch_bounds__(kThreads) knn_select_kernel(const uint32_t *__
                                                               const uint64_t *__restrict__ keys, int cap, int kp1,
                                                               const SelectOut so, FusedIntersect fx) {
     const StampScope stamp(kStampSelect);
+    GEM_DIAG_DECL;
+    GEM_DIAG_T(0);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *all = reinterpret_cast<uint64_t *>(smem_raw);        // cap
     __shared__ uint64_t sub[kThreads];
@@ -1603,10 +1823,20 @@ __global__ void __launch_bounds__(kThreads) knn_select_kernel(const uint32_t *__
     // a hinted (shard-local) search may find fewer than kp1 candidates: pad with (+inf, -1)
     for (int r = n + t; r < kp1; r += kThreads) select_emit(so, (int64_t)q * kp1 + r, -1, kInf);
     __syncthreads();
-    // shrink by strided-subsample thresholds until direct rank counting is cheap
-    while (n > kSurvMax || (n > 2 * kThreads && n > 8 * kp1)) {
-        const int stride = (n + kThreads - 1) / kThreads;
-        const int m = (n + stride - 1) / stride;
+    GEM_DIAG_T(1);
+#ifdef GEM_SCAN_DIAG
+    if (t == 0) dg[5] = (unsigned long long)n;
+#endif
+    // shrink by strided-subsample thresholds until direct rank counting is cheap: m ~ 4 (k+1) sampled keys (64..256),
+    // the sampled key of rank k is a valid bound and keeps ~ n (k+1) / m keys.  (Rank counting is one broadcast
+    // shared-memory load per comparison, n^2 / 256 per thread: at C3 the CTAs with 300-440 keys spent 6-9 us there
+    // while the first version only shrank lists longer than 512.)
+    int mt = 4 * kp1;
+    if (mt < 64) mt = 64;
+    if (mt > kThreads) mt = kThreads;
+    while (n > 2 * mt) {
+        const int stride = (n + mt - 1) / mt;
+        const int m = (n + stride - 1) / stride;         // <= mt <= kThreads
         if (m < kp1) break;
         if (t == 0) { s_thr = ~0ull; s_nsurv = 0; }
         if (t < m) sub[t] = all[t * stride];
@@ -1633,6 +1863,10 @@ __global__ void __launch_bounds__(kThreads) knn_select_kernel(const uint32_t *__
         if (ns >= n) break;                              // no progress (cannot happen with unique keys)
         n = ns;
     }
+    GEM_DIAG_T(2);
+#ifdef GEM_SCAN_DIAG
+    if (t == 0) dg[6] = (unsigned long long)n;
+#endif
     for (int i = t; i < n; i += kThreads) {
         const uint64_t k = all[i];
         int r = 0;
@@ -1643,7 +1877,13 @@ __global__ void __launch_bounds__(kThreads) knn_select_kernel(const uint32_t *__
             if (r < kMaxFastKp1) s_nb[r] = id;
         }
     }
+    GEM_DIAG_T(3);
     if (fx.force != nullptr) fused_intersect_tail(fx, q, t, kp1, n < kp1 ? n : kp1, s_nb, qi, qe, qa, qb4);
+#ifdef GEM_SCAN_DIAG
+    GEM_DIAG_T(4);
+    if (t == 0 && d_sel_diag != nullptr)
+        for (int i_ = 0; i_ < 8; ++i_) d_sel_diag[(size_t)blockIdx.x * 8 + i_] = dg[i_];
+#endif
 }
 
 // multi-GPU publication stage of the merge kernel (world == 0: none)
@@ -2731,6 +2971,25 @@ int gem_abi_struct_sizes(size_t *out4) {
     out4[3] = sizeof(gem_merge_publish);
     return GEM_OK;
 }
+
+#ifdef GEM_SCAN_DIAG
+int gem_debug_scan_diag(unsigned long long *buffer) {
+    GEM_CUDA(cudaMemcpyToSymbol(d_scan_diag, &buffer, sizeof(buffer)));
+    return GEM_OK;
+}
+int gem_debug_sel_diag(unsigned long long *buffer) {
+    GEM_CUDA(cudaMemcpyToSymbol(d_sel_diag, &buffer, sizeof(buffer)));
+    return GEM_OK;
+}
+int gem_debug_q_diag(unsigned long long *buffer) {
+    GEM_CUDA(cudaMemcpyToSymbol(d_q_diag, &buffer, sizeof(buffer)));
+    return GEM_OK;
+}
+int gem_debug_prep_diag(unsigned long long *buffer) {
+    GEM_CUDA(cudaMemcpyToSymbol(d_prep_diag, &buffer, sizeof(buffer)));
+    return GEM_OK;
+}
+#endif
 
 int gem_debug_stamps(unsigned long long *buffer) {
     GEM_CUDA(cudaMemcpyToSymbol(d_stamps, &buffer, sizeof(buffer)));
