@@ -195,6 +195,7 @@ class GraphEmbedderPyTorch:
         self._sampler_seed = int(seed) if seed is not None else int(torch.randint(0, 2 ** 62, (1,)).item())
         self._bufs = {}
         self._graph = None
+        self._graph_unrolled = None
         self._graph_key = None
         self._torch_sample_ready = False
         self.last_sampled_indices = None
@@ -528,6 +529,7 @@ class GraphEmbedderPyTorch:
             knn_ws_bytes=ws_bytes.value,
         )
         self._graph = None
+        self._graph_unrolled = None
         self._torch_sample_ready = False
         return self._bufs
 
@@ -660,6 +662,38 @@ class GraphEmbedderPyTorch:
             return True
         return self.n_edges >= self._TORCH_SAMPLER_GRAPH_MIN_E and not getattr(self, "_torch_graph_failed", False)
 
+    _GRAPH_UNROLL = 8
+
+    def _capture_iterations(self, count: int, torch_samp: bool):
+        """One CUDA graph of `count` consecutive iterations (both streams of gem_layout_step each)."""
+        b = self._buffers()
+        plan = self._plan(torch_samp)
+        graph = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize(self.device)
+        it0 = b["iter"].clone()
+        pos0 = self._pos.clone()
+        next0 = b["samp_next"].clone()
+        torch.cuda.synchronize(self.device)
+        rc = 0
+        with _nvtx_range("gem.capture_iteration"), torch.cuda.graph(graph):
+            for _ in range(int(count)):
+                if torch_samp:
+                    cur = torch.cuda.current_stream(self.device)
+                    b["samp"].copy_(b["samp_next"])
+                    side = torch.cuda.Stream(device=self.device)
+                    side.wait_stream(cur)
+                    with torch.cuda.stream(side):
+                        self._draw_torch_sample(b["samp_next"])
+                rc = rc or self._lib.gem_layout_step(ctypes.byref(plan), self._stream())
+                if torch_samp:
+                    cur.wait_stream(side)
+        _cabi.check(rc, "gem_layout_step (capture)")
+        # capture does not execute, but keep state exactly as it was in any case
+        b["iter"].copy_(it0)
+        self._pos.copy_(pos0)
+        b["samp_next"].copy_(next0)
+        return graph
+
     def _run_graph(self, num_iterations: int) -> bool:
         """Replay one captured iteration `num_iterations` times.
 
@@ -675,31 +709,20 @@ class GraphEmbedderPyTorch:
             self._draw_torch_sample(b["samp_next"])
             self._torch_sample_ready = True
         if self._graph is None or self._graph_key != key:
-            plan = self._plan(torch_samp)
-            graph = torch.cuda.CUDAGraph()
-            torch.cuda.synchronize(self.device)
-            it0 = b["iter"].clone()
-            pos0 = self._pos.clone()
-            next0 = b["samp_next"].clone()
-            torch.cuda.synchronize(self.device)
-            with _nvtx_range("gem.capture_iteration"), torch.cuda.graph(graph):
-                if torch_samp:
-                    cur = torch.cuda.current_stream(self.device)
-                    b["samp"].copy_(b["samp_next"])
-                    side = torch.cuda.Stream(device=self.device)
-                    side.wait_stream(cur)
-                    with torch.cuda.stream(side):
-                        self._draw_torch_sample(b["samp_next"])
-                rc = self._lib.gem_layout_step(ctypes.byref(plan), self._stream())
-                if torch_samp:
-                    cur.wait_stream(side)
-            _cabi.check(rc, "gem_layout_step (capture)")
-            # capture does not execute, but keep state exactly as it was in any case
-            b["iter"].copy_(it0)
-            self._pos.copy_(pos0)
-            b["samp_next"].copy_(next0)
-            self._graph, self._graph_key = graph, key
-        for _ in range(num_iterations):
+            self._graph, self._graph_key, self._graph_unrolled = self._capture_iterations(1, torch_samp), key, None
+        todo = int(num_iterations)
+        # Several iterations per graph: consecutive replays leave ~8-11 us of launch latency between the last kernel
+        # of one graph and the first of the next (C3: 254 us of kernels in a 266 us step; C1: 46 in 54); inside one
+        # graph a dependent kernel starts 2-4 us after its predecessor.  The device sampler keeps its iteration
+        # counter on the device, so the unrolled graph is the same launches in the same order.
+        U = self._GRAPH_UNROLL
+        if not torch_samp and U > 1 and todo >= U:
+            if self._graph_unrolled is None:
+                self._graph_unrolled = self._capture_iterations(U, torch_samp)
+            for _ in range(todo // U):
+                self._graph_unrolled.replay()
+            todo %= U
+        for _ in range(todo):
             self._graph.replay()
         self.last_sampled_indices = b["samp"]
         self.last_knn_indices = b["knn_idx"][:, 1:]
@@ -750,6 +773,7 @@ class GraphEmbedderPyTorch:
     def close(self):
         """Release the object's coefficient slot and captured graph (also done when it is garbage collected)."""
         self._graph = None
+        self._graph_unrolled = None
         if getattr(self, "_slot_finalizer", None) is not None:
             self._slot_finalizer()
 

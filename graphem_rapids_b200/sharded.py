@@ -29,6 +29,7 @@ symmetric memory is unavailable or a shard is too small for the fast KNN path.
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional
 
 import numpy as np
@@ -464,10 +465,13 @@ class ShardedGraphEmbedder(GraphEmbedderPyTorch):
     (identically seeded) default generator -- the ids are then compared across ranks in debug runs only."""
 
     def __init__(self, adjacency, n_components=2, *args, process_group=None, use_symmetric_memory=True,
-                 use_multicast=False, ownership="strided", **kwargs):
+                 use_multicast=False, ownership="strided", use_unrolled_graph=None, **kwargs):
         if not dist.is_initialized():
             raise RuntimeError("ShardedGraphEmbedder needs an initialised torch.distributed process group")
         self._group = process_group
+        # several iterations per captured graph (GEM_SHARDED_UNROLL=0 switches it off)
+        self.use_unrolled_graph = (os.environ.get("GEM_SHARDED_UNROLL", "1") != "0") if use_unrolled_graph is None \
+            else bool(use_unrolled_graph)
         self._ownership = ownership            # 'strided' (v mod G: balanced for any vertex order) | 'contiguous'
         kwargs["graph_build"] = "host"        # the vertex partition (partition.build_layout) is host work
         super().__init__(adjacency, n_components, *args, **kwargs)
@@ -510,7 +514,6 @@ class ShardedGraphEmbedder(GraphEmbedderPyTorch):
                 self._symm = dict(pos=h_pos, raw=h_raw, xchg=h_x, raw_t=raw, xchg_t=xchg)
                 self._pos = pos_buf
                 eng.pos = pos_buf
-                import os
                 mc = 0
                 # EXPERIMENTAL, off by default (GEM_MULTICAST=1 or use_multicast=True): the rows of the spring kernel go out
                 # as NVSwitch multicast stores (multimem.st.relaxed.sys + fence.sys).  Measured on 2 B200: same iteration
@@ -573,10 +576,14 @@ class ShardedGraphEmbedder(GraphEmbedderPyTorch):
         self.last_sampled_indices = self._engine.samp
         self.last_knn_indices = self._engine.knn_idx[:, 1:]
 
-    def _capture(self, parity: int):
-        """Capture one whole sharded iteration of this parity -- kernels on both streams, peer stores and the two
-        device barriers -- in a CUDA graph.  The raw / exchange buffers alternate with the iteration parity, so there
-        is one graph per parity."""
+    _GRAPH_UNROLL = 4          # even: an unrolled graph starts at parity 0 and ends there
+
+    def _capture(self, parity, count: int = 1):
+        """Capture `count` whole sharded iterations starting at this parity -- kernels on both streams, peer stores and
+        the two device barriers of each -- in a CUDA graph.  The raw / exchange buffers alternate with the iteration
+        parity, so there is one single-iteration graph per parity, plus one of _GRAPH_UNROLL iterations from parity 0
+        (key "unrolled": consecutive replays leave ~10-15 us between the last kernel of one graph and the first of the
+        next, a dependent kernel inside a graph starts after 2-4 us)."""
         eng = self._engine
         torch_samp = self.sampler == "torch"
         b = self._buffers() if torch_samp else None
@@ -594,9 +601,10 @@ class ShardedGraphEmbedder(GraphEmbedderPyTorch):
                 eng.step(b["samp"])
                 cur.wait_stream(side)
             else:
-                eng.step()
+                for _ in range(int(count)):
+                    eng.step()
         eng.iteration = it                      # capture does not execute
-        self._sgraphs[parity] = graph
+        self._sgraphs[parity if count == 1 else "unrolled"] = graph
 
     def _replay(self, num_iterations: int):
         eng = self._engine
@@ -619,12 +627,21 @@ class ShardedGraphEmbedder(GraphEmbedderPyTorch):
             if torch_samp and not self._torch_sample_ready:
                 self._draw_torch_sample(self._buffers()["samp_next"])
                 self._torch_sample_ready = True
-        for _ in range(todo):
+        U = self._GRAPH_UNROLL if (eng.st.p2p_ready and not torch_samp and self.use_unrolled_graph) else 1
+        while todo > 0:
             par = eng.iteration & 1 if eng.st.p2p_ready else 0
+            if U > 1 and par == 0 and todo >= U:
+                if "unrolled" not in self._sgraphs:
+                    self._capture(0, U)
+                self._sgraphs["unrolled"].replay()
+                eng.iteration += U
+                todo -= U
+                continue
             if par not in self._sgraphs:
                 self._capture(par)
             self._sgraphs[par].replay()
             eng.iteration += 1
+            todo -= 1
         self.last_sampled_indices = eng.samp
         self.last_knn_indices = eng.knn_idx[:, 1:]
 

@@ -276,6 +276,30 @@ def test_cuda_graph_replay_matches_eager():
     assert np.all(np.isfinite(pa)) and abs(pa.std(0) - 1).max() < 1e-3 and abs(pa.mean(0)).max() < 1e-4
 
 
+def test_unrolled_graph_is_the_same_iterations():
+    """run_layout_device(n) replays a graph of _GRAPH_UNROLL iterations floor(n / U) times and the single-iteration
+    graph for the rest: same launches in the same order as n eager iterations (same sample stream, same positions up
+    to the summation order of the atomics)."""
+    import graphem_rapids_b200 as gr
+    adj = gr.generate_ba(20000, 4, seed=0)
+    pos0 = (np.random.default_rng(0).standard_normal((20000, 3)) * 0.1).astype(np.float32)
+    kw = dict(n_components=3, device="cuda:0", verbose=False, seed=11, initial_positions=pos0)
+    a = gr.GraphEmbedderPyTorch(adj, **kw)
+    b = gr.GraphEmbedderPyTorch(adj, use_cuda_graph=False, **kw)
+    assert a._GRAPH_UNROLL > 1
+    a._GRAPH_UNROLL = U = 2          # few iterations: the layout is chaotic, the atomics' summation order differs
+    n_it = 2 * U + 1
+    a.run_layout_device(n_it)
+    assert a._graph_unrolled is not None and a._graph is not None
+    b.run_layout_device(n_it)
+    torch.cuda.synchronize()
+    assert int(a._buffers()["iter"].item()) == int(b._buffers()["iter"].item()) == n_it
+    assert torch.equal(a.last_sampled_indices, b.last_sampled_indices)
+    pa, pb = a.positions, b.positions
+    assert rel_inf(pa, pb) <= 2e-3
+    assert np.all(np.isfinite(pa)) and abs(pa.std(0) - 1).max() < 1e-3 and abs(pa.mean(0)).max() < 1e-4
+
+
 def test_private_api_shapes_like_reference_tests():
     """Mirrors tests/test_pytorch_backend.py:465-472,486-490,541 of the reference."""
     import graphem_rapids_b200 as gr
