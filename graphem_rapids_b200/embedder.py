@@ -386,11 +386,31 @@ class GraphEmbedderPyTorch:
         """numpy copy (:324-327): a fresh host array, like the reference's `.cpu().numpy()`."""
         if self.n * self.n_components < 65536:
             return self._positions.detach().cpu().numpy()
-        # large layouts: gather -> pinned staging (full-speed D2H) -> fresh pageable array filled by torch's
-        # multi-threaded host copy
+        # large layouts: gather -> pinned staging (full-speed D2H) -> fresh pageable array.  The D2H runs in chunks and
+        # the host fills the fresh array (page faults included) chunk by chunk behind it: the two copies overlap instead
+        # of adding up (12 MB at C3: ~0.25 ms each)
         pinned = self._pinned_stage()
-        self.read_positions(pinned)
-        return torch.empty_like(pinned, pin_memory=False).copy_(pinned).numpy()
+        d = self.n_components
+        with torch.cuda.device(self.device):
+            if self._ld == d and self._pad_index is None:
+                src = self._pos
+            else:
+                src = self._rows_to_public(out=self._io_stage("d2h_stage"))
+            nchunk = 4 if self.n >= 4 * 65536 else 1
+            bounds = [(self.n * c) // nchunk for c in range(nchunk + 1)]
+            events = []
+            for c in range(nchunk):
+                lo, hi = bounds[c], bounds[c + 1]
+                pinned[lo:hi].copy_(src[lo:hi], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                events.append(ev)
+            out = torch.empty((self.n, d), dtype=torch.float32)
+            for c in range(nchunk):
+                lo, hi = bounds[c], bounds[c + 1]
+                events[c].synchronize()
+                out[lo:hi].copy_(pinned[lo:hi])
+        return out.numpy()
 
     @positions.setter
     def positions(self, value):
@@ -737,8 +757,8 @@ class GraphEmbedderPyTorch:
         with torch.cuda.device(self.device), _nvtx_range(f"gem.run_layout[{int(num_iterations)}]"):
             if self.n_neighbors + 1 > self.n_edges and num_iterations > 0:
                 raise RuntimeError("selected index k out of range")
-            if num_iterations > 1 and self._graph_ok():
-                self._run_graph(int(num_iterations))
+            if self._graph_ok() and (num_iterations > 1 or (num_iterations == 1 and self._graph is not None)):
+                self._run_graph(int(num_iterations))          # a single iteration too, once its graph exists
             else:
                 for _ in range(int(num_iterations)):
                     self.update_positions()
