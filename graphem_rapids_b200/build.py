@@ -35,5 +35,23 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+DIAG_LIB = os.path.join(PKG_DIR, "libgraphem_b200_diag.so")
+
+
+def build_diag(level: int = 1) -> str:
+    """Diagnostic build (-DGEM_SCAN_DIAG=level): the scan / preparation / select kernels record %globaltimer points
+    of their phases (scripts/scan_diag.py).  A separate file: the product library is never replaced by it."""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found: cannot build the diagnostic library")
+    subprocess.check_call([nvcc] + NVCC_FLAGS + [f"-DGEM_SCAN_DIAG={int(level)}", "-I", os.path.join(ROOT, "include"), SRC,
+                                                 "-o", DIAG_LIB])
+    return DIAG_LIB
+
+
 if __name__ == "__main__":
-    print(build(force=True, verbose=True))
+    import sys
+    if "--diag" in sys.argv:
+        print(build_diag())
+    else:
+        print(build(force=True, verbose=True))

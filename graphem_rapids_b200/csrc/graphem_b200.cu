@@ -816,18 +816,18 @@ __device__ __forceinline__ float prep_unkey(unsigned int k) {
 }
 
 // (k+1)-th smallest of the `chunks` slot minima of query q, K = register list length >= kp1; clears the slots
-template <int K>
+template <int K, int B = 16>
 __device__ __forceinline__ float prep_kth_smallest(unsigned int *__restrict__ keys, int chunks, int s, int q, int kp1) {
     float lst[K];
 #pragma unroll
     for (int r = 0; r < K; ++r) lst[r] = kInf;
-    // the loads of a batch are all in flight before the first is consumed (one L2 round trip per 16 slots, not per slot)
-    for (int c0 = 0; c0 < chunks; c0 += 16) {
-        unsigned int kk[16];
+    // the loads of a batch are all in flight before the first is consumed (one L2 round trip per B slots, not per slot)
+    for (int c0 = 0; c0 < chunks; c0 += B) {
+        unsigned int kk[B];
 #pragma unroll
-        for (int u = 0; u < 16; ++u) kk[u] = (c0 + u < chunks) ? __ldcg(keys + (int64_t)(c0 + u) * s + q) : 0u;
+        for (int u = 0; u < B; ++u) kk[u] = (c0 + u < chunks) ? __ldcg(keys + (int64_t)(c0 + u) * s + q) : 0u;
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
+        for (int u = 0; u < B; ++u) {
             const float x = kk[u] ? prep_unkey(kk[u]) : kInf;
 #pragma unroll
             for (int r = K - 1; r >= 1; --r) lst[r] = fminf(lst[r], fmaxf(lst[r - 1], x));   // sorted insertion, branch-free
@@ -973,7 +973,10 @@ __global__ void __launch_bounds__(kThreads, 3) knn_prep_kernel(const PrepArgs A)
     for (int q = threadIdx.x; q < A.s; q += kThreads) {
         // list lengths 16 / 40 / 64 cover k+1 <= 64; the launch bound (3 CTAs per SM, what the bound pass wants) keeps
         // the kernel at <= 85 registers, so only the 64-entry variant (k >= 40) spills part of its list to local memory
-        const float worst = A.kp1 <= 16 ? prep_kth_smallest<16>(A.chunkkey, A.chunks, A.s, q, A.kp1)
+        // (k = 10, the reference's default: a 12-entry list and two batches of 24 slots -- the pass is ALU-bound, 2 ops
+        // per list entry and slot at half rate, and sits on the critical path of small problems and of every multi-GPU step)
+        const float worst = A.kp1 <= 12 ? prep_kth_smallest<12, 24>(A.chunkkey, A.chunks, A.s, q, A.kp1)
+                          : A.kp1 <= 16 ? prep_kth_smallest<16>(A.chunkkey, A.chunks, A.s, q, A.kp1)
                           : A.kp1 <= 40 ? prep_kth_smallest<40>(A.chunkkey, A.chunks, A.s, q, A.kp1)
                                         : prep_kth_smallest<64>(A.chunkkey, A.chunks, A.s, q, A.kp1);
         const float4 qv = (A.qmid_in != nullptr || (int)blockIdx.x < A.g) ? s_q[q] : make_float4(0.f, 0.f, 0.f, 0.f);

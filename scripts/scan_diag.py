@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """Where does the FIXED cost of a knn_scan_kernel launch go?  (C1: 27 candidate blocks take 20 us.)
 
-Needs the diagnostic build of the library (-DGEM_SCAN_DIAG -> graphem_rapids_b200/libgraphem_b200_diag.so, see
-scripts/gpu_run_diag.sh): thread 0 of every scan CTA records %globaltimer at the kernel's phase boundaries; this script
+Uses the diagnostic build of the library (-DGEM_SCAN_DIAG=1 -> graphem_rapids_b200/libgraphem_b200_diag.so, built on
+demand by graphem_rapids_b200.build.build_diag()): thread 0 of every scan CTA records %globaltimer at the kernel's phase boundaries; this script
 replays the captured iteration of several workloads and prints, per phase, the mean / max over CTAs.
 usage: scan_diag.py [lib] [workload ...]"""
 import ctypes
@@ -16,7 +16,10 @@ import torch                # noqa: E402
 
 import graphem_rapids_b200.build as _b      # noqa: E402
 
-LIBP = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "graphem_rapids_b200", "libgraphem_b200_diag.so")
+LIBP = sys.argv[1] if len(sys.argv) > 1 else _b.DIAG_LIB
+if not os.path.exists(LIBP) or os.path.getmtime(LIBP) < os.path.getmtime(_b.SRC):
+    assert os.path.abspath(LIBP) == os.path.abspath(_b.DIAG_LIB), f"{LIBP} is missing or older than the source"
+    _b.build_diag()
 _b.LIB = LIBP
 _b.needs_build = lambda: False
 import bench                                 # noqa: E402
