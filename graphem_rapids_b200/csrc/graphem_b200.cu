@@ -629,13 +629,14 @@ __global__ void __launch_bounds__(kThreads) knn_exact_kernel(const float *__rest
 }
 
 // ---- fast path ------------------------------------------------------------------------------
-// phase 1  knn_bound_kernel    : per (CTA, query) minimum exact d2 over the CTA's first tiles
-// phase 1b knn_threshold_kernel: tau_q = (k+1)-th smallest CTA minimum -> a valid upper bound of the
-//                                (k+1)-th neighbour distance; theta_q = conservative filter threshold
-// phase 2  knn_scan_kernel     : all pairs, d FFMA + 1 FSETP each; the rare passes are re-checked in
-//                                the exact cdist chain and inserted into a per-CTA top-(k+1) list in
-//                                shared memory whose worst key tightens the filter (bounded work even
-//                                when the bound is poor or thousands of distances tie at zero)
+// phase 1  knn_prep_kernel     : ONE launch -- sample, query midpoints, per (CTA, query) minimum of a 3-FMA upper
+//                                bound of the chain over an evenly spaced candidate sample, line-graph bound,
+//                                tau_q = (k+1)-th smallest slot minimum -> a valid upper bound of the (k+1)-th
+//                                neighbour distance, theta_q = conservative filter threshold, coefficient bank
+// phase 2  knn_scan_kernel     : all pairs, d FFMA + 1/3 min + 1/3 compare each; the rare passes are queued per
+//                                warp, re-checked 32 wide in the exact cdist chain and inserted into a per-CTA
+//                                top-(k+1) list in shared memory whose worst key tightens the filter (bounded
+//                                work even when the bound is poor or thousands of distances tie at zero)
 // phase 3  knn_select_kernel   : exact top-(k+1) by (distance, index) among <= G*(k+1) survivors
 constexpr int kQ = 8;                       // bound pass: queries per lane -> 256 queries per warp pass
 constexpr int kQB = 32 * kQ;                // query block (queries per scan CTA)
