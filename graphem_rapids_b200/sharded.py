@@ -576,7 +576,7 @@ class ShardedGraphEmbedder(GraphEmbedderPyTorch):
         self.last_sampled_indices = self._engine.samp
         self.last_knn_indices = self._engine.knn_idx[:, 1:]
 
-    _GRAPH_UNROLL = 4          # even: an unrolled graph starts at parity 0 and ends there
+    _GRAPH_UNROLL = 4          # even: an unrolled graph starts at parity 0 and ends there (8: same time on 2 GPUs, measured)
 
     def _capture(self, parity, count: int = 1):
         """Capture `count` whole sharded iterations starting at this parity -- kernels on both streams, peer stores and
