@@ -52,6 +52,24 @@ def test_committed_bench_line_matches_contract(name, line):
             assert line["cpu_baseline"]["kind"] in ("port", "reference")
 
 
+def test_timing_rule_is_a_function_of_the_workload():
+    """`config.l2` names the timing rule (L2 flushed before every step, or inputs larger than L2 and K iterations back
+    to back) from the workload alone, so both arms print the same `config`; a line timed back to back also carries
+    the flushed single-iteration figure."""
+    sys.path.insert(0, ROOT)
+    import bench
+    c3, c2 = bench.WORKLOADS["c3"], bench.WORKLOADS["c2"]
+    assert bench.iteration_bytes(c3, 1_000_000, 3_999_789) == pytest.approx(212e6, rel=0.01)
+    assert bench.back_to_back(c3, 1_000_000, 3_999_789) and not bench.back_to_back(c2, 100_000, 399_984)
+    assert "NOT flushed" in bench.workload_config(c3, 1_000_000, 3_999_789)["l2"]
+    assert "flushed before every timed step" in bench.workload_config(c2, 100_000, 399_984)["l2"]
+    for name, line in _lines():
+        if "NOT flushed" in line["config"].get("l2", ""):
+            fl = line["flushed_single_replays"]
+            assert fl is not None and fl["ms_per_step"] > 0, name
+            assert line["ms_per_step"] <= 1.05 * fl["ms_per_step"], name      # launch latency of one graph per iteration
+
+
 def test_reference_arm_runs_on_host_cores():
     """`bench.py --impl reference`: one JSON line, impl = reference, e2e repeats the line's own value with zero
     transfer bytes, cpu_baseline describes the run."""
